@@ -1,0 +1,230 @@
+"""carnd-mpc-project_b200 -- B200-native batched nonlinear-MPC solve (host-side Python binding).
+
+The product is ``libmpc_b200.so`` (C-ABI in ``include/mpc_b200.h`` over hand-written sm_100a
+kernels in ``csrc/``).  This module is a thin ctypes view of that C-ABI for tests, ``bench.py`` and
+multi-GPU orchestration; PyTorch is used only for device memory, streams and torch.distributed.
+
+There is NO CPU fallback: importing works without a GPU (so the symbol table can be checked), but
+every compute call raises ``MpcError`` unless the CUDA library loaded and a device is present.
+
+Boundary mirrored: ``MPC::solve`` (/root/reference/src/control/MPC.cpp:183-325) and ``Config::load``
+(/root/reference/src/utils/Config.cpp:31-87).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+NCOEF, NTAB, NWEIGHTS, NMAX = 5, 16, 12, 32
+
+STATUS_SUCCESS = 1
+STATUS_NAMES = {0: "not_defined", 1: "success", 2: "maxiter_exceeded", 3: "stop_at_tiny_step",
+                4: "stop_at_acceptable_point", 5: "local_infeasibility", 9: "restoration_failure",
+                10: "error_in_step_computation", 11: "invalid_number_detected", 13: "internal_error"}
+
+EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json", "mpc_create",
+           "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
+           "mpc_launch_count", "mpc_last_error", "mpc_version"]
+
+
+class MpcError(RuntimeError):
+    pass
+
+
+class MpcConfig(C.Structure):
+    """``mpc_config`` of include/mpc_b200.h (field order must match)."""
+    _fields_ = [
+        ("N", C.c_int), ("n_steers", C.c_int), ("n_steer_speeds", C.c_int), ("max_iter", C.c_int),
+        ("dt", C.c_double), ("Lf", C.c_double), ("cte_panic", C.c_double), ("epsi_panic", C.c_double),
+        ("max_speed", C.c_double), ("max_steering", C.c_double), ("max_accel", C.c_double),
+        ("max_decel", C.c_double), ("weights", C.c_double * NWEIGHTS), ("steers", C.c_double * NTAB),
+        ("steer_speeds", C.c_double * NTAB), ("tol", C.c_double),
+        ("max_fit_order", C.c_int), ("latency_ms", C.c_int), ("max_fit_error", C.c_double),
+        ("lookahead", C.c_double), ("ipopt_timeout", C.c_double), ("steer_adjust_thresh", C.c_double),
+        ("steer_adjust_ratio", C.c_double), ("n_yaw_changes", C.c_int), ("n_yaw_change_speeds", C.c_int),
+        ("yaw_changes", C.c_double * NTAB), ("yaw_change_speeds", C.c_double * NTAB),
+    ]
+
+    def as_dict(self):
+        """Same keys as oracle.pyoracle.load_config_dict (SI units)."""
+        return {
+            "N": self.N, "dt": self.dt, "Lf": self.Lf, "cte_panic": self.cte_panic,
+            "epsi_panic": self.epsi_panic, "max_speed": self.max_speed, "max_steering": self.max_steering,
+            "max_accel": self.max_accel, "max_decel": self.max_decel, "weights": list(self.weights),
+            "steers": list(self.steers[: self.n_steers]),
+            "steer_speeds": list(self.steer_speeds[: self.n_steer_speeds]),
+            "max_fit_order": self.max_fit_order, "max_fit_error": self.max_fit_error,
+            "latency": self.latency_ms, "lookahead": self.lookahead, "ipopt_timeout": self.ipopt_timeout,
+            "steer_adjust_thresh": self.steer_adjust_thresh, "steer_adjust_ratio": self.steer_adjust_ratio,
+            "yaw_changes": list(self.yaw_changes[: self.n_yaw_changes]),
+            "yaw_change_speeds": list(self.yaw_change_speeds[: self.n_yaw_change_speeds]),
+        }
+
+
+def build(verbose=False):
+    """Compile csrc/ for sm_100a with nvcc into libmpc_b200.so (in-tree)."""
+    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise MpcError("nvcc build of libmpc_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library; raises loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpcError("libmpc_b200.so is missing (%s): run __graft_entry__.build() -- there is no "
+                       "CPU fallback for the MPC solve" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    cfgp = C.POINTER(MpcConfig)
+    L.mpc_config_defaults.argtypes = [cfgp]
+    L.mpc_config_load_json.argtypes = [C.c_char_p, cfgp]
+    L.mpc_config_parse_json.argtypes = [C.c_char_p, cfgp]
+    L.mpc_create.argtypes = [cfgp, C.c_int, C.POINTER(vp)]
+    L.mpc_destroy.argtypes = [vp]
+    L.mpc_destroy.restype = None
+    L.mpc_set_config.argtypes = [vp, cfgp]
+    L.mpc_solve_batch.argtypes = [vp, C.c_int] + [vp] * 13 + [vp]
+    L.mpc_solve_batch_host.argtypes = [vp, C.c_int] + [vp] * 13
+    L.mpc_solve_one.argtypes = [vp, dp, dp, C.c_double, C.c_double, dp, dp, dp, ip, ip]
+    L.mpc_launch_count.argtypes = [vp]
+    L.mpc_launch_count.restype = C.c_longlong
+    L.mpc_last_error.restype = C.c_char_p
+    L.mpc_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        names = {-1: "MPC_EINVAL", -2: "MPC_ENODEV", -3: "MPC_ECUDA", -4: "MPC_ENOMEM", -5: "MPC_EIO",
+                 -6: "MPC_EPARSE"}
+        raise MpcError("%s failed: %s (%d) %s" % (what, names.get(rc, "?"), rc,
+                                                  lib().mpc_last_error().decode()))
+
+
+def config_defaults():
+    cfg = MpcConfig()
+    _check(lib().mpc_config_defaults(C.byref(cfg)), "mpc_config_defaults")
+    return cfg
+
+
+def config_from_json_file(path):
+    """Config::load(path)."""
+    cfg = MpcConfig()
+    _check(lib().mpc_config_load_json(path.encode(), C.byref(cfg)), "mpc_config_load_json")
+    return cfg
+
+
+def config_from_json_text(text):
+    cfg = MpcConfig()
+    _check(lib().mpc_config_parse_json(text.encode(), C.byref(cfg)), "mpc_config_parse_json")
+    return cfg
+
+
+def _ptr(t):
+    """Device/host pointer of a torch tensor, numpy array or None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Solver:
+    """One ``mpc_handle``: the batched replacement of an ``MPC`` object (MPC.cpp:160-325)."""
+
+    def __init__(self, cfg, device=0):
+        self.cfg = cfg
+        self.device = device
+        h = C.c_void_p()
+        _check(lib().mpc_create(C.byref(cfg), device, C.byref(h)), "mpc_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_config(self, cfg):
+        _check(lib().mpc_set_config(self._h, C.byref(cfg)), "mpc_set_config")
+        self.cfg = cfg
+
+    @property
+    def launches(self):
+        return int(lib().mpc_launch_count(self._h))
+
+    def solve_batch_device(self, B, state, coeffs, yaw_lo, yaw_hi, result, traj_x=None, traj_y=None,
+                           full=None, status=None, iters=None, weights=None, N_per=None, dt_per=None,
+                           stream=None):
+        """Asynchronous solve; every array is a DEVICE tensor in the [k][B] layout of the header.
+
+        ``stream`` is a raw cudaStream_t (int); None = torch's current stream."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        _check(lib().mpc_solve_batch(self._h, B, _ptr(state), _ptr(coeffs), _ptr(yaw_lo), _ptr(yaw_hi),
+                                     _ptr(weights), _ptr(N_per), _ptr(dt_per), _ptr(result), _ptr(traj_x),
+                                     _ptr(traj_y), _ptr(full), _ptr(status), _ptr(iters), stream),
+               "mpc_solve_batch")
+
+    def solve_batch_host(self, state, coeffs, yaw_lo, yaw_hi, weights=None, N_per=None, dt_per=None,
+                         want_traj=True, want_full=False):
+        """Host numpy in ([B,6], [B,5], [B], [B]) -> dict of host numpy outputs ([B,...])."""
+        B = state.shape[0]
+        N = self.cfg.N
+        st = np.ascontiguousarray(np.asarray(state, dtype=np.float64).T)
+        co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64).T)
+        yl = np.ascontiguousarray(yaw_lo, dtype=np.float64)
+        yh = np.ascontiguousarray(yaw_hi, dtype=np.float64)
+        w = None if weights is None else np.ascontiguousarray(np.asarray(weights, dtype=np.float64).T)
+        npp = None if N_per is None else np.ascontiguousarray(N_per, dtype=np.int32)
+        dtp = None if dt_per is None else np.ascontiguousarray(dt_per, dtype=np.float64)
+        res = np.zeros((9, B))
+        tx = np.zeros((N, B)) if want_traj else None
+        ty = np.zeros((N, B)) if want_traj else None
+        full = np.zeros((8 * N - 2, B)) if want_full else None
+        status = np.zeros(B, dtype=np.int32)
+        iters = np.zeros(B, dtype=np.int32)
+        _check(lib().mpc_solve_batch_host(self._h, B, _ptr(st), _ptr(co), _ptr(yl), _ptr(yh), _ptr(w),
+                                          _ptr(npp), _ptr(dtp), _ptr(res), _ptr(tx), _ptr(ty), _ptr(full),
+                                          _ptr(status), _ptr(iters)), "mpc_solve_batch_host")
+        out = {"result": res.T.copy(), "status": status, "iters": iters}
+        if want_traj:
+            out["traj_x"], out["traj_y"] = tx.T.copy(), ty.T.copy()
+        if want_full:
+            out["full"] = full.T.copy()
+        return out
+
+    def solve_one(self, state, coeffs, yaw_lo, yaw_hi):
+        N = self.cfg.N
+        st = np.ascontiguousarray(state, dtype=np.float64)
+        co = np.zeros(NCOEF)
+        co[: len(coeffs)] = coeffs
+        res, tx, ty = np.zeros(9), np.zeros(N), np.zeros(N)
+        status, iters = C.c_int(0), C.c_int(0)
+        dp = C.POINTER(C.c_double)
+        _check(lib().mpc_solve_one(self._h, st.ctypes.data_as(dp), co.ctypes.data_as(dp), float(yaw_lo),
+                                   float(yaw_hi), res.ctypes.data_as(dp), tx.ctypes.data_as(dp),
+                                   ty.ctypes.data_as(dp), C.byref(status), C.byref(iters)), "mpc_solve_one")
+        return {"result": res, "traj_x": tx, "traj_y": ty, "status": status.value, "iters": iters.value}

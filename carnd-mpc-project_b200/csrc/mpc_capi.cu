@@ -1,0 +1,389 @@
+// mpc_capi.cu -- the C-ABI of include/mpc_b200.h on top of the sm_100a kernel.
+//
+// Boundary it replaces: MPC::MPC / MPC::solve (/root/reference/src/control/MPC.cpp:160-325) and
+// Config::load (/root/reference/src/utils/Config.cpp:31-87).  No CPU fallback: every compute entry
+// point fails with MPC_ENODEV / MPC_ECUDA when the device or the launch is unavailable.
+#include "../../include/mpc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "mpc_kernel.cuh"
+
+using namespace mpcb200;
+
+static thread_local char g_err[512] = "";
+
+static int cuda_fail(cudaError_t e, const char *what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return MPC_ECUDA;
+}
+#define CK(call)                                      \
+  do {                                                \
+    cudaError_t e__ = (call);                         \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct mpc_handle {
+  mpc_config cfg;
+  int device;
+  int sm_count;
+  int *d_counter;
+  long long launches;
+  // staging buffers for the host-pointer entry points (grown on demand)
+  double *d_in, *d_out;
+  int *d_iout;
+  double *h_pin;       // pinned host mirror for mpc_solve_one
+  size_t cap_B;
+  int cap_N;
+  bool cap_w;
+  cudaStream_t stream;
+};
+
+// ------------------------------------------------------------------------------------------------
+// minimal JSON reader (objects, arrays, numbers, strings, true/false/null): enough for the
+// config-*.json files Config::load reads (Config.cpp:34-35)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct JVal {
+  enum { NUL, NUM, STR, ARR, OBJ, BOOL } t = NUL;
+  double num = 0;
+  std::string str;
+  std::vector<JVal> arr;
+  std::map<std::string, JVal> obj;
+};
+struct JParser {
+  const char *p;
+  bool ok = true;
+  explicit JParser(const char *s) : p(s) {}
+  void ws() { while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') p++; }
+  bool lit(const char *s) { size_t n = strlen(s); if (strncmp(p, s, n) == 0) { p += n; return true; } return false; }
+  std::string str() {
+    std::string out;
+    if (*p != '"') { ok = false; return out; }
+    p++;
+    while (*p && *p != '"') {
+      if (*p == '\\' && p[1]) { p++; char c = *p; out += (c == 'n' ? '\n' : c == 't' ? '\t' : c); }
+      else out += *p;
+      p++;
+    }
+    if (*p != '"') ok = false; else p++;
+    return out;
+  }
+  JVal val() {
+    JVal v;
+    ws();
+    if (*p == '{') {
+      v.t = JVal::OBJ; p++; ws();
+      if (*p == '}') { p++; return v; }
+      while (ok) {
+        ws(); std::string k = str(); ws();
+        if (*p != ':') { ok = false; break; }
+        p++;
+        v.obj[k] = val(); ws();
+        if (*p == ',') { p++; continue; }
+        if (*p == '}') { p++; break; }
+        ok = false;
+      }
+    } else if (*p == '[') {
+      v.t = JVal::ARR; p++; ws();
+      if (*p == ']') { p++; return v; }
+      while (ok) {
+        v.arr.push_back(val()); ws();
+        if (*p == ',') { p++; continue; }
+        if (*p == ']') { p++; break; }
+        ok = false;
+      }
+    } else if (*p == '"') {
+      v.t = JVal::STR; v.str = str();
+    } else if (lit("true")) { v.t = JVal::BOOL; v.num = 1;
+    } else if (lit("false")) { v.t = JVal::BOOL; v.num = 0;
+    } else if (lit("null")) { v.t = JVal::NUL;
+    } else {
+      char *end = nullptr;
+      v.num = strtod(p, &end);
+      if (end == p) ok = false; else { v.t = JVal::NUM; p = end; }
+    }
+    return v;
+  }
+};
+inline double mph2mps(double mph) { return mph * 1609.34 / 3600.0; }   // utils.h:11-13
+inline double deg2rad(double x) { return x * M_PI / 180; }             // utils.h:69
+}  // namespace
+
+extern "C" int mpc_config_defaults(mpc_config *c) {
+  if (!c) return MPC_EINVAL;
+  memset(c, 0, sizeof(*c));
+  // Config.cpp:5-29
+  c->N = 25;
+  c->max_fit_order = 4;
+  c->max_fit_error = 0.5;
+  c->latency_ms = 100;
+  c->lookahead = 0;
+  c->ipopt_timeout = 0.5;
+  c->dt = 0.025;
+  c->max_steering = deg2rad(25.0);
+  c->max_accel = mph2mps(8);
+  c->max_decel = mph2mps(-20);
+  c->max_speed = mph2mps(100);
+  c->Lf = 2.67;
+  c->epsi_panic = 1;
+  c->cte_panic = 0.6;
+  c->steer_adjust_thresh = 0.6;
+  c->steer_adjust_ratio = 0.025;
+  const double w[8] = {100, 100, 1, 1, 1, 5000, 1, 1000};
+  for (int i = 0; i < 8; i++) c->weights[i] = w[i];
+  c->n_steers = 3;
+  c->steers[0] = 0.1; c->steers[1] = 0.2; c->steers[2] = 0.3;
+  c->n_steer_speeds = 4;
+  c->steer_speeds[0] = mph2mps(80); c->steer_speeds[1] = mph2mps(65);
+  c->steer_speeds[2] = mph2mps(30); c->steer_speeds[3] = mph2mps(25);
+  c->max_iter = 3000;
+  c->tol = 1e-8;
+  return MPC_OK;
+}
+
+extern "C" int mpc_config_parse_json(const char *text, mpc_config *c) {
+  if (!text || !c) return MPC_EINVAL;
+  JParser jp(text);
+  JVal js = jp.val();
+  if (!jp.ok || js.t != JVal::OBJ) return MPC_EPARSE;
+  auto has = [&](const char *k) { return js.obj.count(k) && js.obj[k].t != JVal::NUL; };
+  auto num = [&](const char *k, double &out) { if (!has(k) || js.obj[k].t != JVal::NUM) return false; out = js.obj[k].num; return true; };
+  auto arr = [&](const char *k, std::vector<double> &out) {
+    if (!has(k) || js.obj[k].t != JVal::ARR) return false;
+    out.clear();
+    for (auto &e : js.obj[k].arr) { if (e.t != JVal::NUM) return false; out.push_back(e.num); }
+    return true;
+  };
+  mpc_config_defaults(c);
+  double v;
+  // same keys, same order and conversions as Config.cpp:39-86
+  if (!num("N", v)) return MPC_EPARSE; c->N = (int)v;
+  if (!num("dt", c->dt)) return MPC_EPARSE;
+  if (!num("max acceleration", v)) return MPC_EPARSE; c->max_accel = mph2mps(v);
+  if (!num("max deceleration", v)) return MPC_EPARSE; c->max_decel = mph2mps(v);
+  if (!num("max steering", v)) return MPC_EPARSE; c->max_steering = deg2rad(v);
+  if (!num("max speed", v)) return MPC_EPARSE; c->max_speed = mph2mps(v);
+  const double speed_scale = c->max_speed / mph2mps(100.0);
+  if (!num("latency", v)) return MPC_EPARSE; c->latency_ms = (int)v;
+  c->lookahead = c->latency_ms * 1.0E-3;
+  if (!num("max polynomial fitting order", v)) return MPC_EPARSE; c->max_fit_order = (int)v;
+  if (!num("max polynomial fitting error", c->max_fit_error)) return MPC_EPARSE;
+  if (!num("ipopt timeout", c->ipopt_timeout)) return MPC_EPARSE;
+  if (!num("Lf", c->Lf)) return MPC_EPARSE;
+  if (!num("epsi panic", c->epsi_panic)) return MPC_EPARSE;
+  if (!num("cte panic", c->cte_panic)) return MPC_EPARSE;
+  if (!num("steer adjustment threshold", c->steer_adjust_thresh)) return MPC_EPARSE;
+  if (!num("steer adjustment ratio", v)) return MPC_EPARSE;
+  c->steer_adjust_ratio = v < 0.0 ? 0.0 : (v > 0.1 ? 0.1 : v);
+  std::vector<double> a;
+  if (!arr("weights", a) || a.size() <= 11) return MPC_EPARSE;   // assert(w.size() > WEIGHT_LARGE_CTE)
+  for (int i = 0; i < MPC_NWEIGHTS; i++) c->weights[i] = a[i];
+  if (!arr("steers", a) || a.size() > MPC_NTAB) return MPC_EPARSE;
+  c->n_steers = (int)a.size();
+  for (size_t i = 0; i < a.size(); i++) c->steers[i] = a[i];
+  auto conv = [&](double s) { return speed_scale <= 1 ? std::fmin(mph2mps(s), c->max_speed) : mph2mps(s) * speed_scale; };
+  if (!arr("steer speeds", a) || a.empty() || a.size() > MPC_NTAB) return MPC_EPARSE;
+  c->n_steer_speeds = (int)a.size();
+  for (size_t i = 0; i < a.size(); i++) c->steer_speeds[i] = conv(a[i]);
+  if (!arr("yaw changes", a) || a.size() > MPC_NTAB) return MPC_EPARSE;
+  c->n_yaw_changes = (int)a.size();
+  for (size_t i = 0; i < a.size(); i++) c->yaw_changes[i] = a[i];
+  if (!arr("yaw change speeds", a) || a.size() > MPC_NTAB) return MPC_EPARSE;
+  c->n_yaw_change_speeds = (int)a.size();
+  for (size_t i = 0; i < a.size(); i++) c->yaw_change_speeds[i] = conv(a[i]);
+  return MPC_OK;
+}
+
+extern "C" int mpc_config_load_json(const char *path, mpc_config *c) {
+  if (!path || !c) return MPC_EINVAL;
+  FILE *f = fopen(path, "rb");
+  if (!f) return MPC_EIO;
+  std::string text;
+  char buf[4096];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+  fclose(f);
+  return mpc_config_parse_json(text.c_str(), c);
+}
+
+static int check_config(const mpc_config *c) {
+  if (!c) return MPC_EINVAL;
+  if (c->N < 2 || c->N > MPC_NMAX) return MPC_EINVAL;
+  if (c->n_steers < 0 || c->n_steers > MPC_NTAB || c->n_steer_speeds < 1 || c->n_steer_speeds > MPC_NTAB) return MPC_EINVAL;
+  if (!(c->dt > 0) || !(c->Lf > 0) || c->max_iter < 0 || !(c->tol > 0)) return MPC_EINVAL;
+  return MPC_OK;
+}
+
+extern "C" int mpc_create(const mpc_config *cfg, int device, mpc_handle **out) {
+  if (!out) return MPC_EINVAL;
+  *out = nullptr;
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return MPC_ENODEV;
+  }
+  if (device < 0 || device >= ndev) return MPC_ENODEV;
+  CK(cudaSetDevice(device));
+  mpc_handle *h = new (std::nothrow) mpc_handle();
+  if (!h) return MPC_ENOMEM;
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  CK(cudaMalloc(&h->d_counter, sizeof(int)));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  *out = h;
+  return MPC_OK;
+}
+
+extern "C" void mpc_destroy(mpc_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_counter);
+  cudaFree(h->d_in);
+  cudaFree(h->d_out);
+  cudaFree(h->d_iout);
+  cudaFreeHost(h->h_pin);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int mpc_set_config(mpc_handle *h, const mpc_config *cfg) {
+  if (!h) return MPC_EINVAL;
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  h->cfg = *cfg;
+  return MPC_OK;
+}
+
+template <int G>
+static int launch(mpc_handle *h, KParams &kp, cudaStream_t st) {
+  const int threads = 128;
+  const int groups = threads / G;
+  kp.ws_stride = workspace_doubles(kp.Nmax);
+  const size_t smem = (size_t)groups * kp.ws_stride * sizeof(double);
+  static thread_local int cached_dev = -1;
+  static thread_local size_t cached_smem = 0;
+  if (cached_dev != h->device || cached_smem < smem) {
+    CK(cudaFuncSetAttribute(mpc_ipm_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cached_dev = h->device;
+    cached_smem = smem;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_ipm_kernel<G>, threads, smem));
+  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "kernel does not fit on an SM (smem %zu)", smem); return MPC_ECUDA; }
+  long long want = ((long long)kp.B + groups - 1) / groups;
+  long long grid = (long long)h->sm_count * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
+  mpc_ipm_kernel<G><<<(unsigned)grid, threads, smem, st>>>(kp);
+  CK(cudaGetLastError());
+  h->launches++;
+  return MPC_OK;
+}
+
+extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const double *coeffs,
+                               const double *yaw_lo, const double *yaw_hi, const double *weights,
+                               const int *N_per, const double *dt_per, double *result, double *traj_x,
+                               double *traj_y, double *full, int *status, int *iters, void *cuda_stream) {
+  if (!h || B < 0 || !state || !coeffs || !yaw_lo || !yaw_hi || !result) return MPC_EINVAL;
+  if (B == 0) return MPC_OK;
+  CK(cudaSetDevice(h->device));
+  const mpc_config &c = h->cfg;
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.B = B; kp.Nmax = c.N; kp.max_iter = c.max_iter; kp.n_steers = c.n_steers; kp.n_steer_speeds = c.n_steer_speeds;
+  kp.dt = c.dt; kp.Lf = c.Lf; kp.cte_panic = c.cte_panic; kp.epsi_panic = c.epsi_panic;
+  kp.max_speed = c.max_speed; kp.max_steering = c.max_steering; kp.max_accel = c.max_accel; kp.max_decel = c.max_decel;
+  kp.tol = c.tol;
+  memcpy(kp.weights, c.weights, sizeof(kp.weights));
+  memcpy(kp.steers, c.steers, sizeof(kp.steers));
+  memcpy(kp.steer_speeds, c.steer_speeds, sizeof(kp.steer_speeds));
+  kp.state = state; kp.coeffs = coeffs; kp.yaw_lo = yaw_lo; kp.yaw_hi = yaw_hi; kp.weights_pp = weights;
+  kp.N_pp = N_per; kp.dt_pp = dt_per;
+  kp.result = result; kp.traj_x = traj_x; kp.traj_y = traj_y; kp.full = full; kp.status = status; kp.iters = iters;
+  kp.counter = h->d_counter;
+  return launch<32>(h, kp, (cudaStream_t)cuda_stream);
+}
+
+// ---- host-pointer entry points -------------------------------------------------------------------
+static int ensure_staging(mpc_handle *h, size_t B, int N, bool with_w) {
+  if (h->d_in && h->cap_B >= B && h->cap_N >= N && (h->cap_w || !with_w)) return MPC_OK;
+  cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_iout); cudaFreeHost(h->h_pin);
+  h->d_in = h->d_out = nullptr; h->d_iout = nullptr; h->h_pin = nullptr;
+  size_t cap = B < 256 ? 256 : B;
+  size_t nin = (6 + 5 + 2 + 12 + 1) * cap;            // state, coeffs, yaw, weights, dt
+  size_t nout = (9 + 2 * (size_t)N + (8 * (size_t)N - 2)) * cap;
+  CK(cudaMalloc(&h->d_in, nin * sizeof(double)));
+  CK(cudaMalloc(&h->d_out, nout * sizeof(double)));
+  CK(cudaMalloc(&h->d_iout, 3 * cap * sizeof(int)));
+  CK(cudaMallocHost(&h->h_pin, 64 * sizeof(double) + (9 + 2 * (size_t)N) * sizeof(double)));
+  h->cap_B = cap; h->cap_N = N; h->cap_w = true;
+  return MPC_OK;
+}
+
+extern "C" int mpc_solve_batch_host(mpc_handle *h, int B, const double *state, const double *coeffs,
+                                    const double *yaw_lo, const double *yaw_hi, const double *weights,
+                                    const int *N_per, const double *dt_per, double *result, double *traj_x,
+                                    double *traj_y, double *full, int *status, int *iters) {
+  if (!h || B < 0 || !state || !coeffs || !yaw_lo || !yaw_hi || !result) return MPC_EINVAL;
+  if (B == 0) return MPC_OK;
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.N;
+  int rc = ensure_staging(h, (size_t)B, N, weights != nullptr);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  const size_t cap = h->cap_B, sB = (size_t)B * sizeof(double);
+  double *d_state = h->d_in, *d_coef = d_state + 6 * cap, *d_ylo = d_coef + 5 * cap, *d_yhi = d_ylo + cap;
+  double *d_w = d_yhi + cap, *d_dt = d_w + 12 * cap;
+  double *d_res = h->d_out, *d_tx = d_res + 9 * cap, *d_ty = d_tx + (size_t)N * cap, *d_full = d_ty + (size_t)N * cap;
+  int *d_status = h->d_iout, *d_iters = d_status + cap, *d_N = d_iters + cap;
+  // inputs are [k][B] with stride B on the host and on the device
+  CK(cudaMemcpyAsync(d_state, state, 6 * sB, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_coef, coeffs, 5 * sB, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_ylo, yaw_lo, sB, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_yhi, yaw_hi, sB, cudaMemcpyHostToDevice, st));
+  if (weights) CK(cudaMemcpyAsync(d_w, weights, 12 * sB, cudaMemcpyHostToDevice, st));
+  if (dt_per) CK(cudaMemcpyAsync(d_dt, dt_per, sB, cudaMemcpyHostToDevice, st));
+  if (N_per) CK(cudaMemcpyAsync(d_N, N_per, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
+  rc = mpc_solve_batch(h, B, d_state, d_coef, d_ylo, d_yhi, weights ? d_w : nullptr, N_per ? d_N : nullptr,
+                       dt_per ? d_dt : nullptr, d_res, traj_x ? d_tx : nullptr, traj_y ? d_ty : nullptr,
+                       full ? d_full : nullptr, d_status, d_iters, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(result, d_res, 9 * sB, cudaMemcpyDeviceToHost, st));
+  if (traj_x) CK(cudaMemcpyAsync(traj_x, d_tx, (size_t)N * sB, cudaMemcpyDeviceToHost, st));
+  if (traj_y) CK(cudaMemcpyAsync(traj_y, d_ty, (size_t)N * sB, cudaMemcpyDeviceToHost, st));
+  if (full) CK(cudaMemcpyAsync(full, d_full, (8 * (size_t)N - 2) * sB, cudaMemcpyDeviceToHost, st));
+  if (status) CK(cudaMemcpyAsync(status, d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (iters) CK(cudaMemcpyAsync(iters, d_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPC_OK;
+}
+
+extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs, double yaw_lo,
+                             double yaw_hi, double *result, double *traj_x, double *traj_y, int *status,
+                             int *iters) {
+  if (!h || !state || !coeffs || !result) return MPC_EINVAL;
+  return mpc_solve_batch_host(h, 1, state, coeffs, &yaw_lo, &yaw_hi, nullptr, nullptr, nullptr, result, traj_x,
+                              traj_y, nullptr, status, iters);
+}
+
+extern "C" long long mpc_launch_count(const mpc_handle *h) { return h ? h->launches : 0; }
+extern "C" const char *mpc_last_error(void) { return g_err; }
+extern "C" const char *mpc_version(void) { return "mpc_b200 0.1 (sm_100a, fp64 interior point, one problem per warp)"; }

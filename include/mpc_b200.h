@@ -1,0 +1,150 @@
+/*
+ * mpc_b200.h -- C-ABI of the B200-native batched nonlinear-MPC solver.
+ *
+ * This is the drop-in boundary for the reference's one hot path,
+ *     std::vector<double> MPC::solve(VectorXd &state, double target_velocity,
+ *                                    vector<double>* x_trajectory, vector<double>* y_trajectory, double dir)
+ *     /root/reference/src/control/MPC.h:42-43, /root/reference/src/control/MPC.cpp:183-325
+ * (NLP assembly MPC.cpp:204-281, FG_eval MPC.cpp:50-154, CppAD::ipopt::solve call MPC.cpp:290-292,
+ * output unpacking MPC.cpp:306-324) and its hidden inputs: the fitted polynomial held in
+ * MPC::roadGeometry (MPC.h:26) and the Config:: statics (src/utils/Config.h:66-177).
+ *
+ * Plain pointers and sizes only; no exceptions cross the boundary; every entry point returns
+ * 0 on success or a negative MPC_E* code.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point returns MPC_ENODEV.
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_NCOEF 5        /* polynomial coefficients per problem, low -> high order, zero padded
+                              (Config::maxFitOrder = 5 => order <= 4, RoadGeometry.cpp:27-34) */
+#define MPC_NTAB 16        /* capacity of the steers / steer-speeds tables (9 in config-*.json) */
+#define MPC_NWEIGHTS 12    /* Config::weights, indices Config.h:14-61 */
+#define MPC_NMAX 32        /* maximum horizon N handled by the sm_100a kernel in this round */
+
+/* error codes */
+#define MPC_OK 0
+#define MPC_EINVAL (-1)    /* bad argument (NULL pointer, N out of range, B < 0 ...) */
+#define MPC_ENODEV (-2)    /* no CUDA device / device index out of range */
+#define MPC_ECUDA (-3)     /* CUDA runtime error; mpc_last_error() has the text */
+#define MPC_ENOMEM (-4)
+#define MPC_EIO (-5)       /* config file unreadable */
+#define MPC_EPARSE (-6)    /* config file is not the JSON Config::load expects */
+
+/* Per-problem solver status: the integers of CppAD::ipopt::solve_result<>::status_type that
+ * MPC.cpp:295-303 compares against / prints ("Ipopt failed with <int>"). */
+#define MPC_STATUS_NOT_DEFINED 0
+#define MPC_STATUS_SUCCESS 1
+#define MPC_STATUS_MAXITER_EXCEEDED 2
+#define MPC_STATUS_STOP_AT_TINY_STEP 3
+#define MPC_STATUS_STOP_AT_ACCEPTABLE_POINT 4
+#define MPC_STATUS_LOCAL_INFEASIBILITY 5
+#define MPC_STATUS_RESTORATION_FAILURE 9
+#define MPC_STATUS_ERROR_IN_STEP_COMPUTATION 10
+#define MPC_STATUS_INVALID_NUMBER_DETECTED 11
+#define MPC_STATUS_INTERNAL_ERROR 13
+
+/* The Config:: statics the hot path reads, AFTER Config::load's unit conversions
+ * (Config.cpp:39-86): SI units, radians.  POD, caller-owned, copied by mpc_create. */
+typedef struct mpc_config {
+  int N;                         /* Config::N      -- horizon length (2..MPC_NMAX) */
+  int n_steers;                  /* Config::steers.size() */
+  int n_steer_speeds;            /* Config::steerSpeeds.size() */
+  int max_iter;                  /* Ipopt max_iter; replaces the wall-clock cap max_cpu_time
+                                    (MPC.cpp:178), default 3000 */
+  double dt;                     /* Config::dt */
+  double Lf;                     /* Config::Lf */
+  double cte_panic;              /* Config::ctePanic */
+  double epsi_panic;             /* Config::epsiPanic */
+  double max_speed;              /* Config::maxSpeed          [m/s] */
+  double max_steering;           /* Config::maxSteering       [rad] */
+  double max_accel;              /* Config::maxAcceleration   [m/s^2] */
+  double max_decel;              /* Config::maxDeceleration   [m/s^2], negative */
+  double weights[MPC_NWEIGHTS];  /* Config::weights */
+  double steers[MPC_NTAB];       /* Config::steers            [rad] */
+  double steer_speeds[MPC_NTAB]; /* Config::steerSpeeds       [m/s] */
+  double tol;                    /* Ipopt tol, default 1e-8 */
+  /* ---- fields below are only used by MPC::run-level helpers (not by the NLP) ---- */
+  int max_fit_order;             /* Config::maxFitOrder */
+  int latency_ms;                /* Config::latency */
+  double max_fit_error;          /* Config::maxFitError */
+  double lookahead;              /* Config::lookahead [s] */
+  double ipopt_timeout;          /* Config::ipoptTimeout (kept for fidelity; not used) */
+  double steer_adjust_thresh;    /* Config::steerAdjustmentThresh */
+  double steer_adjust_ratio;     /* Config::steerAdjustmentRatio */
+  int n_yaw_changes;             /* Config::yawChanges.size() */
+  int n_yaw_change_speeds;       /* Config::yawChangeSpeeds.size() */
+  double yaw_changes[MPC_NTAB];
+  double yaw_change_speeds[MPC_NTAB];
+} mpc_config;
+
+typedef struct mpc_handle mpc_handle;
+
+/* Config.cpp:5-29 -- the compiled-in defaults of the Config statics (before any load). */
+int mpc_config_defaults(mpc_config *cfg);
+/* Config::load(fileName), Config.cpp:31-87 -- same JSON keys, same unit conversions. */
+int mpc_config_load_json(const char *path, mpc_config *cfg);
+/* same, from an in-memory JSON text */
+int mpc_config_parse_json(const char *text, mpc_config *cfg);
+
+/* Create a solver bound to CUDA device `device` (workspace, stream-ordered work queue counter).
+ * Replaces `MPC::MPC()` (MPC.cpp:160-179): the Ipopt option string becomes max_iter / tol. */
+int mpc_create(const mpc_config *cfg, int device, mpc_handle **out);
+void mpc_destroy(mpc_handle *h);
+/* replace the configuration of an existing handle (Config::load on a live controller) */
+int mpc_set_config(mpc_handle *h, const mpc_config *cfg);
+
+/*
+ * Solve B independent MPC problems.  ALL POINTERS ARE DEVICE POINTERS on the handle's device;
+ * the launch is asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).
+ *
+ * Inputs (struct-of-arrays, batch index fastest):
+ *   state   [6][B]  x, y, psi, v, cte, epsi                      (MPC.cpp:213-218)
+ *   coeffs  [5][B]  polynomial, low -> high, zero padded          (RoadGeometry::polynomial)
+ *   yaw_lo, yaw_hi [B]  Config::yawLow / yawHigh                  (MPC.cpp:229-232, 345-352)
+ *   weights [12][B] or NULL: per-problem Config::weights override (weight sweeps)
+ *   N_per   [B] or NULL: per-problem horizon (<= cfg.N); dt_per [B] or NULL: per-problem dt
+ * Outputs:
+ *   result  [9][B]  x1,y1,psi1,v1,cte1,epsi1,delta0,a0,cost       (MPC.cpp:322-324)
+ *   traj_x, traj_y [cfg.N][B] or NULL: predicted x_i, y_i, stage 0 included (MPC.cpp:306-311);
+ *                   rows >= the problem's N are left untouched
+ *   full    [8*cfg.N-2][B] or NULL: solution.x in the reference's layout (MPC.cpp:189-196),
+ *                   only valid when N_per is NULL
+ *   status  [B]     MPC_STATUS_* ; iters [B] interior-point iterations (either may be NULL)
+ */
+int mpc_solve_batch(mpc_handle *h, int B,
+                    const double *state, const double *coeffs,
+                    const double *yaw_lo, const double *yaw_hi,
+                    const double *weights, const int *N_per, const double *dt_per,
+                    double *result, double *traj_x, double *traj_y, double *full,
+                    int *status, int *iters, void *cuda_stream);
+
+/* Same contract with HOST pointers: copies inputs to the device, solves, copies the outputs
+ * back and synchronises.  This is the call the reference-facing C++ `MPC` shim uses. */
+int mpc_solve_batch_host(mpc_handle *h, int B,
+                         const double *state, const double *coeffs,
+                         const double *yaw_lo, const double *yaw_hi,
+                         const double *weights, const int *N_per, const double *dt_per,
+                         double *result, double *traj_x, double *traj_y, double *full,
+                         int *status, int *iters);
+
+/* One problem, host pointers: state[6], coeffs[5] -> result[9], traj_x/traj_y[N] (or NULL).
+ * What `MPC::solve` calls once per telemetry message. */
+int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs,
+                  double yaw_lo, double yaw_hi,
+                  double *result, double *traj_x, double *traj_y, int *status, int *iters);
+
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+long long mpc_launch_count(const mpc_handle *h);
+/* text of the last CUDA error seen by this thread's calls ("" if none) */
+const char *mpc_last_error(void);
+const char *mpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,26 @@
+"""Import shim: the package directory is named ``carnd-mpc-project_b200`` (not a Python identifier),
+so it is loaded here under the module name ``carnd_mpc_project_b200`` and re-exported.
+
+    import mpc_b200 as mpc          # mpc.Solver, mpc.config_from_json_text, mpc.workloads ...
+"""
+import importlib.util
+import os
+import sys
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+_PKG_DIR = os.path.join(_ROOT, "carnd-mpc-project_b200")
+_NAME = "carnd_mpc_project_b200"
+
+if _NAME not in sys.modules:
+    _spec = importlib.util.spec_from_file_location(
+        _NAME, os.path.join(_PKG_DIR, "__init__.py"), submodule_search_locations=[_PKG_DIR])
+    _mod = importlib.util.module_from_spec(_spec)
+    sys.modules[_NAME] = _mod
+    _spec.loader.exec_module(_mod)
+
+_pkg = sys.modules[_NAME]
+from carnd_mpc_project_b200 import *  # noqa: F401,F403,E402
+from carnd_mpc_project_b200 import (MpcConfig, MpcError, Solver, build, lib, LIB_PATH, EXPORTS,  # noqa: E402,F401
+                                    config_defaults, config_from_json_file, config_from_json_text,
+                                    STATUS_NAMES, STATUS_SUCCESS)
+import carnd_mpc_project_b200.workloads as workloads  # noqa: E402,F401
