@@ -29,7 +29,7 @@ STATUS_NAMES = {0: "not_defined", 1: "success", 2: "maxiter_exceeded", 3: "stop_
 
 EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json", "mpc_create",
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
-           "mpc_launch_count", "mpc_last_error", "mpc_version"]
+           "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak"]
 
 
 class MpcError(RuntimeError):
@@ -101,6 +101,7 @@ def lib():
     L.mpc_solve_batch.argtypes = [vp, C.c_int] + [vp] * 13 + [vp]
     L.mpc_solve_batch_host.argtypes = [vp, C.c_int] + [vp] * 13
     L.mpc_solve_one.argtypes = [vp, dp, dp, C.c_double, C.c_double, dp, dp, dp, ip, ip]
+    L.mpc_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.mpc_launch_count.argtypes = [vp]
     L.mpc_launch_count.restype = C.c_longlong
     L.mpc_last_error.restype = C.c_char_p
@@ -134,6 +135,13 @@ def config_from_json_text(text):
     cfg = MpcConfig()
     _check(lib().mpc_config_parse_json(text.encode(), C.byref(cfg)), "mpc_config_parse_json")
     return cfg
+
+
+def measure_fp64_peak(device=0):
+    """Measured DFMA peak of the device in TFLOP/s (2 flop per FMA)."""
+    v = C.c_double(0.0)
+    _check(lib().mpc_measure_fp64_peak(device, C.byref(v)), "mpc_measure_fp64_peak")
+    return v.value
 
 
 def _ptr(t):

@@ -384,6 +384,52 @@ extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *c
                               traj_y, nullptr, status, iters);
 }
 
+// ---- FP64 FMA peak micro-benchmark (roofline denominator) -----------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[0] = s;   // keep the chains alive
+}
+
+extern "C" int mpc_measure_fp64_peak(int device, double *tflops) {
+  if (!tflops) return MPC_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { (void)cudaGetLastError(); return MPC_ENODEV; }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double *d = nullptr;
+  CK(cudaMalloc(&d, 8));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(e0));
+    dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+    double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return MPC_OK;
+}
+
 extern "C" long long mpc_launch_count(const mpc_handle *h) { return h ? h->launches : 0; }
 extern "C" const char *mpc_last_error(void) { return g_err; }
 extern "C" const char *mpc_version(void) { return "mpc_b200 0.1 (sm_100a, fp64 interior point, one problem per warp)"; }

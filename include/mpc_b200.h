@@ -138,6 +138,11 @@ int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs,
                   double yaw_lo, double yaw_hi,
                   double *result, double *traj_x, double *traj_y, int *status, int *iters);
 
+/* Measure the device's FP64 FMA peak with a dependent-chain-free DFMA micro-kernel (8 independent
+ * chains per thread, every SM full): the roofline denominator bench.py reports against, since
+ * MEASURED_PEAKS.json holds no FP64 figure.  *tflops = 2 * FMAs / seconds / 1e12. */
+int mpc_measure_fp64_peak(int device, double *tflops);
+
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long mpc_launch_count(const mpc_handle *h);
 /* text of the last CUDA error seen by this thread's calls ("" if none) */

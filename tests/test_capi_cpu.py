@@ -1,0 +1,107 @@
+"""No-GPU checks of the product library: it loads, exports every symbol the header declares,
+parses config-*.json exactly like Config::load, and refuses to compute without a device."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(mpc):
+    hdr = open(os.path.join(ROOT, "include", "mpc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mpc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = mpc.lib()
+    for name in declared:
+        assert hasattr(L, name), "missing export %s" % name
+    assert declared == set(mpc.EXPORTS)
+    assert b"sm_100a" in L.mpc_version()
+
+
+def test_config_struct_size_matches_header(mpc):
+    # 4 ints + 8 doubles + 12 + 16 + 16 doubles + tol + 2 ints + 5 doubles + 2 ints + 32 doubles
+    assert C.sizeof(mpc.MpcConfig) == 16 + 8 * (8 + 12 + 16 + 16 + 1) + 8 + 8 * 5 + 8 + 8 * 32
+
+
+@pytest.mark.parametrize("name", ["stable", "fast", "no-latency"])
+def test_config_load_matches_config_cpp(mpc, po, refdata, name, tmp_path):
+    """Config::load conversions (Config.cpp:39-86): product C++ loader == Python restatement."""
+    js = refdata["configs"][name]
+    path = tmp_path / ("config-%s.json" % name)
+    path.write_text(json.dumps(js, indent=2))
+    got = mpc.config_from_json_file(str(path)).as_dict()
+    want = po.load_config_dict(js)
+    for k, v in want.items():
+        if isinstance(v, list):
+            assert np.array_equal(np.array(got[k][: len(v)]), np.array(v)), k
+        else:
+            assert got[k] == v, k
+    # SURVEY.md App. A.5 numerics for config-stable
+    if name == "stable":
+        assert got["max_accel"] == pytest.approx(4.4703889, abs=1e-7)
+        assert got["max_decel"] == pytest.approx(-8.9407778, abs=1e-7)
+        assert got["max_steering"] == pytest.approx(0.4363323, abs=1e-7)
+        assert got["max_speed"] == pytest.approx(53.6446667, abs=1e-7)
+        assert got["steer_speeds"][0] == got["max_speed"]
+
+
+def test_config_errors(mpc, tmp_path):
+    with pytest.raises(mpc.MpcError, match="MPC_EIO"):
+        mpc.config_from_json_file(str(tmp_path / "nope.json"))
+    with pytest.raises(mpc.MpcError, match="MPC_EPARSE"):
+        mpc.config_from_json_text("{\"N\": 10")
+    with pytest.raises(mpc.MpcError, match="MPC_EPARSE"):
+        mpc.config_from_json_text("{\"N\": 10, \"dt\": 0.1}")          # missing keys
+    bad = {"N": 10, "weights": [1, 2, 3]}
+    with pytest.raises(mpc.MpcError, match="MPC_EPARSE"):
+        mpc.config_from_json_text(json.dumps(bad))
+
+
+def test_defaults_are_config_cpp_statics(mpc):
+    d = mpc.config_defaults()
+    assert (d.N, d.dt, d.Lf, d.max_fit_order) == (25, 0.025, 2.67, 4)       # Config.cpp:5-17
+    assert d.max_speed == pytest.approx(100 * 1609.34 / 3600.0)
+    assert list(d.weights[:8]) == [100, 100, 1, 1, 1, 5000, 1, 1000]
+    assert (d.max_iter, d.tol) == (3000, 1e-8)
+
+
+def test_no_cpu_fallback(mpc, stable_cfg):
+    """Without a CUDA device the product must fail loudly (MPC_ENODEV), never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mpc.MpcError, match="MPC_ENODEV"):
+        mpc.Solver(stable_cfg, 0)
+
+
+def test_create_rejects_bad_config(mpc, stable_cfg):
+    import copy
+    for field, val in [("N", 1), ("N", 33), ("dt", 0.0), ("Lf", -1.0), ("n_steer_speeds", 0)]:
+        c = mpc.MpcConfig.from_buffer_copy(stable_cfg)
+        setattr(c, field, val)
+        with pytest.raises(mpc.MpcError, match="MPC_EINVAL"):
+            mpc.Solver(c, 0)
+
+
+def test_workload_generator_matches_scalar_preprocessing(mpc, po, stable_cd, refdata):
+    """workloads.preprocess_batch (vectorised MPC::run pre-processing) == the scalar restatement."""
+    b = mpc.workloads.batch_perturbed_states(64, 0, stable_cd)
+    wx, wy = np.array(refdata["waypoints"]["x"]), np.array(refdata["waypoints"]["y"])
+    for i in range(64):
+        win = (b["segment"][i] + np.arange(6)) % len(wx)
+        st, co, lo, hi, ex = po.preprocess(stable_cd, (b["px"][i], b["py"][i], b["psi"][i], b["v"][i]), wx[win], wy[win])
+        assert ex["order"] == b["fit_order"][i]
+        assert np.allclose(co, b["coeffs"][i], rtol=1e-7, atol=1e-9)
+        assert np.allclose(st, b["state"][i], rtol=1e-9, atol=1e-9)
+        assert (lo, hi) == pytest.approx((b["yaw_lo"][i], b["yaw_hi"][i]), rel=1e-7, abs=1e-9)
+    # determinism and the characterisation of SURVEY.md App. C
+    b2 = mpc.workloads.batch_perturbed_states(64, 0, stable_cd)
+    assert np.array_equal(b["state"], b2["state"]) and np.array_equal(b["coeffs"], b2["coeffs"])
+    big = mpc.workloads.batch_perturbed_states(4096, 0, stable_cd)
+    assert 0.2 < (np.abs(big["state"][:, 4]) > 0.8).mean() < 0.5
+    assert 0.3 < (np.abs(big["state"][:, 5]) > 0.1).mean() < 0.55

@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle, the committed
+golden vectors and size-independent properties.
+
+Tolerances are the north star's: actuations / predicted trajectory 1e-4 absolute, cost 1e-6 relative
+(FP64).  In practice the two agree to ~1e-8 because they run the same interior-point iteration with
+independent linear algebra (Riccati recursion on the GPU, dense Bunch-Kaufman LDL^T in the oracle)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import nlp_numpy as nn
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ABS_TOL, REL_TOL = 1e-4, 1e-6
+
+
+def _assert_parity(g, c, mask=None):
+    ok = c["status"] == 1 if mask is None else mask
+    assert np.array_equal(g["status"][ok], c["status"][ok])
+    d = np.abs(g["result"] - c["result"])[ok]
+    assert d[:, :8].max() < ABS_TOL
+    assert (d[:, 8] / np.abs(c["result"][ok, 8])).max() < REL_TOL
+    assert np.abs(g["traj_x"] - c["traj_x"])[ok].max() < ABS_TOL
+    assert np.abs(g["traj_y"] - c["traj_y"])[ok].max() < ABS_TOL
+    return d
+
+
+def test_golden_testcpp_scenarios(solver):
+    """run() + 25 x solve() of src/test.cpp:64-111 for the four fixtures, vs tests/golden."""
+    gold = json.load(open(os.path.join(GOLD, "oracle_golden.json")))
+    for sc in gold["scenarios"]:
+        state = np.array(sc["state0"])
+        for step in sc["steps"]:
+            r = solver.solve_one(state, sc["coeffs"], sc["yaw_lo"], sc["yaw_hi"])
+            assert r["status"] == step["status"] == 1
+            assert np.abs(r["result"][:8] - np.array(step["result"][:8])).max() < ABS_TOL
+            assert r["result"][8] == pytest.approx(step["result"][8], rel=REL_TOL)
+            assert np.abs(r["traj_x"] - np.array(step["traj_x"])).max() < ABS_TOL
+            assert np.abs(r["traj_y"] - np.array(step["traj_y"])).max() < ABS_TOL
+            assert abs(r["iters"] - step["iters"]) <= 2
+            state = np.array(step["result"][:6])     # feed the golden state back (no drift accumulation)
+
+
+def test_testcpp_first_solve_survey_values(solver, po, stable_cd, refdata):
+    fx = refdata["test_cpp_fixtures"][0]
+    state, coeffs, ylo, yhi, _ = po.preprocess(stable_cd, (fx["x"], fx["y"], fx["psi"], fx["v"]), fx["ptsx"], fx["ptsy"])
+    r = solver.solve_one(state, coeffs, ylo, yhi)
+    assert r["status"] == 1 and r["iters"] == 10
+    assert r["result"][:8] == pytest.approx(
+        [2.66806, 0, 0.00241174, 27.1276389, -0.1072304, 0.0283982, 0.002413, 4.4703889], abs=2e-6)
+    assert r["result"][8] == pytest.approx(6243.443671, rel=1e-9)
+
+
+@pytest.mark.parametrize("seed,B", [(0, 4096), (7, 1000), (8, 33), (9, 1)])
+def test_batch_vs_oracle(solver, mpc, po, stable_cd, seed, B):
+    b = mpc.workloads.batch_perturbed_states(B, seed, stable_cd)
+    g = solver.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    c = po.solve_batch(po.make_config(stable_cd), po.problems_from_arrays(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"]), 16)
+    assert (c["status"] == 1).mean() > 0.99
+    d = _assert_parity(g, c)
+    assert np.median(d[:, :8].max(axis=1)) < 1e-9
+    assert (np.abs(g["iters"] - c["iters"]) <= 1).mean() > 0.97
+
+
+@pytest.mark.parametrize("name", ["fast", "no-latency"])
+def test_other_shipped_configs(mpc, po, refdata, name):
+    cfg = mpc.config_from_json_text(json.dumps(refdata["configs"][name]))
+    cd = po.load_config_dict(refdata["configs"][name])
+    b = mpc.workloads.batch_perturbed_states(512, 21, cd)
+    S = mpc.Solver(cfg, 0)
+    g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.close()
+    c = po.solve_batch(po.make_config(cd), po.problems_from_arrays(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"]), 16)
+    _assert_parity(g, c)
+
+
+@pytest.mark.parametrize("N,dt", [(2, 0.1), (3, 0.1), (10, 0.05), (10, 0.02), (20, 0.05), (25, 0.025), (30, 0.02), (32, 0.05)])
+def test_horizon_and_timestep_grid(mpc, po, refdata, N, dt):
+    """N x dt cells of the reference's examples/ grid that fit one lane per stage (N <= 32)."""
+    js = dict(refdata["configs"]["stable"], N=N, dt=dt)
+    cfg = mpc.config_from_json_text(json.dumps(js))
+    cd = po.load_config_dict(js)
+    b = mpc.workloads.batch_perturbed_states(96, 31, cd)
+    S = mpc.Solver(cfg, 0)
+    g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.close()
+    c = po.solve_batch(po.make_config(cd), po.problems_from_arrays(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"]), 16)
+    both = (c["status"] == 1) & (g["status"] == 1)
+    assert both.mean() > 0.9
+    assert (g["status"] == c["status"]).mean() > 0.97
+    _assert_parity(g, c, both)
+
+
+def test_per_problem_weights_and_frozen_accel_terms(solver, mpc, po, stable_cd):
+    """Weight sweep (BASELINE config 4): per-problem weights; w_a, w_adot, w_decel must have NO effect."""
+    B = 256
+    b = mpc.workloads.batch_perturbed_states(B, 41, stable_cd)
+    rng = np.random.default_rng(2)
+    W = np.tile(np.array(stable_cd["weights"]), (B, 1))
+    W[:, 3] = np.exp(rng.uniform(np.log(1), np.log(5000), B))
+    W[:, 4] = np.exp(rng.uniform(np.log(1), np.log(5000), B))
+    W[:, 1] = np.exp(rng.uniform(np.log(1), np.log(1000), B))
+    W[:, 2] = rng.choice([0.01, 0.1, 1, 10, 100], B)
+    g = solver.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"], weights=W)
+    W2 = W.copy()
+    W2[:, 6] = rng.uniform(0, 1e4, B); W2[:, 7] = rng.uniform(0, 1e4, B); W2[:, 8] = rng.uniform(0, 1e4, B); W2[:, 5] = 7.0
+    g2 = solver.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"], weights=W2)
+    assert np.array_equal(g["result"], g2["result"]) and np.array_equal(g["iters"], g2["iters"])
+    # oracle, problem by problem with its own weights
+    for i in range(0, B, 8):
+        cd = dict(stable_cd, weights=list(W[i]))
+        r = po.solve(po.make_config(cd), po.make_problem(b["state"][i], b["coeffs"][i], b["yaw_lo"][i], b["yaw_hi"][i]))
+        if r["status"] != 1:
+            continue
+        assert g["status"][i] == 1
+        assert np.abs(g["result"][i, :8] - r["result"][:8]).max() < ABS_TOL
+        assert g["result"][i, 8] == pytest.approx(r["result"][8], rel=REL_TOL)
+
+
+def test_ragged_per_problem_horizon_and_dt(mpc, po, refdata):
+    """Horizon/timestep sweep (BASELINE config 3) in ONE launch: per-problem N and dt."""
+    js = dict(refdata["configs"]["stable"], N=30)
+    cfg = mpc.config_from_json_text(json.dumps(js))
+    cd = po.load_config_dict(js)
+    B = 192
+    b = mpc.workloads.batch_perturbed_states(B, 51, cd)
+    rng = np.random.default_rng(1)
+    pairs = [(10, 0.1), (20, 0.1), (30, 0.1), (10, 0.05), (20, 0.05), (30, 0.05), (10, 0.02), (20, 0.02), (30, 0.02)]
+    pick = rng.integers(0, len(pairs), B)
+    Np = np.array([pairs[k][0] for k in pick], dtype=np.int32)
+    dtp = np.array([pairs[k][1] for k in pick])
+    S = mpc.Solver(cfg, 0)
+    g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"], N_per=Np, dt_per=dtp)
+    S.close()
+    n_checked = 0
+    for i in range(0, B, 3):
+        cdi = dict(cd, N=int(Np[i]), dt=float(dtp[i]))
+        r = po.solve(po.make_config(cdi), po.make_problem(b["state"][i], b["coeffs"][i], b["yaw_lo"][i], b["yaw_hi"][i]))
+        if r["status"] != 1 or g["status"][i] != 1:
+            continue
+        n_checked += 1
+        assert np.abs(g["result"][i, :8] - r["result"][:8]).max() < ABS_TOL
+        assert g["result"][i, 8] == pytest.approx(r["result"][8], rel=REL_TOL)
+        assert np.abs(g["traj_x"][i, :Np[i]] - r["z"][:Np[i]]).max() < ABS_TOL
+    assert n_checked > 40
+
+
+def test_full_size_batch_properties(solver, mpc, stable_cd):
+    """BASELINE configs[1] at full size (65,536 problems): solver-independent checks of every result
+    against the independent numpy statement of the reference NLP."""
+    B = 65536
+    cd = stable_cd
+    N = cd["N"]
+    b = mpc.workloads.batch_perturbed_states(B, 0, cd)
+    g = solver.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"], want_full=True)
+    ok = g["status"] == 1
+    assert ok.mean() > 0.995, np.bincount(g["status"])
+    z = g["full"]
+    # feasibility of the dynamics (equality constraints of MPC.cpp:116-153)
+    c = nn.constraints(cd, b["state"], b["coeffs"], z)
+    assert np.abs(c[ok]).max() < 1e-6
+    # bounds (MPC.cpp:220-257), honoured exactly after the final clip
+    xl, xu = nn.var_bounds(cd, b["yaw_lo"], b["yaw_hi"])
+    assert (z[ok] >= xl[ok]).all() and (z[ok] <= xu[ok]).all()
+    # returned cost == objective of the returned point; outputs are the documented slices
+    f = nn.objective(cd, nn.frozen(cd, b["state"]), z)
+    assert np.allclose(g["result"][ok, 8], f[ok], rtol=1e-12)
+    assert np.array_equal(g["result"][:, 0], z[:, 1]) and np.array_equal(g["result"][:, 6], z[:, 6 * N])
+    assert np.array_equal(g["result"][:, 7], z[:, 7 * N - 1])
+    assert np.array_equal(g["traj_x"], z[:, :N]) and np.array_equal(g["traj_y"], z[:, N:2 * N])
+    assert np.percentile(g["iters"], 50) <= 11 and g["iters"][ok].max() < 200
+    # shard invariance (multi-GPU contract): solving a slice alone gives bit-identical results
+    s = slice(12345, 12345 + 4096)
+    g2 = solver.solve_batch_host(b["state"][s], b["coeffs"][s], b["yaw_lo"][s], b["yaw_hi"][s])
+    assert np.array_equal(g2["result"], g["result"][s]) and np.array_equal(g2["iters"], g["iters"][s])
+    # determinism
+    g3 = solver.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    assert np.array_equal(g3["result"], g["result"])
+
+
+def test_edge_cases(solver, mpc, stable_cfg, stable_cd):
+    import ctypes as C
+    L = mpc.lib()
+    # B = 0 is a no-op; NULL required pointers and negative B are EINVAL
+    assert L.mpc_solve_batch_host(solver._h, 0, 1, 1, 1, 1, None, None, None, 1, None, None, None, None, None) == 0
+    assert L.mpc_solve_batch_host(solver._h, 4, None, 1, 1, 1, None, None, None, 1, None, None, None, None, None) == -1
+    assert L.mpc_solve_batch_host(solver._h, -1, 1, 1, 1, 1, None, None, None, 1, None, None, None, None, None) == -1
+    # infeasible start (psi0 outside the yaw bounds, |v0| above max speed): terminates with a
+    # non-success status like the reference ("Ipopt failed with <int>", MPC.cpp:301), no hang
+    st = np.array([[0, 0, 0.5, 10.0, 0.1, 0.0], [0, 0, 0.0, 80.0, 0.1, 0.0], [0, 0, 0, 20.0, 0.0, 0.0]])
+    co = np.zeros((3, 5))
+    r = solver.solve_batch_host(st, co, np.array([-0.1, -0.1, -0.1]), np.array([0.1, 0.1, 0.1]))
+    assert r["status"][0] != 1 and r["status"][1] != 1 and r["status"][2] == 1
+    assert np.isfinite(r["result"][2]).all()
+    # straight road, centred: steer 0, full throttle (a at its upper bound)
+    assert abs(r["result"][2, 6]) < 1e-9 and r["result"][2, 7] == pytest.approx(stable_cd["max_accel"], abs=1e-7)
+    # outputs are optional
+    out = solver.solve_batch_host(st[2:], co[2:], np.array([-0.1]), np.array([0.1]), want_traj=False)
+    assert out["status"][0] == 1
