@@ -20,7 +20,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-NCOEF, NTAB, NWEIGHTS, NMAX = 5, 16, 12, 32
+NCOEF, NTAB, NWEIGHTS, NMAX = 5, 16, 12, 64
+KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE = 0, 1, 2
+LANE_MIN_BATCH = 1024
 
 STATUS_SUCCESS = 1
 STATUS_NAMES = {0: "not_defined", 1: "success", 2: "maxiter_exceeded", 3: "stop_at_tiny_step",
@@ -29,7 +31,7 @@ STATUS_NAMES = {0: "not_defined", 1: "success", 2: "maxiter_exceeded", 3: "stop_
 
 EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json", "mpc_create",
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
-           "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak"]
+           "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel"]
 
 
 class MpcError(RuntimeError):
@@ -98,6 +100,7 @@ def lib():
     L.mpc_destroy.argtypes = [vp]
     L.mpc_destroy.restype = None
     L.mpc_set_config.argtypes = [vp, cfgp]
+    L.mpc_set_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_solve_batch.argtypes = [vp, C.c_int] + [vp] * 13 + [vp]
     L.mpc_solve_batch_host.argtypes = [vp, C.c_int] + [vp] * 13
     L.mpc_solve_one.argtypes = [vp, dp, dp, C.c_double, C.c_double, dp, dp, dp, ip, ip]
@@ -177,6 +180,10 @@ class Solver:
     def set_config(self, cfg):
         _check(lib().mpc_set_config(self._h, C.byref(cfg)), "mpc_set_config")
         self.cfg = cfg
+
+    def set_kernel(self, kind=KERNEL_AUTO, lane_threads=0, lane_ctas_per_sm=0):
+        """Pick the kernel (auto / one problem per warp / one problem per lane) and the lane grid."""
+        _check(lib().mpc_set_kernel(self._h, kind, lane_threads, lane_ctas_per_sm), "mpc_set_kernel")
 
     @property
     def launches(self):

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "mpc_kernel.cuh"
+#include "mpc_lane_kernel.cuh"
 
 using namespace mpcb200;
 
@@ -37,6 +38,9 @@ struct mpc_handle {
   int sm_count;
   int *d_counter;
   long long launches;
+  int kernel_kind;      // MPC_KERNEL_AUTO / WARP / LANE
+  int lane_threads;     // threads per CTA of the lane kernel
+  int lane_ctas_per_sm; // CTAs per SM of the lane kernel (0 = occupancy maximum)
   // staging buffers for the host-pointer entry points (grown on demand)
   double *d_in, *d_out;
   int *d_iout;
@@ -247,6 +251,9 @@ extern "C" int mpc_create(const mpc_config *cfg, int device, mpc_handle **out) {
   h->sm_count = prop.multiProcessorCount;
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->kernel_kind = MPC_KERNEL_AUTO;
+  h->lane_threads = 128;
+  h->lane_ctas_per_sm = 0;
   *out = h;
   return MPC_OK;
 }
@@ -298,6 +305,40 @@ static int launch(mpc_handle *h, KParams &kp, cudaStream_t st) {
   return MPC_OK;
 }
 
+// The lane kernel keeps everything in registers and thread-private memory: no shared memory, so
+// the whole unified L1 is cache for the per-stage arrays.
+template <int NS>
+static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
+  const int threads = h->lane_threads;
+  static thread_local int cached_dev = -1;
+  if (cached_dev != h->device) {
+    CK(cudaFuncSetAttribute(mpc_lane_kernel<NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    cached_dev = h->device;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_lane_kernel<NS>, threads, 0));
+  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "lane kernel does not fit on an SM"); return MPC_ECUDA; }
+  if (h->lane_ctas_per_sm > 0 && per_sm > h->lane_ctas_per_sm) per_sm = h->lane_ctas_per_sm;
+  long long want = ((long long)kp.B + threads - 1) / threads;
+  long long grid = (long long)h->sm_count * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
+  mpc_lane_kernel<NS><<<(unsigned)grid, threads, 0, st>>>(kp);
+  CK(cudaGetLastError());
+  h->launches++;
+  return MPC_OK;
+}
+
+extern "C" int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm) {
+  if (!h || kind < MPC_KERNEL_AUTO || kind > MPC_KERNEL_LANE) return MPC_EINVAL;
+  if (lane_threads != 0 && (lane_threads < 32 || lane_threads > 128 || lane_threads % 32)) return MPC_EINVAL;
+  h->kernel_kind = kind;
+  if (lane_threads) h->lane_threads = lane_threads;
+  h->lane_ctas_per_sm = lane_ctas_per_sm < 0 ? 0 : lane_ctas_per_sm;
+  return MPC_OK;
+}
+
 extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const double *coeffs,
                                const double *yaw_lo, const double *yaw_hi, const double *weights,
                                const int *N_per, const double *dt_per, double *result, double *traj_x,
@@ -319,7 +360,18 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   kp.N_pp = N_per; kp.dt_pp = dt_per;
   kp.result = result; kp.traj_x = traj_x; kp.traj_y = traj_y; kp.full = full; kp.status = status; kp.iters = iters;
   kp.counter = h->d_counter;
-  return launch<32>(h, kp, (cudaStream_t)cuda_stream);
+  // Kernel choice: the warp kernel (one problem per warp, N <= 32) minimises the latency of a
+  // handful of problems; the lane kernel (one problem per lane) maximises batch throughput.
+  int kind = h->kernel_kind;
+  if (kind == MPC_KERNEL_AUTO) kind = (B >= MPC_LANE_MIN_BATCH || c.N > 32) ? MPC_KERNEL_LANE : MPC_KERNEL_WARP;
+  if (kind == MPC_KERNEL_WARP) {
+    if (c.N > 32) { snprintf(g_err, sizeof(g_err), "warp kernel handles N <= 32"); return MPC_EINVAL; }
+    return launch<32>(h, kp, (cudaStream_t)cuda_stream);
+  }
+  if (c.N <= 10) return launch_lane<10>(h, kp, (cudaStream_t)cuda_stream);
+  if (c.N <= 20) return launch_lane<20>(h, kp, (cudaStream_t)cuda_stream);
+  if (c.N <= 32) return launch_lane<32>(h, kp, (cudaStream_t)cuda_stream);
+  return launch_lane<MPC_NMAX>(h, kp, (cudaStream_t)cuda_stream);
 }
 
 // ---- host-pointer entry points -------------------------------------------------------------------

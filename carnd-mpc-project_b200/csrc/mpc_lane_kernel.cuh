@@ -1,0 +1,949 @@
+// mpc_lane_kernel.cuh -- the throughput kernel: one MPC problem per LANE.
+//
+// Same algorithm as mpc_kernel.cuh (the one-problem-per-warp latency kernel): the NLP of FG_eval
+// (/root/reference/src/control/MPC.cpp:50-154) with hand-derived derivatives, Ipopt's primal-dual
+// filter line-search iteration (Ipopt 3.12 defaults, MPC.cpp:160-179) and a stage-wise Riccati
+// factorisation of the block-banded KKT system instead of MUMPS (MPC.cpp:175).  What changes is
+// the mapping onto the machine.  The warp kernel keeps 17 of 32 lanes busy and spends most of its
+// issue slots on shuffles and shared-memory hand-offs (profiles/r01_v1_*); a batch of 64K problems
+// has far more problem-level parallelism than the chip has lanes, so here every lane owns one
+// problem, runs the whole recursion on its own registers and keeps the per-stage iterate in
+// thread-private (lane-interleaved, hence fully coalesced) memory.
+//
+// Lanes of a warp work on different problems with different iteration counts.  To keep them
+// converged the solver is written as a state machine whose trip has a fixed shape
+//        [evaluate a point] -> [accept / update / KKT errors / mu] -> [Riccati] -> [forward + costate]
+// and every lane executes the slots its state needs.  A lane that finishes pulls the next problem
+// from a global counter, so the spread of iteration counts (10 typical, 50 worst) costs nothing.
+// The rare paths (inertia correction 0.3 % of iterations, second-order correction and backtracking
+// ~0.002 %) simply take extra trips.
+#pragma once
+#include "mpc_kernel.cuh"
+
+namespace mpcb200 {
+
+enum {
+  LM_IDLE = 0,    // no problem: fetch one
+  LM_EV0,         // evaluate the start point
+  LM_LSQ,         // least-squares multiplier estimate (Riccati with H = I)
+  LM_LSQ_DONE,    // take the multipliers, compute the KKT error, go to NEWTON
+  LM_NEWTON,      // factor (with inertia correction) and solve for the search direction
+  LM_TRIAL,       // evaluate x + alpha dx and test it against the filter
+  LM_SOC,         // solve with the second-order-corrected right-hand side
+  LM_SOC_TRIAL,   // evaluate the corrected trial point
+  LM_RESOLVE,     // SOC failed: recompute the uncorrected direction, then backtrack
+  LM_FINISH,      // write the outputs
+  LM_DONE         // queue empty
+};
+
+// constants of one problem (thread-private)
+enum { LC_DT = 0, LC_DTLF, LC_SF, LC_CW, LC_WC2, LC_WE2, LC_WV2, LC_VREF, LC_WD2, LC_WC2_0, LC_WE2_0,
+       LC_VREF_0, LC_NV2_0, LC_C0, LC_S0 = LC_C0 + 5, LC_LO = LC_S0 + 6, LC_HI = LC_LO + 4,
+       LC_LO0 = LC_HI + 4, LC_HI0 = LC_LO0 + 4, LC_SIZE = LC_HI0 + 4 };
+
+__device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+
+template <int NS>
+struct Lane {
+  // ---- per-stage data (thread-private memory) ----
+  double S[NS][6], U[NS][2], LAM[NS][6], ZL[NS][4], ZU[NS][4], IL[NS][4], IU[NS][4];
+  double TG[NS][7], CN[NS][6];            // trig/poly and c_{i+1} at the iterate
+  double DS[NS][6], DU[NS][2], LN[NS][6]; // search direction and new multipliers
+  double KG[NS][12];                      // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
+  double TT[NS][7], CT[NS][6];            // trig/poly and residuals at the trial point
+  double CS[NS][6];                       // second-order-correction right-hand side
+  double PC[LC_SIZE];
+  double FLT[2 * K_NFILT];
+  double c0[6], c0t[6], cs0[6];
+  // ---- scalars ----
+  int b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt;
+  double mu, tau, theta_min, theta_max, dw, dw_last, dw_used;
+  double alpha, alpha_z, alpha_test, alpha_soc, alpha_min;
+  double ls_theta, ls_phi, ls_gbd, pow_gbd, pow_theta;
+  double fx, lsum, theta, ft, lt, tht, theta_soc_old;
+  double dinf, cviol, amin, amax, lam1, z1, lsq_lmax, gbd_new;
+
+  __device__ __forceinline__ double wc2(int i) const { return i == 0 ? PC[LC_WC2_0] : PC[LC_WC2]; }
+  __device__ __forceinline__ double we2(int i) const { return i == 0 ? PC[LC_WE2_0] : PC[LC_WE2]; }
+  __device__ __forceinline__ double vref(int i) const { return i == 0 ? PC[LC_VREF_0] : PC[LC_VREF]; }
+  __device__ __forceinline__ double nv2(int i) const { return i == 0 ? PC[LC_NV2_0] : 0.0; }
+
+  // ------------------------------------------------------------------------------------------
+  // problem set-up: MPC.cpp:204-281 (start point, bounds), frozen branches of FG_eval at the
+  // start point (MPC.cpp:72,79,87,89), Ipopt's objective scaling and bound relaxation / push
+  // ------------------------------------------------------------------------------------------
+  __device__ void init(const KParams &P, int b_) {
+    b = b_;
+    const int B = P.B;
+    N = P.N_pp ? P.N_pp[b] : P.Nmax;
+    if (N > NS) N = NS;
+    if (N > P.Nmax) N = P.Nmax;
+    if (N < 2) N = 2;
+    double w[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) w[k] = P.weights_pp ? P.weights_pp[(size_t)k * B + b] : P.weights[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) PC[LC_S0 + k] = P.state[(size_t)k * B + b];
+#pragma unroll
+    for (int k = 0; k < 5; k++) PC[LC_C0 + k] = P.coeffs[(size_t)k * B + b];
+    const double ylo = P.yaw_lo[b], yhi = P.yaw_hi[b];
+    const double dt = P.dt_pp ? P.dt_pp[b] : P.dt;
+    const double cte0 = PC[LC_S0 + 4], epsi0 = PC[LC_S0 + 5], psi0 = PC[LC_S0 + 2], v0 = PC[LC_S0 + 3];
+    const double wc0 = fabs(cte0) < P.cte_panic ? w[0] : w[11];
+    const double wcN = 0.0 < P.cte_panic ? w[0] : w[11];
+    const double we0 = fabs(epsi0) > P.epsi_panic ? w[10] : w[1];
+    const double weN = 0.0 > P.epsi_panic ? w[10] : w[1];
+    const double vr0 = speed_target(P, psi0, P.max_speed), vrN = speed_target(P, 0.0, P.max_speed);
+    const double nvw0 = v0 < 0.0 ? w[9] : 0.0;
+    double gmx = fmax(fabs(2.0 * wc0 * cte0), fabs(2.0 * we0 * epsi0));
+    gmx = fmax(gmx, fabs(2.0 * w[2] * (v0 - vr0) + 2.0 * nvw0 * v0));
+    gmx = fmax(gmx, fabs(2.0 * w[2] * vrN));
+    const double sf = gmx > 100.0 ? fmax(100.0 / gmx, 1e-8) : 1.0;
+    PC[LC_DT] = dt;
+    PC[LC_DTLF] = dt / P.Lf;
+    PC[LC_SF] = sf;
+    PC[LC_CW] = 2.0 * sf * w[4];
+    PC[LC_WC2] = 2.0 * sf * wcN; PC[LC_WE2] = 2.0 * sf * weN; PC[LC_WV2] = 2.0 * sf * w[2];
+    PC[LC_VREF] = vrN; PC[LC_WD2] = 2.0 * sf * w[3];
+    PC[LC_WC2_0] = 2.0 * sf * wc0; PC[LC_WE2_0] = 2.0 * sf * we0; PC[LC_VREF_0] = vr0;
+    PC[LC_NV2_0] = 2.0 * sf * nvw0;
+    const double lo0[4] = {ylo, -P.max_speed, -P.max_steering, P.max_decel};
+    const double hi0[4] = {yhi, P.max_speed, P.max_steering, P.max_accel};
+    double x0[4];   // pushed start values of psi, v, delta, a for stages >= 1 (start point 0)
+    double x00[2];  // pushed psi, v of stage 0
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double lo = lo0[k] - fmin(K_CONSTR_VIOL_TOL, K_BOUND_RELAX * fmax(1.0, fabs(lo0[k])));
+      const double hi = hi0[k] + fmin(K_CONSTR_VIOL_TOL, K_BOUND_RELAX * fmax(1.0, fabs(hi0[k])));
+      PC[LC_LO0 + k] = lo0[k]; PC[LC_HI0 + k] = hi0[k]; PC[LC_LO + k] = lo; PC[LC_HI + k] = hi;
+      const double span = hi - lo;
+      const double pl = fmin(K_KAPPA_1 * fmax(1.0, fabs(lo)), K_KAPPA_2 * span);
+      const double pu = fmin(K_KAPPA_1 * fmax(1.0, fabs(hi)), K_KAPPA_2 * span);
+      double v = 0.0;
+      if (v < lo + pl) v = lo + pl;
+      if (v > hi - pu) v = hi - pu;
+      x0[k] = v;
+      if (k < 2) {
+        double v2 = k == 0 ? psi0 : v0;
+        if (v2 < lo + pl) v2 = lo + pl;
+        if (v2 > hi - pu) v2 = hi - pu;
+        x00[k] = v2;
+      }
+    }
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) { S[i][k] = (i == 0) ? PC[LC_S0 + k] : 0.0; LAM[i][k] = 0.0; DS[i][k] = 0.0; LN[i][k] = 0.0; }
+      S[i][2] = i == 0 ? x00[0] : x0[0];
+      S[i][3] = i == 0 ? x00[1] : x0[1];
+      U[i][0] = x0[2]; U[i][1] = x0[3];
+      DU[i][0] = 0.0; DU[i][1] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool valid = k < 2 || i < N - 1;
+        ZL[i][k] = valid ? 1.0 : 0.0;
+        ZU[i][k] = valid ? 1.0 : 0.0;
+        IL[i][k] = 1.0; IU[i][k] = 1.0;
+      }
+    }
+    mu = 0.1;
+    tau = fmax(K_TAU_MIN, 1.0 - mu);
+    dw = 0.0; dw_last = 0.0; dw_used = 0.0;
+    nfilt = 0; iter = 0; accept_cnt = 0; status = 0; ntrial = 0; soc_cnt = 0;
+    alpha = 0.0; alpha_z = 0.0;
+    mode = LM_EV0;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slot 1: residuals, scaled objective, log-barrier sum and ||c||_1 at x + a*dx; the trig /
+  // polynomial values of every stage are kept for the derivative build (MPC.cpp:144-152)
+  // ------------------------------------------------------------------------------------------
+  __device__ void eval_sweep(double a) {
+    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF];
+    const double c0_ = PC[LC_C0], c1_ = PC[LC_C0 + 1], c2_ = PC[LC_C0 + 2], c3_ = PC[LC_C0 + 3], c4_ = PC[LC_C0 + 4];
+    const double lo_p = PC[LC_LO], hi_p = PC[LC_HI], lo_v = PC[LC_LO + 1], hi_v = PC[LC_HI + 1];
+    const double lo_d = PC[LC_LO + 2], hi_d = PC[LC_HI + 2], lo_a = PC[LC_LO + 3], hi_a = PC[LC_HI + 3];
+    double F[6] = {0, 0, 0, 0, 0, 0};
+    double th = 0.0, fl = 0.0, ll = 0.0, dprev = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+      double s[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) s[k] = fma(a, DS[i][k], S[i][k]);
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { const double c = s[k] - PC[LC_S0 + k]; c0t[k] = c; th += fabs(c); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { const double c = s[k] - F[k]; CT[i - 1][k] = c; th += fabs(c); }
+      }
+      const double dv = s[3] - vref(i);
+      fl += 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + PC[LC_WV2] * dv * dv + nv2(i) * s[3] * s[3]);
+      double prod = (s[2] - lo_p) * (hi_p - s[2]) * (s[3] - lo_v) * (hi_v - s[3]);
+      if (i < N - 1) {
+        const double u0 = fma(a, DU[i][0], U[i][0]), u1 = fma(a, DU[i][1], U[i][1]);
+        double sp, cp, se, ce;
+        sincos(s[2], &sp, &cp);
+        sincos(s[5], &se, &ce);
+        const double x = s[0];
+        const double f = (((c4_ * x + c3_) * x + c2_) * x + c1_) * x + c0_;
+        const double f1 = ((4.0 * c4_ * x + 3.0 * c3_) * x + 2.0 * c2_) * x + c1_;
+        const double f2 = (12.0 * c4_ * x + 6.0 * c3_) * x + 2.0 * c2_;
+        const double f3 = 24.0 * c4_ * x + 6.0 * c3_;
+        TT[i][0] = sp; TT[i][1] = cp; TT[i][2] = se; TT[i][3] = ce; TT[i][4] = f1; TT[i][5] = f2; TT[i][6] = f3;
+        const double vdt = s[3] * dt;
+        F[0] = s[0] + cp * vdt;
+        F[1] = s[1] + sp * vdt;
+        F[2] = s[2] + u0 * s[3] * dtLf;
+        F[3] = s[3] + u1 * dt;
+        F[4] = (f - s[1]) + se * vdt;
+        F[5] = F[2] - atan(f1);
+        fl += 0.5 * PC[LC_WD2] * u0 * u0;
+        if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * PC[LC_CW] * dd * dd; }
+        dprev = u0;
+        prod *= (u0 - lo_d) * (hi_d - u0) * (u1 - lo_a) * (hi_a - u1);
+      }
+      ll += log(prod);
+    }
+    ft = fl; lt = ll; tht = th;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slot 2 (backward sweep): accept the trial point (x += alpha dx, lambda, z, slack reciprocals,
+  // residuals and trig of the new iterate) and/or evaluate Ipopt's optimality error terms
+  // ------------------------------------------------------------------------------------------
+  __device__ void update_and_errors(bool do_update, bool take_lsq, bool lsq_bad) {
+    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    const double a = alpha, az = alpha_z;
+    double ln[6] = {0, 0, 0, 0, 0, 0};
+    double dnext = 0.0;
+    double r = 0.0, cv = 0.0, l1 = 0.0, zz = 0.0, am = 1e300, aM = 0.0;
+    if (do_update) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) c0[k] = c0t[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) cv = nanmax(cv, fabs(c0[k]));
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; i--) {
+      const bool hasu = i < N - 1;
+      double s[6], u[2] = {0, 0}, lam[6], zl[4], zu[4];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { s[k] = S[i][k]; lam[k] = LAM[i][k]; }
+      if (hasu) { u[0] = U[i][0]; u[1] = U[i][1]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { zl[k] = ZL[i][k]; zu[k] = ZU[i][k]; }
+      double tg[7];
+      if (do_update) {
+        double dx[4];
+        dx[0] = DS[i][2]; dx[1] = DS[i][3]; dx[2] = hasu ? DU[i][0] : 0.0; dx[3] = hasu ? DU[i][1] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { s[k] = fma(a, DS[i][k], s[k]); lam[k] += a * (LN[i][k] - lam[k]); S[i][k] = s[k]; LAM[i][k] = lam[k]; }
+        if (hasu) {
+          u[0] = fma(a, dx[2], u[0]); u[1] = fma(a, dx[3], u[1]);
+          U[i][0] = u[0]; U[i][1] = u[1];
+#pragma unroll
+          for (int k = 0; k < 6; k++) CN[i][k] = CT[i][k];
+#pragma unroll
+          for (int k = 0; k < 7; k++) { tg[k] = TT[i][k]; TG[i][k] = tg[k]; }
+        }
+        const double xv[4] = {s[2], s[3], u[0], u[1]};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (k < 2 || hasu) {
+            const double il = IL[i][k], iu = IU[i][k];
+            const double dzl = (mu - zl[k] * dx[k]) * il - zl[k];
+            const double dzu = (mu + zu[k] * dx[k]) * iu - zu[k];
+            const double iln = rcp(xv[k] - PC[LC_LO + k]), iun = rcp(PC[LC_HI + k] - xv[k]);
+            double t = zl[k] + az * dzl;
+            zl[k] = fmax(fmin(t, K_KAPPA_SIGMA * mu * iln), mu * iln / K_KAPPA_SIGMA);
+            t = zu[k] + az * dzu;
+            zu[k] = fmax(fmin(t, K_KAPPA_SIGMA * mu * iun), mu * iun / K_KAPPA_SIGMA);
+            IL[i][k] = iln; IU[i][k] = iun; ZL[i][k] = zl[k]; ZU[i][k] = zu[k];
+          }
+        }
+      } else {
+        if (take_lsq) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) { lam[k] = lsq_bad ? 0.0 : LN[i][k]; LAM[i][k] = lam[k]; }
+        }
+        if (hasu) {
+#pragma unroll
+          for (int k = 0; k < 7; k++) tg[k] = TG[i][k];
+        }
+      }
+      // ---- optimality error terms
+      double os[6] = {0, 0, 0, 0, 0, 0}, ou0 = 0.0, ou1 = 0.0;
+      const double v = s[3];
+      if (hasu) {
+        const double vdt = v * dt;
+        const double a13 = -vdt * tg[0], a14 = dt * tg[1], a23 = vdt * tg[1], a24 = dt * tg[0];
+        const double a34 = u[0] * dtLf, b3 = v * dtLf, a51 = tg[4], a54 = dt * tg[2], a56 = vdt * tg[3];
+        const double a61 = -tg[5] / (1.0 + tg[4] * tg[4]);
+        const double l25 = ln[2] + ln[5];
+        os[0] = ln[0] + a51 * ln[4] + a61 * ln[5];
+        os[1] = ln[1] - ln[4];
+        os[2] = a13 * ln[0] + a23 * ln[1] + l25;
+        os[3] = a14 * ln[0] + a24 * ln[1] + a34 * l25 + ln[3] + a54 * ln[4];
+        os[5] = a56 * ln[4];
+        ou0 = b3 * l25;
+        ou1 = dt * ln[3];
+      }
+      double gs[6];
+      gs[0] = 0.0; gs[1] = 0.0;
+      gs[2] = -zl[0] + zu[0];
+      gs[3] = wv2 * (v - vref(i)) + nv2(i) * v - zl[1] + zu[1];
+      gs[4] = wc2(i) * s[4];
+      gs[5] = we2(i) * s[5];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        r = nanmax(r, fabs(gs[k] + lam[k] - os[k]));
+        l1 += fabs(lam[k]);
+      }
+      zz += fabs(zl[0]) + fabs(zu[0]) + fabs(zl[1]) + fabs(zu[1]);
+      {
+        const double p0 = (s[2] - PC[LC_LO]) * zl[0], p1 = (PC[LC_HI] - s[2]) * zu[0];
+        const double p2 = (s[3] - PC[LC_LO + 1]) * zl[1], p3 = (PC[LC_HI + 1] - s[3]) * zu[1];
+        am = fmin(am, fmin(fmin(p0, p1), fmin(p2, p3)));
+        aM = fmax(aM, fmax(fmax(p0, p1), fmax(p2, p3)));
+      }
+      if (hasu) {
+        // delta_{i-1} of the NEW iterate (stage i-1 is updated after this one)
+        double dprev = 0.0;
+        if (i >= 1) dprev = do_update ? fma(a, DU[i - 1][0], U[i - 1][0]) : U[i - 1][0];
+        double gd = wd2 * u[0];
+        if (i >= 1) gd += cw * (u[0] - dprev);
+        if (i <= N - 3) gd -= cw * (dnext - u[0]);
+        r = nanmax(r, fabs(gd - ou0 - zl[2] + zu[2]));
+        r = nanmax(r, fabs(-ou1 - zl[3] + zu[3]));
+        zz += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
+        const double p0 = (u[0] - PC[LC_LO + 2]) * zl[2], p1 = (PC[LC_HI + 2] - u[0]) * zu[2];
+        const double p2 = (u[1] - PC[LC_LO + 3]) * zl[3], p3 = (PC[LC_HI + 3] - u[1]) * zu[3];
+        am = fmin(am, fmin(fmin(p0, p1), fmin(p2, p3)));
+        aM = fmax(aM, fmax(fmax(p0, p1), fmax(p2, p3)));
+#pragma unroll
+        for (int k = 0; k < 6; k++) cv = nanmax(cv, fabs(do_update ? CT[i][k] : CN[i][k]));
+        dnext = u[0];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) ln[k] = lam[k];
+    }
+    dinf = r; cviol = cv; lam1 = l1; z1 = zz; amin = am; amax = aM;
+  }
+  // max_i |slack_i * z_i - m|  from the extreme complementarity products
+  __device__ __forceinline__ double compl_err(double m) const { return nanmax(fabs(amax - m), fabs(amin - m)); }
+
+  // ------------------------------------------------------------------------------------------
+  // derivative pieces of stage i at the iterate (App. A.4 of SURVEY.md)
+  // ------------------------------------------------------------------------------------------
+  struct StageLin { double a13, a14, a23, a24, a34, b3, a51, a54, a56, a61; };
+  struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa, gp, gv, gc, ge, gdp, gd, ga; };
+
+  __device__ __forceinline__ void stage_lin(int i, StageLin &L, double *tg) const {
+    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF];
+#pragma unroll
+    for (int k = 0; k < 7; k++) tg[k] = TG[i][k];
+    const double v = S[i][3], vdt = v * dt;
+    L.a13 = -vdt * tg[0]; L.a14 = dt * tg[1]; L.a23 = vdt * tg[1]; L.a24 = dt * tg[0];
+    L.a34 = U[i][0] * dtLf; L.b3 = v * dtLf; L.a51 = tg[4]; L.a54 = dt * tg[2]; L.a56 = vdt * tg[3];
+    L.a61 = -tg[5] / (1.0 + tg[4] * tg[4]);
+  }
+  // Hessian of the Lagrangian + barrier Sigma + dw on the primal diagonal, gradient of the barrier
+  // objective.  ls: the least-squares multiplier system (Hessian = I, gradient = grad f - zl + zu).
+  __device__ __forceinline__ void stage_hess(int i, bool ls, double dwv, const double *tg, StageHess &H) const {
+    const bool hasu = i < N - 1;
+    const bool cpl = hasu && i >= 1;
+    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    double sig[4], gb[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < 2 || hasu) {
+        const double il = IL[i][k], iu = IU[i][k], zl = ZL[i][k], zu = ZU[i][k];
+        sig[k] = zl * il + zu * iu;
+        gb[k] = ls ? (zu - zl) : mu * (iu - il);
+      } else {
+        sig[k] = 0.0; gb[k] = 0.0;
+      }
+    }
+    const double v = S[i][3];
+    H.gp = gb[0];
+    H.gv = wv2 * (v - vref(i)) + nv2(i) * v + gb[1];
+    H.gc = wc2(i) * S[i][4];
+    H.ge = we2(i) * S[i][5];
+    H.gdp = 0.0; H.gd = 0.0; H.ga = 0.0;
+    if (hasu) {
+      const double d0 = U[i][0];
+      const double dd = cpl ? d0 - U[i - 1][0] : 0.0;
+      H.gdp = -cw * dd;
+      H.gd = wd2 * d0 + cw * dd + gb[2];
+      H.ga = gb[3];
+    }
+    if (ls) {
+      H.qxx = 1.0; H.qyy = 1.0; H.qpp = 1.0; H.qpv = 0.0; H.qvv = 1.0; H.qve = 0.0; H.qcc = 1.0; H.qee = 1.0;
+      H.svd = 0.0; H.rdd = 1.0; H.raa = 1.0;
+      return;
+    }
+    H.qyy = dwv;
+    H.qvv = wv2 + nv2(i) + sig[1] + dwv;
+    H.qcc = wc2(i) + dwv;
+    if (hasu) {
+      double ln[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) ln[k] = LAM[i + 1][k];
+      const double vdt = v * dt;
+      const double q = 1.0 + tg[4] * tg[4], iq = 1.0 / q;
+      H.qxx = -ln[4] * tg[5] + ln[5] * (tg[6] * q - 2.0 * tg[4] * tg[5] * tg[5]) * iq * iq + dwv;
+      H.qpp = (ln[0] * tg[1] + ln[1] * tg[0]) * vdt + sig[0] + dwv;
+      H.qpv = (ln[0] * tg[0] - ln[1] * tg[1]) * dt;
+      H.qve = -ln[4] * tg[3] * dt;
+      H.qee = ln[4] * tg[2] * vdt + we2(i) + dwv;
+      H.svd = -(ln[2] + ln[5]) * dtLf;
+      H.rdd = wd2 + (cpl ? cw : 0.0) + sig[2] + dwv;
+      H.raa = sig[3] + dwv;
+    } else {
+      H.qxx = dwv; H.qpp = sig[0] + dwv; H.qpv = 0.0; H.qve = 0.0; H.qee = we2(i) + dwv;
+      H.svd = 0.0; H.rdd = 0.0; H.raa = 0.0;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slot 3: backward Riccati sweep.  Cost-to-go over (x, y, psi, v, epsi, delta_prev) as a dense
+  // symmetric 6x6 in registers; cte enters only its own stage cost and the next cte linearly, so
+  // it is carried as a scalar (P44, p4).  Returns whether every 2x2 control pivot was positive
+  // definite, i.e. the KKT matrix has inertia (n, m, 0)  -- what Ipopt asks of MUMPS.
+  // ------------------------------------------------------------------------------------------
+  __device__ bool riccati(bool ls, bool soc, double dwv) {
+    const double dt = PC[LC_DT];
+    const double cwv = ls ? 0.0 : PC[LC_CW];
+    double Pm[6][6], pv[6], P44, p4;
+    {
+      StageHess H;
+      double tg[7] = {0, 0, 0, 0, 0, 0, 0};
+      stage_hess(N - 1, ls, dwv, tg, H);
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) Pm[r][c] = 0.0;
+      }
+      Pm[0][0] = H.qxx; Pm[1][1] = H.qyy; Pm[2][2] = H.qpp; Pm[3][3] = H.qvv; Pm[4][4] = H.qee;
+      P44 = H.qcc;
+      pv[0] = 0.0; pv[1] = 0.0; pv[2] = H.gp; pv[3] = H.gv; pv[4] = H.ge; pv[5] = 0.0;
+      p4 = H.gc;
+    }
+    bool ok = true;
+#pragma unroll 1
+    for (int i = N - 2; i >= 0; i--) {
+      StageLin L;
+      StageHess H;
+      double tg[7];
+      stage_lin(i, L, tg);
+      stage_hess(i, ls, dwv, tg, H);
+      double d[6];
+      if (ls) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = 0.0;
+      } else if (soc) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = -CS[i][k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = -CN[i][k];
+      }
+      const bool cpl = i >= 1;
+      const double cwe = cpl ? cwv : 0.0;
+      // v = P+ d + p+   (rows X, Y, PSI, V, E, DP; d over x, y, psi, v, epsi; cte apart)
+      double vv[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+        vv[r] = pv[r] + Pm[r][0] * d[0] + Pm[r][1] * d[1] + Pm[r][2] * d[2] + Pm[r][3] * d[3] + Pm[r][4] * d[5];
+      const double v4 = p4 + P44 * d[4];
+      // T = P+ G, columns x, y, psi, v, delta, a
+      double T[6][6];
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double pe = Pm[r][2] + Pm[r][4];
+        T[r][0] = Pm[r][0] + L.a61 * Pm[r][4];
+        T[r][1] = Pm[r][1];
+        T[r][2] = L.a13 * Pm[r][0] + L.a23 * Pm[r][1] + pe;
+        T[r][3] = L.a14 * Pm[r][0] + L.a24 * Pm[r][1] + L.a34 * pe + Pm[r][3];
+        T[r][4] = L.b3 * pe + Pm[r][5];
+        T[r][5] = dt * Pm[r][3];
+      }
+      // M = G^T T (upper triangle over x, y, psi, v, delta, a), then + cte rank-1 + stage Hessian
+      double M[6][6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const double te = T[2][c] + T[4][c];
+        M[0][c] = T[0][c] + L.a61 * T[4][c];
+        if (c >= 1) M[1][c] = T[1][c];
+        if (c >= 2) M[2][c] = L.a13 * T[0][c] + L.a23 * T[1][c] + te;
+        if (c >= 3) M[3][c] = L.a14 * T[0][c] + L.a24 * T[1][c] + L.a34 * te + T[3][c];
+        if (c >= 4) M[4][c] = L.b3 * te + T[5][c];
+        if (c >= 5) M[5][c] = dt * T[3][c];
+      }
+      // cte row of G: (a51 [x], -1 [y], a54 [v], a56 [epsi])
+      const double g4x = P44 * L.a51, g4v = P44 * L.a54, g4e = P44 * L.a56;
+      const double Mxx = M[0][0] + g4x * L.a51 + H.qxx;
+      const double Mxy = M[0][1] - g4x;
+      const double Mxp = M[0][2];
+      const double Mxv = M[0][3] + g4x * L.a54;
+      const double Mxe = g4x * L.a56;
+      const double Mxd = M[0][4], Mxa = M[0][5];
+      const double Myy = M[1][1] + P44 + H.qyy;
+      const double Myp = M[1][2];
+      const double Myv = M[1][3] - g4v;
+      const double Mye = -g4e;
+      const double Myd = M[1][4], Mya = M[1][5];
+      const double Mpp = M[2][2] + H.qpp;
+      const double Mpv = M[2][3] + H.qpv;
+      const double Mpd = M[2][4], Mpa = M[2][5];
+      const double Mvv = M[3][3] + g4v * L.a54 + H.qvv;
+      const double Mve = g4v * L.a56 + H.qve;
+      const double Mvd = M[3][4] + H.svd, Mva = M[3][5];
+      const double Mee = g4e * L.a56 + H.qee;
+      const double Mdd = M[4][4] + H.rdd, Mda = M[4][5], Maa = M[5][5] + H.raa;
+      // delta_prev row: only the rate coupling:  M[dp][dp] = cwe, M[dp][delta] = -cwe
+      // m = G^T v + g
+      const double ve = vv[2] + vv[4];
+      const double mx = vv[0] + L.a61 * vv[4] + L.a51 * v4;
+      const double my = vv[1] - v4;
+      const double mp = L.a13 * vv[0] + L.a23 * vv[1] + ve + H.gp;
+      const double mv = L.a14 * vv[0] + L.a24 * vv[1] + L.a34 * ve + vv[3] + L.a54 * v4 + H.gv;
+      const double me = L.a56 * v4 + H.ge;
+      const double mdp = H.gdp;
+      const double md = L.b3 * ve + vv[5] + H.gd;
+      const double ma = dt * vv[3] + H.ga;
+      // 2x2 control pivot
+      const double det = Mdd * Maa - Mda * Mda;
+      ok = ok && (Mdd > 0.0) && (det > 0.0);
+      const double idet = 1.0 / det;
+      const double i11 = Maa * idet, i12 = -Mda * idet, i22 = Mdd * idet;
+      // gains K0 (delta), K1 (a) over columns x, y, psi, v, delta_prev (epsi column is zero)
+      const double cd[5] = {Mxd, Myd, Mpd, Mvd, -cwe};
+      const double ca[5] = {Mxa, Mya, Mpa, Mva, 0.0};
+      double K0[5], K1[5];
+#pragma unroll
+      for (int c = 0; c < 5; c++) {
+        K0[c] = -(i11 * cd[c] + i12 * ca[c]);
+        K1[c] = -(i12 * cd[c] + i22 * ca[c]);
+        KG[i][c] = K0[c];
+        KG[i][5 + c] = K1[c];
+      }
+      const double k0 = -(i11 * md + i12 * ma), k1 = -(i12 * md + i22 * ma);
+      KG[i][10] = k0; KG[i][11] = k1;
+      // Schur complement -> new cost-to-go (index order X, Y, PSI, V, E, DP)
+      Pm[0][0] = Mxx + Mxd * K0[0] + Mxa * K1[0];
+      Pm[0][1] = Mxy + Mxd * K0[1] + Mxa * K1[1];
+      Pm[0][2] = Mxp + Mxd * K0[2] + Mxa * K1[2];
+      Pm[0][3] = Mxv + Mxd * K0[3] + Mxa * K1[3];
+      Pm[0][4] = Mxe;
+      Pm[0][5] = Mxd * K0[4] + Mxa * K1[4];
+      Pm[1][1] = Myy + Myd * K0[1] + Mya * K1[1];
+      Pm[1][2] = Myp + Myd * K0[2] + Mya * K1[2];
+      Pm[1][3] = Myv + Myd * K0[3] + Mya * K1[3];
+      Pm[1][4] = Mye;
+      Pm[1][5] = Myd * K0[4] + Mya * K1[4];
+      Pm[2][2] = Mpp + Mpd * K0[2] + Mpa * K1[2];
+      Pm[2][3] = Mpv + Mpd * K0[3] + Mpa * K1[3];
+      Pm[2][4] = 0.0;
+      Pm[2][5] = Mpd * K0[4] + Mpa * K1[4];
+      Pm[3][3] = Mvv + Mvd * K0[3] + Mva * K1[3];
+      Pm[3][4] = Mve;
+      Pm[3][5] = Mvd * K0[4] + Mva * K1[4];
+      Pm[4][4] = Mee;
+      Pm[4][5] = 0.0;
+      Pm[5][5] = cwe - cwe * K0[4];
+#pragma unroll
+      for (int r = 1; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < r; c++) Pm[r][c] = Pm[c][r];
+      }
+      pv[0] = mx + Mxd * k0 + Mxa * k1;
+      pv[1] = my + Myd * k0 + Mya * k1;
+      pv[2] = mp + Mpd * k0 + Mpa * k1;
+      pv[3] = mv + Mvd * k0 + Mva * k1;
+      pv[4] = me;
+      pv[5] = mdp - cwe * k0;
+      P44 = H.qcc;
+      p4 = H.gc;
+    }
+    return ok;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slot 4a: forward sweep -> primal step
+  // ------------------------------------------------------------------------------------------
+  __device__ void forward(bool ls, bool soc) {
+    const double dt = PC[LC_DT];
+    double t[6], dp = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) t[k] = ls ? 0.0 : (soc ? -cs0[k] : -c0[k]);
+#pragma unroll 1
+    for (int i = 0; i < N - 1; i++) {
+      double kg[12];
+#pragma unroll
+      for (int k = 0; k < 12; k++) kg[k] = KG[i][k];
+      const double u0 = kg[10] + kg[0] * t[0] + kg[1] * t[1] + kg[2] * t[2] + kg[3] * t[3] + kg[4] * dp;
+      const double u1 = kg[11] + kg[5] * t[0] + kg[6] * t[1] + kg[7] * t[2] + kg[8] * t[3] + kg[9] * dp;
+#pragma unroll
+      for (int k = 0; k < 6; k++) DS[i][k] = t[k];
+      DU[i][0] = u0; DU[i][1] = u1;
+      StageLin L;
+      double tg[7];
+      stage_lin(i, L, tg);
+      double d[6];
+      if (ls) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = 0.0;
+      } else if (soc) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = -CS[i][k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = -CN[i][k];
+      }
+      const double n0 = t[0] + L.a13 * t[2] + L.a14 * t[3] + d[0];
+      const double n1 = t[1] + L.a23 * t[2] + L.a24 * t[3] + d[1];
+      const double n2 = t[2] + L.a34 * t[3] + L.b3 * u0 + d[2];
+      const double n3 = t[3] + dt * u1 + d[3];
+      const double n4 = L.a51 * t[0] - t[1] + L.a54 * t[3] + L.a56 * t[5] + d[4];
+      const double n5 = L.a61 * t[0] + t[2] + L.a34 * t[3] + L.b3 * u0 + d[5];
+      t[0] = n0; t[1] = n1; t[2] = n2; t[3] = n3; t[4] = n4; t[5] = n5;
+      dp = u0;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) DS[N - 1][k] = t[k];
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slot 4b: backward costate recursion -> new multipliers, fused with the step-length ratios
+  // (fraction to the boundary for x and z) and grad(phi_mu)^T dx
+  // ------------------------------------------------------------------------------------------
+  __device__ void costate_and_ratios(bool ls, double dwv) {
+    const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    double ln[6] = {0, 0, 0, 0, 0, 0};
+    double rmax = 0.0;             // max over bounds of  -dx/(x-lo)  or  dx/(hi-x)
+    double zn = 1.0, zd = 0.0;     // running minimum of z / (-dz) as a fraction zn / zd (zd > 0)
+    double acc = 0.0, dnext = 0.0, lmax = 0.0;
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; i--) {
+      const bool hasu = i < N - 1;
+      StageLin L;
+      StageHess H;
+      double tg[7] = {0, 0, 0, 0, 0, 0, 0};
+      if (hasu) stage_lin(i, L, tg);
+      stage_hess(i, ls, dwv, tg, H);
+      double ds[6], du0 = 0.0, du1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) ds[k] = DS[i][k];
+      if (hasu) { du0 = DU[i][0]; du1 = DU[i][1]; }
+      double h[6];
+      h[0] = H.qxx * ds[0];
+      h[1] = H.qyy * ds[1];
+      h[2] = H.qpp * ds[2] + H.qpv * ds[3] + H.gp;
+      h[3] = H.qpv * ds[2] + H.qvv * ds[3] + H.qve * ds[5] + H.gv + H.svd * du0;
+      h[4] = H.qcc * ds[4] + H.gc;
+      h[5] = H.qve * ds[3] + H.qee * ds[5] + H.ge;
+      double out[6];
+      if (hasu) {
+        const double l25 = ln[2] + ln[5];
+        out[0] = ln[0] + L.a51 * ln[4] + L.a61 * ln[5] - h[0];
+        out[1] = ln[1] - ln[4] - h[1];
+        out[2] = L.a13 * ln[0] + L.a23 * ln[1] + l25 - h[2];
+        out[3] = L.a14 * ln[0] + L.a24 * ln[1] + L.a34 * l25 + ln[3] + L.a54 * ln[4] - h[3];
+        out[4] = -h[4];
+        out[5] = L.a56 * ln[4] - h[5];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) out[k] = -h[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) { LN[i][k] = out[k]; ln[k] = out[k]; lmax = nanmax(lmax, fabs(out[k])); }
+      if (!ls) {
+        const double v = S[i][3];
+        acc += (wv2 * (v - vref(i)) + nv2(i) * v) * ds[3] + wc2(i) * S[i][4] * ds[4] + we2(i) * S[i][5] * ds[5];
+        if (hasu) {
+          const double d0 = U[i][0];
+          double gd = wd2 * d0;
+          if (i >= 1) gd += cw * (d0 - U[i - 1][0]);
+          if (i <= N - 3) gd -= cw * (dnext - d0);
+          acc += gd * du0;
+          dnext = d0;
+        }
+        const double dx[4] = {ds[2], ds[3], du0, du1};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (k < 2 || hasu) {
+            const double il = IL[i][k], iu = IU[i][k], zl = ZL[i][k], zu = ZU[i][k];
+            acc += mu * (iu - il) * dx[k];
+            rmax = fmax(rmax, fmax(-dx[k] * il, dx[k] * iu));
+            const double dzl = (mu - zl * dx[k]) * il - zl;
+            const double dzu = (mu + zu * dx[k]) * iu - zu;
+            // z/(-dz) < zn/zd  <=>  z*zd < zn*(-dz)   (all denominators positive)
+            if (dzl < 0.0 && (zd == 0.0 || zl * zd < zn * (-dzl))) { zn = zl; zd = -dzl; }
+            if (dzu < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu))) { zn = zu; zd = -dzu; }
+          }
+        }
+      }
+    }
+    lsq_lmax = lmax;
+    gbd_new = acc;
+    if (ls) return;
+    // alpha_max = min(1, tau / rmax),  alpha_z = min(1, tau * zn / zd)
+    alpha_soc = (rmax * 1.0 > tau) ? tau / rmax : 1.0;
+    alpha_z = (zd > 0.0 && tau * zn < zd) ? tau * zn / zd : 1.0;
+  }
+
+  // ---- filter (Ipopt's FilterLSAcceptor) ---------------------------------------------------------
+  __device__ __forceinline__ static bool cmp_le(double lhs, double rhs, double basis) {
+    return lhs - rhs <= 10.0 * K_EPS * fabs(basis);
+  }
+  __device__ __forceinline__ bool is_ftype(double a) const { return ls_gbd < 0.0 && a * pow_gbd > pow_theta; }
+  __device__ __forceinline__ bool armijo(double a, double phi_t) const {
+    return cmp_le(phi_t - ls_phi, K_ETA_PHI * a * ls_gbd, ls_phi);
+  }
+  __device__ bool ls_accept(double a, double theta_t, double phi_t) const {
+    if (!(theta_t == theta_t) || !(phi_t == phi_t) || isinf(phi_t)) return false;
+    if (theta_t > theta_max) return false;
+    bool ok;
+    if (a > 0.0 && is_ftype(a) && ls_theta <= theta_min) {
+      ok = armijo(a, phi_t);
+    } else {
+      ok = cmp_le(theta_t, (1.0 - K_GAMMA_THETA) * ls_theta, ls_theta) ||
+           cmp_le(phi_t - ls_phi, -K_GAMMA_PHI * ls_theta, ls_phi);
+    }
+    if (!ok) return false;
+    for (int k = 0; k < nfilt; k++) {
+      const double f_t = FLT[2 * k], f_p = FLT[2 * k + 1];
+      if (!(cmp_le(theta_t, f_t, f_t) || cmp_le(phi_t, f_p, f_p))) return false;
+    }
+    return true;
+  }
+  __device__ void filter_add(double th, double ph) {
+    int k = 0;
+    for (int j = 0; j < nfilt; j++) {
+      const double f_t = FLT[2 * j], f_p = FLT[2 * j + 1];
+      if (!(f_t >= th && f_p >= ph)) { FLT[2 * k] = f_t; FLT[2 * k + 1] = f_p; k++; }
+    }
+    if (k == K_NFILT) {   // full: drop the oldest entry
+      for (int j = 1; j < k; j++) { FLT[2 * (j - 1)] = FLT[2 * j]; FLT[2 * (j - 1) + 1] = FLT[2 * j + 1]; }
+      k--;
+    }
+    FLT[2 * k] = th; FLT[2 * k + 1] = ph;
+    nfilt = k + 1;
+  }
+
+  // Ipopt's convergence tests and monotone barrier update at the (new) iterate; sets mode
+  __device__ void check_and_update_mu(const KParams &P) {
+    const double sf = PC[LC_SF];
+    const int nz = 4 * N + 4 * (N - 1), m = 6 * N;
+    const double sd = fmax(K_S_MAX, (lam1 + z1) / (double)(m + nz)) / K_S_MAX;
+    const double sc = fmax(K_S_MAX, z1 / (double)nz) / K_S_MAX;
+    const double compl0 = compl_err(0.0);
+    const double E0 = nanmax(dinf / sd, nanmax(cviol, compl0 / sc));
+    const double dinf_u = dinf / sf, compl_u = compl0 / sf;
+    if (E0 <= P.tol && dinf_u <= K_DUAL_INF_TOL && cviol <= K_CONSTR_VIOL_TOL && compl_u <= K_COMPL_INF_TOL) {
+      status = 1; mode = LM_FINISH; return;
+    }
+    if (E0 <= K_ACCEPT_TOL && cviol <= K_ACCEPT_CONSTR_VIOL_TOL && compl_u <= K_ACCEPT_COMPL_INF_TOL) {
+      if (++accept_cnt >= K_ACCEPT_ITER) { status = 4; mode = LM_FINISH; return; }
+    } else {
+      accept_cnt = 0;
+    }
+    if (!(E0 == E0)) { status = 11; mode = LM_FINISH; return; }
+    if (iter >= P.max_iter) { status = 2; mode = LM_FINISH; return; }
+    for (;;) {
+      const double cm = compl_err(mu);
+      const double Emu = nanmax(dinf / sd, nanmax(cviol, cm / sc));
+      if (!(Emu <= K_KAPPA_EPS * mu)) break;
+      const double mu_min = fmin(P.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0);
+      const double new_mu = fmax(mu_min, fmin(K_KAPPA_MU * mu, mu * sqrt(mu)));
+      if (new_mu == mu) break;
+      mu = new_mu;
+      tau = fmax(K_TAU_MIN, 1.0 - mu);
+      nfilt = 0;
+    }
+    dw = 0.0;
+    mode = LM_NEWTON;
+  }
+
+  // honor_original_bounds, unscaled objective, outputs of MPC.cpp:306-324
+  __device__ void write_outputs(const KParams &P) {
+    const size_t B = (size_t)P.B;
+    const double cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    double fl = 0.0, dprev = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+      const bool hasu = i < N - 1;
+      double s[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) s[k] = S[i][k];
+      s[2] = fmin(fmax(s[2], PC[LC_LO0]), PC[LC_HI0]);
+      s[3] = fmin(fmax(s[3], PC[LC_LO0 + 1]), PC[LC_HI0 + 1]);
+      const double dv = s[3] - vref(i);
+      fl += 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + wv2 * dv * dv + nv2(i) * s[3] * s[3]);
+      double u0 = 0.0, u1 = 0.0;
+      if (hasu) {
+        u0 = fmin(fmax(U[i][0], PC[LC_LO0 + 2]), PC[LC_HI0 + 2]);
+        u1 = fmin(fmax(U[i][1], PC[LC_LO0 + 3]), PC[LC_HI0 + 3]);
+        fl += 0.5 * wd2 * u0 * u0;
+        if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * cw * dd * dd; }
+        dprev = u0;
+      }
+      if (i == 1) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) P.result[(size_t)k * B + b] = s[k];
+      }
+      if (i == 0) { P.result[6 * B + b] = u0; P.result[7 * B + b] = u1; }
+      if (P.traj_x) P.traj_x[(size_t)i * B + b] = s[0];
+      if (P.traj_y) P.traj_y[(size_t)i * B + b] = s[1];
+      if (P.full) {
+        const int Nf = P.Nmax;
+#pragma unroll
+        for (int k = 0; k < 6; k++) P.full[(size_t)(k * Nf + i) * B + b] = s[k];
+        if (hasu) {
+          P.full[(size_t)(6 * Nf + i) * B + b] = u0;
+          P.full[(size_t)(7 * Nf - 1 + i) * B + b] = u1;
+        }
+      }
+    }
+    P.result[8 * B + b] = fl / PC[LC_SF];
+    if (P.status) P.status[b] = status;
+    if (P.iters) P.iters[b] = iter;
+  }
+
+  // CS = a * (first ? CN : CS) + CT     (Ipopt's accumulated second-order-correction rhs)
+  __device__ void soc_rhs(bool first, double a) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) cs0[k] = a * (first ? c0[k] : cs0[k]) + c0t[k];
+#pragma unroll 1
+    for (int i = 0; i < N - 1; i++) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) CS[i][k] = a * (first ? CN[i][k] : CS[i][k]) + CT[i][k];
+    }
+  }
+};
+
+// Persistent grid; every lane pulls problems from the global counter until the batch is exhausted.
+template <int NS>
+__global__ void __launch_bounds__(128) mpc_lane_kernel(const KParams P) {
+  Lane<NS> Z;
+  Z.mode = LM_IDLE;
+  Z.b = 0;
+  for (;;) {
+    // ---- slot 0: retire / fetch
+    if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
+    if (Z.mode == LM_IDLE) {
+      const int nb = atomicAdd(P.counter, 1);
+      if (nb < P.B) Z.init(P, nb); else Z.mode = LM_DONE;
+    }
+    if (__all_sync(0xffffffffu, Z.mode == LM_DONE)) break;
+
+    // ---- slot 1: evaluate a point
+    const int m1 = Z.mode;
+    if (m1 == LM_EV0 || m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
+      const double a = m1 == LM_EV0 ? 0.0 : (m1 == LM_TRIAL ? Z.alpha : Z.alpha_soc);
+      Z.eval_sweep(a);
+    }
+
+    // ---- slot 2: acceptance logic, iterate update, KKT errors, barrier update
+    bool upd = false, err = false, take_lsq = false, lsq_bad = false;
+    if (m1 == LM_EV0) {
+      Z.alpha = 0.0; Z.alpha_z = 0.0;
+      Z.theta_max = 1e4 * fmax(1.0, Z.tht);
+      Z.theta_min = 1e-4 * fmax(1.0, Z.tht);
+      upd = true;
+    } else if (m1 == LM_LSQ_DONE) {
+      err = true; take_lsq = true;
+      lsq_bad = !(Z.lsq_lmax <= K_CONSTR_MULT_INIT_MAX);
+    } else if (m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
+      const double phi_t = Z.ft - Z.mu * Z.lt;
+      if (m1 == LM_TRIAL) Z.alpha_test = Z.alpha;
+      if (Z.ls_accept(Z.alpha_test, Z.tht, phi_t)) {
+        if (m1 == LM_SOC_TRIAL) Z.alpha = Z.alpha_soc;
+        if (!Z.is_ftype(Z.alpha_test) || !Z.armijo(Z.alpha_test, phi_t))
+          Z.filter_add((1.0 - K_GAMMA_THETA) * Z.ls_theta, Z.ls_phi - K_GAMMA_PHI * Z.ls_theta);
+        upd = true; err = true;
+      } else if (m1 == LM_TRIAL) {
+        if (Z.ntrial == 0 && Z.tht >= Z.ls_theta) {
+          // second-order correction (Ipopt max_soc = 4): same matrix, corrected constraint rhs
+          Z.soc_cnt = 0;
+          Z.theta_soc_old = Z.tht;
+          Z.soc_rhs(true, Z.alpha);
+          Z.mode = LM_SOC;
+        } else {
+          Z.alpha *= 0.5;
+          Z.ntrial++;
+          if (Z.alpha < Z.alpha_min) { Z.status = 9; Z.mode = LM_FINISH; }   // Ipopt would enter restoration
+        }
+      } else {   // rejected SOC trial
+        Z.soc_cnt++;
+        if (Z.soc_cnt < K_MAX_SOC && Z.tht <= K_KAPPA_SOC * Z.theta_soc_old) {
+          Z.theta_soc_old = Z.tht;
+          Z.soc_rhs(false, Z.alpha_soc);
+          Z.mode = LM_SOC;
+        } else {
+          Z.mode = LM_RESOLVE;
+        }
+      }
+    }
+    if (upd || err) {
+      Z.update_and_errors(upd, take_lsq, lsq_bad);
+      if (upd) { Z.fx = Z.ft; Z.lsum = Z.lt; Z.theta = Z.tht; }
+      if (m1 == LM_EV0) {
+        Z.mode = LM_LSQ;
+      } else {
+        if (m1 != LM_LSQ_DONE) Z.iter++;
+        Z.check_and_update_mu(P);
+      }
+    }
+
+    // ---- slot 3 + 4: factor and solve
+    const int m3 = Z.mode;
+    if (m3 == LM_LSQ || m3 == LM_NEWTON || m3 == LM_SOC || m3 == LM_RESOLVE) {
+      const bool ls = m3 == LM_LSQ, soc = m3 == LM_SOC;
+      const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? Z.dw : Z.dw_used);
+      bool ok = Z.riccati(ls, soc, dwv);
+      if (m3 == LM_NEWTON && !ok) {
+        // Ipopt's inertia correction schedule (delta_w)
+        double d = Z.dw;
+        if (d == 0.0) d = (Z.dw_last == 0.0) ? K_DW_FIRST : fmax(K_DW_MIN, Z.dw_last * K_DW_DEC);
+        else d = (Z.dw_last == 0.0) ? d * K_DW_INC_FIRST : d * K_DW_INC;
+        Z.dw = d;
+        if (d > K_DW_MAX) { Z.status = 10; Z.mode = LM_FINISH; }
+      } else {
+        Z.forward(ls, soc);
+        Z.costate_and_ratios(ls, dwv);
+        if (m3 == LM_LSQ) {
+          Z.mode = LM_LSQ_DONE;
+        } else if (m3 == LM_NEWTON) {
+          if (Z.dw > 0.0) Z.dw_last = Z.dw;
+          Z.dw_used = Z.dw;
+          Z.alpha = Z.alpha_soc;   // alpha_max
+          Z.ls_gbd = Z.gbd_new;
+          Z.ls_theta = Z.theta;
+          Z.ls_phi = Z.fx - Z.mu * Z.lsum;
+          Z.pow_gbd = Z.ls_gbd < 0.0 ? pow(-Z.ls_gbd, K_S_PHI) : 0.0;
+          Z.pow_theta = pow(Z.ls_theta, K_S_THETA);
+          double amin_ = K_GAMMA_THETA;
+          if (Z.ls_gbd < 0.0) {
+            amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * Z.ls_theta / (-Z.ls_gbd));
+            if (Z.ls_theta <= Z.theta_min) amin_ = fmin(amin_, Z.pow_theta / Z.pow_gbd);
+          }
+          Z.alpha_min = amin_ * K_ALPHA_MIN_FRAC;
+          Z.ntrial = 0;
+          Z.mode = LM_TRIAL;
+        } else if (m3 == LM_SOC) {
+          Z.mode = LM_SOC_TRIAL;
+        } else {   // LM_RESOLVE: the uncorrected direction is back; continue backtracking
+          Z.alpha *= 0.5;
+          Z.ntrial++;
+          Z.mode = (Z.alpha < Z.alpha_min) ? LM_FINISH : LM_TRIAL;
+          if (Z.mode == LM_FINISH) Z.status = 9;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mpcb200

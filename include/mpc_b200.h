@@ -24,7 +24,7 @@ extern "C" {
                               (Config::maxFitOrder = 5 => order <= 4, RoadGeometry.cpp:27-34) */
 #define MPC_NTAB 16        /* capacity of the steers / steer-speeds tables (9 in config-*.json) */
 #define MPC_NWEIGHTS 12    /* Config::weights, indices Config.h:14-61 */
-#define MPC_NMAX 32        /* maximum horizon N handled by the sm_100a kernel in this round */
+#define MPC_NMAX 64        /* maximum horizon N (the reference's examples/ grid goes to N = 50) */
 
 /* error codes */
 #define MPC_OK 0
@@ -131,6 +131,16 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
                          const double *weights, const int *N_per, const double *dt_per,
                          double *result, double *traj_x, double *traj_y, double *full,
                          int *status, int *iters);
+
+/* Kernel selection.  MPC_KERNEL_AUTO (default): batches of at least MPC_LANE_MIN_BATCH problems, or
+ * horizons above 32, run the throughput kernel (one problem per lane); smaller batches run the
+ * latency kernel (one problem per warp).  lane_threads (32..128, multiple of 32; 0 = keep) and
+ * lane_ctas_per_sm (0 = as many as fit) tune the persistent grid of the lane kernel. */
+#define MPC_KERNEL_AUTO 0
+#define MPC_KERNEL_WARP 1
+#define MPC_KERNEL_LANE 2
+#define MPC_LANE_MIN_BATCH 1024
+int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm);
 
 /* One problem, host pointers: state[6], coeffs[5] -> result[9], traj_x/traj_y[N] (or NULL).
  * What `MPC::solve` calls once per telemetry message. */
