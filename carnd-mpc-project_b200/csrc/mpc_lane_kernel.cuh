@@ -41,16 +41,16 @@ enum { LC_DT = 0, LC_DTLF, LC_SF, LC_CW, LC_WC2, LC_WE2, LC_WV2, LC_VREF, LC_WD2
        LC_VREF_0, LC_NV2_0, LC_C0, LC_S0 = LC_C0 + 5, LC_LO = LC_S0 + 6, LC_HI = LC_LO + 4,
        LC_LO0 = LC_HI + 4, LC_HI0 = LC_LO0 + 4, LC_SIZE = LC_HI0 + 4 };
 
-__device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
 
 template <int NS>
 struct Lane {
   // ---- per-stage data (thread-private memory) ----
   double S[NS][6], U[NS][2], LAM[NS][6], ZL[NS][4], ZU[NS][4], IL[NS][4], IU[NS][4];
-  double TG[NS][7], CN[NS][6];            // trig/poly and c_{i+1} at the iterate
+  double TG[NS][8], CN[NS][6];            // sin/cos psi, sin/cos epsi, f', f'', a61, g3 and c_{i+1} at the iterate
   double DS[NS][6], DU[NS][2], LN[NS][6]; // search direction and new multipliers
   double KG[NS][12];                      // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
-  double TT[NS][7], CT[NS][6];            // trig/poly and residuals at the trial point
+  double TT[NS][8], CT[NS][6];            // the same at the trial point
   double CS[NS][6];                       // second-order-correction right-hand side
   double PC[LC_SIZE];
   double FLT[2 * K_NFILT];
@@ -190,7 +190,11 @@ struct Lane {
         const double f1 = ((4.0 * c4_ * x + 3.0 * c3_) * x + 2.0 * c2_) * x + c1_;
         const double f2 = (12.0 * c4_ * x + 6.0 * c3_) * x + 2.0 * c2_;
         const double f3 = 24.0 * c4_ * x + 6.0 * c3_;
-        TT[i][0] = sp; TT[i][1] = cp; TT[i][2] = se; TT[i][3] = ce; TT[i][4] = f1; TT[i][5] = f2; TT[i][6] = f3;
+        // d/dx of -atan(f') and its derivative (row epsi of App. A.4), once per point
+        const double q = fma(f1, f1, 1.0), iq = __drcp_rn(q);
+        TT[i][0] = sp; TT[i][1] = cp; TT[i][2] = se; TT[i][3] = ce; TT[i][4] = f1; TT[i][5] = f2;
+        TT[i][6] = -f2 * iq;
+        TT[i][7] = (f3 * q - 2.0 * f1 * f2 * f2) * iq * iq;
         const double vdt = s[3] * dt;
         F[0] = s[0] + cp * vdt;
         F[1] = s[1] + sp * vdt;
@@ -215,6 +219,7 @@ struct Lane {
   __device__ void update_and_errors(bool do_update, bool take_lsq, bool lsq_bad) {
     const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     const double a = alpha, az = alpha_z;
+    const double zcap = K_KAPPA_SIGMA * mu, zfloor = mu / K_KAPPA_SIGMA;   // Ipopt's kappa_sigma safeguard
     double ln[6] = {0, 0, 0, 0, 0, 0};
     double dnext = 0.0;
     double r = 0.0, cv = 0.0, l1 = 0.0, zz = 0.0, am = 1e300, aM = 0.0;
@@ -233,7 +238,7 @@ struct Lane {
       if (hasu) { u[0] = U[i][0]; u[1] = U[i][1]; }
 #pragma unroll
       for (int k = 0; k < 4; k++) { zl[k] = ZL[i][k]; zu[k] = ZU[i][k]; }
-      double tg[7];
+      double tg[8];
       if (do_update) {
         double dx[4];
         dx[0] = DS[i][2]; dx[1] = DS[i][3]; dx[2] = hasu ? DU[i][0] : 0.0; dx[3] = hasu ? DU[i][1] : 0.0;
@@ -245,7 +250,7 @@ struct Lane {
 #pragma unroll
           for (int k = 0; k < 6; k++) CN[i][k] = CT[i][k];
 #pragma unroll
-          for (int k = 0; k < 7; k++) { tg[k] = TT[i][k]; TG[i][k] = tg[k]; }
+          for (int k = 0; k < 8; k++) { tg[k] = TT[i][k]; TG[i][k] = tg[k]; }
         }
         const double xv[4] = {s[2], s[3], u[0], u[1]};
 #pragma unroll
@@ -256,9 +261,9 @@ struct Lane {
             const double dzu = (mu + zu[k] * dx[k]) * iu - zu[k];
             const double iln = rcp(xv[k] - PC[LC_LO + k]), iun = rcp(PC[LC_HI + k] - xv[k]);
             double t = zl[k] + az * dzl;
-            zl[k] = fmax(fmin(t, K_KAPPA_SIGMA * mu * iln), mu * iln / K_KAPPA_SIGMA);
+            zl[k] = fmax(fmin(t, zcap * iln), zfloor * iln);
             t = zu[k] + az * dzu;
-            zu[k] = fmax(fmin(t, K_KAPPA_SIGMA * mu * iun), mu * iun / K_KAPPA_SIGMA);
+            zu[k] = fmax(fmin(t, zcap * iun), zfloor * iun);
             IL[i][k] = iln; IU[i][k] = iun; ZL[i][k] = zl[k]; ZU[i][k] = zu[k];
           }
         }
@@ -269,7 +274,7 @@ struct Lane {
         }
         if (hasu) {
 #pragma unroll
-          for (int k = 0; k < 7; k++) tg[k] = TG[i][k];
+          for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
         }
       }
       // ---- optimality error terms
@@ -279,7 +284,7 @@ struct Lane {
         const double vdt = v * dt;
         const double a13 = -vdt * tg[0], a14 = dt * tg[1], a23 = vdt * tg[1], a24 = dt * tg[0];
         const double a34 = u[0] * dtLf, b3 = v * dtLf, a51 = tg[4], a54 = dt * tg[2], a56 = vdt * tg[3];
-        const double a61 = -tg[5] / (1.0 + tg[4] * tg[4]);
+        const double a61 = tg[6];
         const double l25 = ln[2] + ln[5];
         os[0] = ln[0] + a51 * ln[4] + a61 * ln[5];
         os[1] = ln[1] - ln[4];
@@ -342,11 +347,11 @@ struct Lane {
   __device__ __forceinline__ void stage_lin(int i, StageLin &L, double *tg) const {
     const double dt = PC[LC_DT], dtLf = PC[LC_DTLF];
 #pragma unroll
-    for (int k = 0; k < 7; k++) tg[k] = TG[i][k];
+    for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
     const double v = S[i][3], vdt = v * dt;
     L.a13 = -vdt * tg[0]; L.a14 = dt * tg[1]; L.a23 = vdt * tg[1]; L.a24 = dt * tg[0];
     L.a34 = U[i][0] * dtLf; L.b3 = v * dtLf; L.a51 = tg[4]; L.a54 = dt * tg[2]; L.a56 = vdt * tg[3];
-    L.a61 = -tg[5] / (1.0 + tg[4] * tg[4]);
+    L.a61 = tg[6];
   }
   // Hessian of the Lagrangian + barrier Sigma + dw on the primal diagonal, gradient of the barrier
   // objective.  ls: the least-squares multiplier system (Hessian = I, gradient = grad f - zl + zu).
@@ -391,8 +396,7 @@ struct Lane {
 #pragma unroll
       for (int k = 0; k < 6; k++) ln[k] = LAM[i + 1][k];
       const double vdt = v * dt;
-      const double q = 1.0 + tg[4] * tg[4], iq = 1.0 / q;
-      H.qxx = -ln[4] * tg[5] + ln[5] * (tg[6] * q - 2.0 * tg[4] * tg[5] * tg[5]) * iq * iq + dwv;
+      H.qxx = -ln[4] * tg[5] + ln[5] * tg[7] + dwv;
       H.qpp = (ln[0] * tg[1] + ln[1] * tg[0]) * vdt + sig[0] + dwv;
       H.qpv = (ln[0] * tg[0] - ln[1] * tg[1]) * dt;
       H.qve = -ln[4] * tg[3] * dt;
@@ -418,7 +422,7 @@ struct Lane {
     double Pm[6][6], pv[6], P44, p4;
     {
       StageHess H;
-      double tg[7] = {0, 0, 0, 0, 0, 0, 0};
+      double tg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       stage_hess(N - 1, ls, dwv, tg, H);
 #pragma unroll
       for (int r = 0; r < 6; r++) {
@@ -435,7 +439,7 @@ struct Lane {
     for (int i = N - 2; i >= 0; i--) {
       StageLin L;
       StageHess H;
-      double tg[7];
+      double tg[8];
       stage_lin(i, L, tg);
       stage_hess(i, ls, dwv, tg, H);
       double d[6];
@@ -589,7 +593,7 @@ struct Lane {
       for (int k = 0; k < 6; k++) DS[i][k] = t[k];
       DU[i][0] = u0; DU[i][1] = u1;
       StageLin L;
-      double tg[7];
+      double tg[8];
       stage_lin(i, L, tg);
       double d[6];
       if (ls) {
@@ -630,7 +634,7 @@ struct Lane {
       const bool hasu = i < N - 1;
       StageLin L;
       StageHess H;
-      double tg[7] = {0, 0, 0, 0, 0, 0, 0};
+      double tg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (hasu) stage_lin(i, L, tg);
       stage_hess(i, ls, dwv, tg, H);
       double ds[6], du0 = 0.0, du1 = 0.0;
@@ -825,8 +829,8 @@ struct Lane {
 };
 
 // Persistent grid; every lane pulls problems from the global counter until the batch is exhausted.
-template <int NS>
-__global__ void __launch_bounds__(128) mpc_lane_kernel(const KParams P) {
+template <int NS, int MINB>
+__global__ void __launch_bounds__(128, MINB) mpc_lane_kernel(const KParams P) {
   Lane<NS> Z;
   Z.mode = LM_IDLE;
   Z.b = 0;
@@ -887,6 +891,11 @@ __global__ void __launch_bounds__(128) mpc_lane_kernel(const KParams P) {
         }
       }
     }
+    // one copy of the sweep for every path: keep the compiler from cloning it per state (a clone run
+    // by two or three lanes costs the warp a full pass)
+    int flags = (upd ? 1 : 0) | (err ? 2 : 0) | (take_lsq ? 4 : 0) | (lsq_bad ? 8 : 0);
+    asm volatile("" : "+r"(flags));
+    upd = flags & 1; err = flags & 2; take_lsq = flags & 4; lsq_bad = flags & 8;
     if (upd || err) {
       Z.update_and_errors(upd, take_lsq, lsq_bad);
       if (upd) { Z.fx = Z.ft; Z.lsum = Z.lt; Z.theta = Z.tht; }

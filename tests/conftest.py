@@ -46,11 +46,19 @@ def stable_cfg(mpc, refdata):
     return mpc.config_from_json_text(json.dumps(refdata["configs"]["stable"]))
 
 
+@pytest.fixture(scope="session", params=[1, 2], ids=["warp-kernel", "lane-kernel"])
+def kernel_kind(request):
+    """Both CUDA kernels are held to the same parity bar: 1 = one problem per warp (latency path),
+    2 = one problem per lane (throughput path)."""
+    return request.param
+
+
 @pytest.fixture(scope="session")
-def solver(mpc, stable_cfg):
+def solver(mpc, stable_cfg, kernel_kind):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     s = mpc.Solver(stable_cfg, 0)
+    s.set_kernel(kernel_kind)
     yield s
     s.close()

@@ -81,7 +81,7 @@ def test_no_cpu_fallback(mpc, stable_cfg):
 
 def test_create_rejects_bad_config(mpc, stable_cfg):
     import copy
-    for field, val in [("N", 1), ("N", 33), ("dt", 0.0), ("Lf", -1.0), ("n_steer_speeds", 0)]:
+    for field, val in [("N", 1), ("N", mpc.NMAX + 1), ("dt", 0.0), ("Lf", -1.0), ("n_steer_speeds", 0)]:
         c = mpc.MpcConfig.from_buffer_copy(stable_cfg)
         setattr(c, field, val)
         with pytest.raises(mpc.MpcError, match="MPC_EINVAL"):

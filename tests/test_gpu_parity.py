@@ -66,25 +66,31 @@ def test_batch_vs_oracle(solver, mpc, po, stable_cd, seed, B):
 
 
 @pytest.mark.parametrize("name", ["fast", "no-latency"])
-def test_other_shipped_configs(mpc, po, refdata, name):
+def test_other_shipped_configs(mpc, po, refdata, name, kernel_kind):
     cfg = mpc.config_from_json_text(json.dumps(refdata["configs"][name]))
     cd = po.load_config_dict(refdata["configs"][name])
     b = mpc.workloads.batch_perturbed_states(512, 21, cd)
     S = mpc.Solver(cfg, 0)
+    S.set_kernel(kernel_kind)
     g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
     S.close()
     c = po.solve_batch(po.make_config(cd), po.problems_from_arrays(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"]), 16)
     _assert_parity(g, c)
 
 
-@pytest.mark.parametrize("N,dt", [(2, 0.1), (3, 0.1), (10, 0.05), (10, 0.02), (20, 0.05), (25, 0.025), (30, 0.02), (32, 0.05)])
-def test_horizon_and_timestep_grid(mpc, po, refdata, N, dt):
-    """N x dt cells of the reference's examples/ grid that fit one lane per stage (N <= 32)."""
+@pytest.mark.parametrize("N,dt", [(2, 0.1), (3, 0.1), (10, 0.05), (10, 0.02), (11, 0.05), (20, 0.05), (21, 0.05),
+                                  (25, 0.025), (30, 0.02), (32, 0.05), (40, 0.05), (50, 0.02), (64, 0.02)])
+def test_horizon_and_timestep_grid(mpc, po, refdata, N, dt, kernel_kind):
+    """N x dt cells of the reference's examples/ grid (submission-report.md:250-265).  The warp kernel
+    holds one stage per lane (N <= 32); the lane kernel goes to MPC_NMAX = 64."""
+    if kernel_kind == 1 and N > 32:
+        pytest.skip("warp kernel: N <= 32")
     js = dict(refdata["configs"]["stable"], N=N, dt=dt)
     cfg = mpc.config_from_json_text(json.dumps(js))
     cd = po.load_config_dict(js)
     b = mpc.workloads.batch_perturbed_states(96, 31, cd)
     S = mpc.Solver(cfg, 0)
+    S.set_kernel(kernel_kind)
     g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
     S.close()
     c = po.solve_batch(po.make_config(cd), po.problems_from_arrays(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"]), 16)
@@ -120,7 +126,7 @@ def test_per_problem_weights_and_frozen_accel_terms(solver, mpc, po, stable_cd):
         assert g["result"][i, 8] == pytest.approx(r["result"][8], rel=REL_TOL)
 
 
-def test_ragged_per_problem_horizon_and_dt(mpc, po, refdata):
+def test_ragged_per_problem_horizon_and_dt(mpc, po, refdata, kernel_kind):
     """Horizon/timestep sweep (BASELINE config 3) in ONE launch: per-problem N and dt."""
     js = dict(refdata["configs"]["stable"], N=30)
     cfg = mpc.config_from_json_text(json.dumps(js))
@@ -133,6 +139,7 @@ def test_ragged_per_problem_horizon_and_dt(mpc, po, refdata):
     Np = np.array([pairs[k][0] for k in pick], dtype=np.int32)
     dtp = np.array([pairs[k][1] for k in pick])
     S = mpc.Solver(cfg, 0)
+    S.set_kernel(kernel_kind)
     g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"], N_per=Np, dt_per=dtp)
     S.close()
     n_checked = 0
@@ -200,3 +207,57 @@ def test_edge_cases(solver, mpc, stable_cfg, stable_cd):
     # outputs are optional
     out = solver.solve_batch_host(st[2:], co[2:], np.array([-0.1]), np.array([0.1]), want_traj=False)
     assert out["status"][0] == 1
+
+
+def test_auto_dispatch_and_kernels_agree(mpc, stable_cfg, stable_cd):
+    """MPC_KERNEL_AUTO: small batches take the warp kernel, large ones the lane kernel; both give the
+    same optimum (they differ only in the order of the floating-point reductions)."""
+    S = mpc.Solver(stable_cfg, 0)
+    b = mpc.workloads.batch_perturbed_states(2048, 77, stable_cd)
+    args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    auto = S.solve_batch_host(*args)
+    S.set_kernel(mpc.KERNEL_LANE)
+    lane = S.solve_batch_host(*args)
+    S.set_kernel(mpc.KERNEL_WARP)
+    warp = S.solve_batch_host(*args)
+    assert np.array_equal(auto["result"], lane["result"])          # 2048 >= MPC_LANE_MIN_BATCH
+    ok = (lane["status"] == 1) & (warp["status"] == 1)
+    assert ok.mean() > 0.99
+    assert np.abs(lane["result"][ok, :8] - warp["result"][ok, :8]).max() < 1e-5
+    S.set_kernel(mpc.KERNEL_AUTO)
+    small = S.solve_batch_host(*(a[:100] for a in args))
+    assert np.array_equal(small["result"], warp["result"][:100])   # 100 < MPC_LANE_MIN_BATCH
+    # lane grid settings change scheduling only, never results
+    S.set_kernel(mpc.KERNEL_LANE, 64, 3)
+    lane2 = S.solve_batch_host(*args)
+    assert np.array_equal(lane2["result"], lane["result"]) and np.array_equal(lane2["iters"], lane["iters"])
+    with pytest.raises(mpc.MpcError):
+        S.set_kernel(7)
+    S.close()
+
+
+def test_rare_paths_regularisation_and_long_runs(mpc, po, refdata, kernel_kind):
+    """Problems that need Ipopt's inertia correction (delta_w) or many iterations: same answers."""
+    cd = po.load_config_dict(refdata["configs"]["stable"])
+    cfg = mpc.config_from_json_text(json.dumps(refdata["configs"]["stable"]))
+    b = mpc.workloads.batch_perturbed_states(16384, 0, cd)
+    S = mpc.Solver(cfg, 0)
+    S.set_kernel(kernel_kind)
+    g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.close()
+    hard = np.argsort(-g["iters"])[:96]                              # the longest runs of the batch
+    assert g["iters"][hard].min() >= 14
+    sub = {k: b[k][hard] for k in ("state", "coeffs", "yaw_lo", "yaw_hi")}
+    import ctypes as C
+    probs = po.problems_from_arrays(sub["state"], sub["coeffs"], sub["yaw_lo"], sub["yaw_hi"])
+    outs = (po.OrcResult * len(hard))()
+    po.lib().orc_solve_batch(C.byref(po.make_config(cd)), probs, len(hard), outs, 16)
+    n_reg = sum(o.n_regularized for o in outs)
+    assert n_reg > 0                                                  # the inertia-correction path is exercised
+    for k, i in enumerate(hard):
+        o = outs[k]
+        if o.status != 1:
+            continue
+        assert g["status"][i] == 1
+        assert np.abs(g["result"][i, :8] - np.array(o.result[:8])).max() < ABS_TOL
+        assert g["result"][i, 8] == pytest.approx(o.result[8], rel=REL_TOL)
