@@ -271,6 +271,14 @@ def main():
         except Exception:
             pass
         fp64_peak = mpc.measure_fp64_peak(local_rank)
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this batch, from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("batch") == B and tj.get("N") == N:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
+        except Exception:
+            pass
         achieved_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_gbs = BYTES_PER_SOLVE(N) * B / (kernel_ms * 1e-3) / 1e9
@@ -282,7 +290,8 @@ def main():
                        "batch_per_gpu": B, "N": N, "dt": cfg.dt, "l2": "flushed between timed steps (256 MiB write)",
                        "sharding": "independent batch shard per rank, no collective in the solve; one all_gather of result[9][B] per step" if world > 1 else "single GPU"},
             "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "mpc_lane_kernel<10,2> (one problem per lane, persistent grid)" if B >= mpc.LANE_MIN_BATCH else "mpc_ipm_kernel<32> (one problem per warp)",
                          "peak_source": "measured in this run by mpc_measure_fp64_peak (DFMA chains; MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_launch": flops_per_launch, "flops_model": "sum_b iters_b * F_iter(N), F_iter(10)=17505 (SURVEY.md 8d)",
                          "kernel_ms": kernel_ms},
