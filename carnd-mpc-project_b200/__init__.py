@@ -31,7 +31,8 @@ STATUS_NAMES = {0: "not_defined", 1: "success", 2: "maxiter_exceeded", 3: "stop_
 
 EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json", "mpc_create",
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
-           "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel"]
+           "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
+           "mpc_run_prepare", "mpc_run_finish"]
 
 
 class MpcError(RuntimeError):
@@ -66,6 +67,12 @@ class MpcConfig(C.Structure):
             "yaw_changes": list(self.yaw_changes[: self.n_yaw_changes]),
             "yaw_change_speeds": list(self.yaw_change_speeds[: self.n_yaw_change_speeds]),
         }
+
+
+class MpcRunAux(C.Structure):
+    """``mpc_run_aux`` of include/mpc_b200.h."""
+    _fields_ = [("max_yaw_change", C.c_double), ("max_speed", C.c_double), ("target_speed", C.c_double),
+                ("fit_error", C.c_double), ("fit_order", C.c_int)]
 
 
 def build(verbose=False):
@@ -105,6 +112,8 @@ def lib():
     L.mpc_solve_batch_host.argtypes = [vp, C.c_int] + [vp] * 13
     L.mpc_solve_one.argtypes = [vp, dp, dp, C.c_double, C.c_double, dp, dp, dp, ip, ip]
     L.mpc_measure_fp64_peak.argtypes = [C.c_int, dp]
+    L.mpc_run_prepare.argtypes = [cfgp, dp, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, C.POINTER(MpcRunAux)]
+    L.mpc_run_finish.argtypes = [cfgp, C.POINTER(MpcRunAux), C.c_double, dp, dp]
     L.mpc_launch_count.argtypes = [vp]
     L.mpc_launch_count.restype = C.c_longlong
     L.mpc_last_error.restype = C.c_char_p
@@ -145,6 +154,32 @@ def measure_fp64_peak(device=0):
     v = C.c_double(0.0)
     _check(lib().mpc_measure_fp64_peak(device, C.byref(v)), "mpc_measure_fp64_peak")
     return v.value
+
+
+def run_prepare(cfg, pose, ptsx, ptsy, steering=0.0):
+    """MPC::run pre-processing (host): pose (x, y, psi, v) + global waypoints -> dict with the NLP
+    inputs, the vehicle-frame waypoints and the ``mpc_run_aux`` needed by :func:`run_finish`."""
+    dp = C.POINTER(C.c_double)
+    po = np.ascontiguousarray(pose, dtype=np.float64)
+    x = np.array(ptsx, dtype=np.float64)
+    y = np.array(ptsy, dtype=np.float64)
+    st, co = np.zeros(6), np.zeros(NCOEF)
+    lo, hi = C.c_double(0), C.c_double(0)
+    aux = MpcRunAux()
+    _check(lib().mpc_run_prepare(C.byref(cfg), po.ctypes.data_as(dp), float(steering), x.ctypes.data_as(dp),
+                                 y.ctypes.data_as(dp), len(x), st.ctypes.data_as(dp), co.ctypes.data_as(dp),
+                                 C.byref(lo), C.byref(hi), C.byref(aux)), "mpc_run_prepare")
+    return {"state": st, "coeffs": co, "yaw_lo": lo.value, "yaw_hi": hi.value, "aux": aux, "ptsx": x, "ptsy": y}
+
+
+def run_finish(cfg, aux, v, result9):
+    """MPC::run post-processing: -> {x1, y1, psi1, v1, steer in [-1, 1], accel, cte1, epsi1}."""
+    dp = C.POINTER(C.c_double)
+    r = np.ascontiguousarray(result9, dtype=np.float64)
+    out = np.zeros(8)
+    _check(lib().mpc_run_finish(C.byref(cfg), C.byref(aux), float(v), r.ctypes.data_as(dp), out.ctypes.data_as(dp)),
+           "mpc_run_finish")
+    return out
 
 
 def _ptr(t):

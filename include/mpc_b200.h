@@ -148,6 +148,24 @@ int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs,
                   double yaw_lo, double yaw_hi,
                   double *result, double *traj_x, double *traj_y, int *status, int *iters);
 
+/* ---- one control step around the solve: MPC::run (MPC.cpp:327-382), host-side, pure functions ---- */
+#define MPC_MAX_WAYPOINTS 16
+typedef struct mpc_run_aux {
+  double max_yaw_change;   /* MPC.cpp:339 */
+  double max_speed;        /* Vehicle::computeYawChangeSpeedLimit, MPC.cpp:340 */
+  double target_speed;     /* Vehicle::computeSpeedTarget(steering, max_speed), MPC.cpp:342 */
+  double fit_error;        /* sum of squared residuals of the accepted fit, RoadGeometry.cpp:30-33 */
+  int fit_order;           /* 2 .. max_fit_order-1 */
+} mpc_run_aux;
+/* pose = (x, y, psi, v) in the global frame, steering = Vehicle::getSteering().  ptsx/ptsy (3..16
+ * global waypoints) are transformed to the vehicle frame IN PLACE, as MPC.cpp:329 does (mpc_main.cpp
+ * sends them back to the simulator).  Outputs the NLP inputs of mpc_solve_one. */
+int mpc_run_prepare(const mpc_config *cfg, const double *pose, double steering, double *ptsx, double *ptsy,
+                    int npts, double *state, double *coeffs, double *yaw_lo, double *yaw_hi, mpc_run_aux *aux);
+/* result9 of the solve -> MPC::run's return vector {x1, y1, psi1, v1, steer in [-1,1], accel, cte1, epsi1}
+ * (sharp-turn steering adjustment, acceleration clamp, normalisation: MPC.cpp:361-381).  v = pose[3]. */
+int mpc_run_finish(const mpc_config *cfg, const mpc_run_aux *aux, double v, const double *result9, double *out8);
+
 /* Measure the device's FP64 FMA peak with a dependent-chain-free DFMA micro-kernel (8 independent
  * chains per thread, every SM full): the roofline denominator bench.py reports against, since
  * MEASURED_PEAKS.json holds no FP64 figure.  *tflops = 2 * FMAs / seconds / 1e12. */

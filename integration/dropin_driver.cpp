@@ -1,0 +1,34 @@
+// Driver for the drop-in check: the calls of the reference's src/test.cpp:13-111 (Config::load,
+// Vehicle::update, MPC::run, 25 x MPC::solve) written against the REFERENCE'S headers, linked with
+// integration/reference_tree/src/control/MPC.cpp instead of the reference's MPC.cpp.  (test.cpp itself
+// cannot be built here: it includes matplotlibcpp.h, which needs python2.7.)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "control/MPC.h"
+#include "utils/Config.h"
+
+int main(int argc, char **argv) {
+  if (argc < 6 + 12) return 2;
+  MPC mpc;
+  Config::load(argv[1]);
+  Vehicle vehicle;
+  vehicle.setLength(Config::Lf);
+  vehicle.update(atof(argv[2]), atof(argv[3]), atof(argv[4]), atof(argv[5]), 0, 0);
+  std::vector<double> px, py;
+  for (int i = 0; i < 6; i++) { px.push_back(atof(argv[6 + 2 * i])); py.push_back(atof(argv[7 + 2 * i])); }
+  std::vector<double> vars = mpc.run(vehicle, px, py);
+  printf("run");
+  for (double x : vars) printf(" %.17g", x);
+  printf("\n");
+  Eigen::VectorXd state(6);
+  state << vars[0], vars[1], vars[2], vars[3], vars[6], vars[7];
+  for (int k = 0; k < 25; k++) {
+    std::vector<double> s = mpc.solve(state, 40);
+    printf("solve");
+    for (double x : s) printf(" %.17g", x);
+    printf("\n");
+    state << s[0], s[1], s[2], s[3], s[4], s[5];
+  }
+  return 0;
+}

@@ -480,9 +480,9 @@ static void ldl_solve(const ldl_t *f, double *b) {
 #define MACH_EPS 2.220446049250313e-16
 
 typedef struct {
-  const orc_config *cfg;
-  const orc_problem *prob;
-  int N, n, m;
+  const orc_config *cfg;     /* solver options only (tol, max_iter, mu_init, max_soc, obj_scaling) */
+  const orc_nlp *nlp;
+  int n, m;
   double sf;           /* objective scaling factor */
   double *cs;          /* constraint scaling (m) */
   double *xl, *xu;     /* relaxed bounds (n), +-inf as +-HUGE_VAL */
@@ -497,17 +497,17 @@ typedef struct {
   int nzl, nzu;
 } ipm_t;
 
-static double nlp_f(const ipm_t *s, const double *x) { return s->sf * orc_eval_f(s->cfg, s->prob, x); }
+static double nlp_f(const ipm_t *s, const double *x) { return s->sf * s->nlp->f(s->nlp->user, x); }
 static void nlp_c(const ipm_t *s, const double *x, double *c) {
-  orc_eval_g(s->cfg, s->prob, x, c);
+  s->nlp->g(s->nlp->user, x, c);
   for (int j = 0; j < s->m; j++) c[j] = (c[j] - s->gl[j]) * s->cs[j];
 }
 static void nlp_grad(const ipm_t *s, const double *x, double *g) {
-  orc_eval_grad(s->cfg, s->prob, x, g);
+  s->nlp->grad(s->nlp->user, x, g);
   for (int i = 0; i < s->n; i++) g[i] *= s->sf;
 }
 static void nlp_jac(const ipm_t *s, const double *x, double *J) {
-  orc_eval_jac(s->cfg, s->prob, x, J);
+  s->nlp->jac(s->nlp->user, x, J);
   for (int j = 0; j < s->m; j++)
     if (s->cs[j] != 1.0)
       for (int i = 0; i < s->n; i++) J[(size_t)j * s->n + i] *= s->cs[j];
@@ -655,12 +655,17 @@ static void kkt_solve_dir(ipm_t *s, double mu, const double *cvec, double *dx, d
   memcpy(dlam, rhs + n, sizeof(double) * m);
 }
 
-int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
+/* Generic core: minimise f(x) s.t. g(x) = gl (= gu), xl <= x <= xu from the start point xi.
+ * Bounds beyond +-1e19 are "no bound".  Outputs x (clipped to the original bounds), lambda, zl, zu
+ * (unscaled) and the run statistics. */
+int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in, const double *xl_in,
+                  const double *xu_in, const double *gl_in, const double *gu_in, double *x_out,
+                  double *lam_out, double *zl_out, double *zu_out, orc_ipm_stats *out) {
   ipm_t S;
   ipm_t *s = &S;
   memset(s, 0, sizeof(S));
-  int N = cfg->N, n = 8 * N - 2, m = 6 * N;
-  s->cfg = cfg; s->prob = prob; s->N = N; s->n = n; s->m = m;
+  int n = nlp->n, m = nlp->m;
+  s->cfg = cfg; s->nlp = nlp; s->n = n; s->m = m;
   size_t nd = sizeof(double);
   double *pool = (double *)calloc((size_t)(30 * n + 10 * m + (size_t)m * n + (size_t)n * n + (n + m)), nd);
   double *q = pool;
@@ -670,7 +675,7 @@ int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
   s->grad = TAKE(n); s->c = TAKE(m); s->J = TAKE((size_t)m * n); s->H = TAKE((size_t)n * n);
   s->rhs = TAKE(n + m); s->dx = TAKE(n); s->dlam = TAKE(m); s->dzl = TAKE(n); s->dzu = TAKE(n);
   s->xt = TAKE(n); s->ct = TAKE(m); s->csoc = TAKE(m);
-  double *gu = TAKE(m), *xi = TAKE(n), *dx_soc = TAKE(n), *dlam_soc = TAKE(m);
+  double *xi = TAKE(n), *dx_soc = TAKE(n), *dlam_soc = TAKE(m);
 #undef TAKE
   s->has_l = (int *)calloc(2 * (size_t)n, sizeof(int));
   s->has_u = s->has_l + n;
@@ -679,16 +684,21 @@ int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
   memset(out, 0, sizeof(*out));
   int status = ORC_NOT_DEFINED;
 
-  orc_bounds(cfg, prob, s->xl0, s->xu0, s->gl, gu, xi);
+  memcpy(xi, xi_in, nd * n);
+  memcpy(s->xl0, xl_in, nd * n);
+  memcpy(s->xu0, xu_in, nd * n);
+  memcpy(s->gl, gl_in, nd * m);
+  for (int j = 0; j < m; j++)
+    if (gl_in[j] != gu_in[j]) { ldl_free(s->kkt); free(s->has_l); free(pool); return -1; }  /* equalities only */
 
   /* gradient-based NLP scaling at the user start point (nlp_scaling_max_gradient 100) */
   s->sf = 1.0;
   for (int j = 0; j < m; j++) s->cs[j] = 1.0;
   if (cfg->obj_scaling) {
-    orc_eval_grad(cfg, prob, xi, s->grad);
+    nlp->grad(nlp->user, xi, s->grad);
     double gmax = norminf(s->grad, n);
     if (gmax > 100.0) s->sf = fmax(100.0 / gmax, 1e-8);
-    orc_eval_jac(cfg, prob, xi, s->J);
+    nlp->jac(nlp->user, xi, s->J);
     for (int j = 0; j < m; j++) {
       double rmax = norminf(s->J + (size_t)j * n, n);
       if (rmax > 100.0) s->cs[j] = fmax(100.0 / rmax, 1e-8);
@@ -807,7 +817,7 @@ int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
     { /* Hessian of sf*f + sum_j lam_j * cs_j * g_j (scaled multipliers on scaled constraints) */
       double *ls = s->ct;
       for (int j = 0; j < m; j++) ls[j] = s->lam[j] * s->cs[j];
-      orc_eval_hess(cfg, prob, s->x, s->sf, ls, s->H);
+      nlp->hess(nlp->user, s->x, s->sf, ls, s->H);
     }
     double dw = 0.0;
     int ok = kkt_factor(s, 0.0, 0.0);
@@ -946,15 +956,48 @@ int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
     double v = s->x[i];
     if (s->has_l[i] && v < s->xl0[i]) v = s->xl0[i];
     if (s->has_u[i] && v > s->xu0[i]) v = s->xu0[i];
-    out->z[i] = v;
-    out->zl[i] = s->zl[i] / s->sf;
-    out->zu[i] = s->zu[i] / s->sf;
+    x_out[i] = v;
+    if (zl_out) zl_out[i] = s->zl[i] / s->sf;
+    if (zu_out) zu_out[i] = s->zu[i] / s->sf;
   }
-  for (int j = 0; j < m; j++) out->lambda[j] = s->lam[j] * s->cs[j] / s->sf;
+  if (lam_out)
+    for (int j = 0; j < m; j++) lam_out[j] = s->lam[j] * s->cs[j] / s->sf;
   out->status = status;
   out->iters = iter;
   out->kkt_error = E0;
-  out->obj = orc_eval_f(cfg, prob, out->z);
+  out->obj = nlp->f(nlp->user, x_out);
+
+  ldl_free(s->kkt);
+  free(s->has_l);
+  free(pool);
+  return 0;
+}
+
+/* The analytic restatement of FG_eval as an orc_nlp */
+typedef struct { const orc_config *cfg; const orc_problem *prob; } mpc_user;
+static double mpc_f(void *u, const double *x) { mpc_user *q = (mpc_user *)u; return orc_eval_f(q->cfg, q->prob, x); }
+static void mpc_grad(void *u, const double *x, double *g) { mpc_user *q = (mpc_user *)u; orc_eval_grad(q->cfg, q->prob, x, g); }
+static void mpc_g(void *u, const double *x, double *c) { mpc_user *q = (mpc_user *)u; orc_eval_g(q->cfg, q->prob, x, c); }
+static void mpc_jac(void *u, const double *x, double *J) { mpc_user *q = (mpc_user *)u; orc_eval_jac(q->cfg, q->prob, x, J); }
+static void mpc_hess(void *u, const double *x, double sigma, const double *lam, double *H) {
+  mpc_user *q = (mpc_user *)u;
+  orc_eval_hess(q->cfg, q->prob, x, sigma, lam, H);
+}
+
+int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
+  int N = cfg->N, n = 8 * N - 2, m = 6 * N;
+  mpc_user user = {cfg, prob};
+  orc_nlp nlp = {n, m, &user, mpc_f, mpc_grad, mpc_g, mpc_jac, mpc_hess};
+  double *buf = (double *)calloc((size_t)(3 * n + 2 * m), sizeof(double));
+  double *xl = buf, *xu = xl + n, *xi = xu + n, *gl = xi + n, *gu = gl + m;
+  orc_bounds(cfg, prob, xl, xu, gl, gu, xi);
+  memset(out, 0, sizeof(*out));
+  orc_ipm_stats st;
+  int rc = orc_ipm_solve(&nlp, cfg, xi, xl, xu, gl, gu, out->z, out->lambda, out->zl, out->zu, &st);
+  free(buf);
+  if (rc) return rc;
+  out->status = st.status; out->iters = st.iters; out->n_regularized = st.n_regularized;
+  out->n_soc = st.n_soc; out->n_backtrack = st.n_backtrack; out->obj = st.obj; out->kkt_error = st.kkt_error;
   /* MPC.cpp:322-324 */
   out->result[0] = out->z[IX(1)];
   out->result[1] = out->z[IY(1)];
@@ -965,10 +1008,6 @@ int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
   out->result[6] = out->z[ID(0)];
   out->result[7] = out->z[IA(0)];
   out->result[8] = out->obj;
-
-  ldl_free(s->kkt);
-  free(s->has_l);
-  free(pool);
   return 0;
 }
 

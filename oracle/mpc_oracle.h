@@ -78,6 +78,27 @@ typedef struct orc_result {
 
 void orc_config_defaults(orc_config *cfg);   /* solver knobs only (Ipopt 3.12 defaults) */
 
+/* A generic equality-constrained, bound-constrained NLP (dense derivatives) for the interior-point
+ * core.  Used twice: by the analytic restatement of FG_eval below, and by oracle/ref_shim, where
+ * f, g and their derivatives come from the reference's OWN FG_eval text through an AD tape. */
+typedef struct orc_nlp {
+  int n, m;
+  void *user;
+  double (*f)(void *user, const double *x);
+  void (*grad)(void *user, const double *x, double *g);                 /* n */
+  void (*g)(void *user, const double *x, double *c);                    /* m */
+  void (*jac)(void *user, const double *x, double *J);                  /* m x n row-major */
+  void (*hess)(void *user, const double *x, double sigma, const double *lam, double *H);  /* n x n */
+} orc_nlp;
+typedef struct orc_ipm_stats {
+  int status, iters, n_regularized, n_soc, n_backtrack;
+  double obj, kkt_error;
+} orc_ipm_stats;
+/* cfg supplies only tol, max_iter, mu_init, max_soc, obj_scaling.  Returns 0, or -1 if gl != gu. */
+int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi, const double *xl,
+                  const double *xu, const double *gl, const double *gu, double *x_out, double *lam_out,
+                  double *zl_out, double *zu_out, orc_ipm_stats *stats);
+
 /* NLP pieces, reference layout; all UNSCALED.  hess is n x n dense row-major, jac m x n. */
 double orc_eval_f(const orc_config *cfg, const orc_problem *p, const double *z);
 void orc_eval_grad(const orc_config *cfg, const orc_problem *p, const double *z, double *grad);
