@@ -25,3 +25,4 @@ from carnd_mpc_project_b200 import (MpcConfig, MpcError, Solver, build, lib, LIB
                                     STATUS_NAMES, STATUS_SUCCESS, KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE,
                                     LANE_MIN_BATCH, MpcRunAux, run_prepare, run_finish)
 import carnd_mpc_project_b200.workloads as workloads  # noqa: E402,F401
+import carnd_mpc_project_b200.sharding as sharding  # noqa: E402,F401
