@@ -252,7 +252,7 @@ extern "C" int mpc_create(const mpc_config *cfg, int device, mpc_handle **out) {
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->kernel_kind = MPC_KERNEL_AUTO;
-  h->lane_threads = 32;
+  h->lane_threads = 0;
   h->lane_ctas_per_sm = 0;
   *out = h;
   return MPC_OK;
@@ -306,32 +306,28 @@ static int launch(mpc_handle *h, KParams &kp, cudaStream_t st) {
 }
 
 // The lane kernel keeps everything in registers and thread-private memory: no shared memory, so
-// the whole unified L1 is cache for the per-stage arrays.
+// the whole unified L1 is cache for the per-stage arrays.  One CTA per SM (its warps run the slots of a
+// trip in step), sized so that every lane gets the same number of problems: with
+// r = ceil(B / (SMs * 256)) problems per lane, ceil(B / (SMs * r)) lanes per SM -- otherwise the lanes
+// without a last problem idle through the final round while their warps still issue every instruction.
 template <int NS, int MINB>
 static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
-  const int threads = h->lane_threads;
   static thread_local int cached_dev = -1;
   if (cached_dev != h->device) {
     CK(cudaFuncSetAttribute(mpc_lane_kernel<NS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     cached_dev = h->device;
   }
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_lane_kernel<NS, MINB>, threads, 0));
-  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "lane kernel does not fit on an SM"); return MPC_ECUDA; }
-  if (h->lane_ctas_per_sm > 0) {
-    if (per_sm > h->lane_ctas_per_sm) per_sm = h->lane_ctas_per_sm;
-  } else {
-    // Balance the persistent grid: with r = ceil(B / (SMs * max lanes per SM)) problems per lane, use
-    // just enough lanes that every lane gets r problems -- otherwise the lanes without a last
-    // problem idle through the final round while their warps still issue every instruction.
-    const long long max_lanes = (long long)h->sm_count * per_sm * threads;
+  int threads = h->lane_threads;           // 0 = automatic
+  if (threads <= 0) {
+    const long long max_lanes = (long long)h->sm_count * 256;
     const long long rounds = (kp.B + max_lanes - 1) / max_lanes;
     const long long lanes_per_sm = (kp.B + rounds * h->sm_count - 1) / (rounds * h->sm_count);
-    int want_ctas = (int)((lanes_per_sm + threads - 1) / threads);
-    if (want_ctas < per_sm) per_sm = want_ctas < 1 ? 1 : want_ctas;
+    threads = (int)((lanes_per_sm + 31) / 32) * 32;
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
   }
   long long want = ((long long)kp.B + threads - 1) / threads;
-  long long grid = (long long)h->sm_count * per_sm;
+  long long grid = (long long)h->sm_count * (h->lane_ctas_per_sm > 0 ? h->lane_ctas_per_sm : 1);
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
@@ -343,9 +339,9 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
 
 extern "C" int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm) {
   if (!h || kind < MPC_KERNEL_AUTO || kind > MPC_KERNEL_LANE) return MPC_EINVAL;
-  if (lane_threads != 0 && (lane_threads < 32 || lane_threads > 128 || lane_threads % 32)) return MPC_EINVAL;
+  if (lane_threads != 0 && (lane_threads < 32 || lane_threads > 256 || lane_threads % 32)) return MPC_EINVAL;
   h->kernel_kind = kind;
-  if (lane_threads) h->lane_threads = lane_threads;
+  h->lane_threads = lane_threads;
   h->lane_ctas_per_sm = lane_ctas_per_sm < 0 ? 0 : lane_ctas_per_sm;
   return MPC_OK;
 }
@@ -379,10 +375,10 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
     if (c.N > 32) { snprintf(g_err, sizeof(g_err), "warp kernel handles N <= 32"); return MPC_EINVAL; }
     return launch<32>(h, kp, (cudaStream_t)cuda_stream);
   }
-  if (c.N <= 10) return launch_lane<10, 2>(h, kp, (cudaStream_t)cuda_stream);
-  if (c.N <= 20) return launch_lane<20, 2>(h, kp, (cudaStream_t)cuda_stream);
-  if (c.N <= 32) return launch_lane<32, 2>(h, kp, (cudaStream_t)cuda_stream);
-  return launch_lane<MPC_NMAX, 2>(h, kp, (cudaStream_t)cuda_stream);
+  if (c.N <= 10) return launch_lane<10, 1>(h, kp, (cudaStream_t)cuda_stream);
+  if (c.N <= 20) return launch_lane<20, 1>(h, kp, (cudaStream_t)cuda_stream);
+  if (c.N <= 32) return launch_lane<32, 1>(h, kp, (cudaStream_t)cuda_stream);
+  return launch_lane<MPC_NMAX, 1>(h, kp, (cudaStream_t)cuda_stream);
 }
 
 // ---- host-pointer entry points -------------------------------------------------------------------

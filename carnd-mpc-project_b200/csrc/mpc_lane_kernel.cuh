@@ -17,6 +17,14 @@
 // from a global counter, so the spread of iteration counts (10 typical, 50 worst) costs nothing.
 // The rare paths (inertia correction 0.3 % of iterations, second-order correction and backtracking
 // ~0.002 %) simply take extra trips.
+//
+// Memory.  The per-stage state of a problem does not fit in registers, and the state of all resident
+// lanes must fit in the 126 MB L2 or every sweep streams it through HBM (profiles/r01_v2_*: 16.5 GB
+// of DRAM traffic per 64K batch).  So only what cannot be recomputed cheaply is stored -- iterate
+// (x, lambda, z), step, Riccati gains, and the trig/polynomial values and residuals at the iterate:
+// 56 doubles per stage.  Slack reciprocals, trial-point values and the new multipliers are recomputed
+// (the FP64 pipe has the headroom); the costate recursion that yields the new multipliers runs inside
+// the sweep that accepts the step, the step-length ratios inside the forward sweep.
 #pragma once
 #include "mpc_kernel.cuh"
 
@@ -27,6 +35,7 @@ enum {
   LM_EV0,         // evaluate the start point
   LM_LSQ,         // least-squares multiplier estimate (Riccati with H = I)
   LM_LSQ_DONE,    // take the multipliers, compute the KKT error, go to NEWTON
+  LM_LSQ_ZERO,    // the estimate was rejected (|lambda| > 1e3): multipliers = 0, KKT error, go to NEWTON
   LM_NEWTON,      // factor (with inertia correction) and solve for the search direction
   LM_TRIAL,       // evaluate x + alpha dx and test it against the filter
   LM_SOC,         // solve with the second-order-corrected right-hand side
@@ -41,17 +50,31 @@ enum { LC_DT = 0, LC_DTLF, LC_SF, LC_CW, LC_WC2, LC_WE2, LC_WV2, LC_VREF, LC_WD2
        LC_VREF_0, LC_NV2_0, LC_C0, LC_S0 = LC_C0 + 5, LC_LO = LC_S0 + 6, LC_HI = LC_LO + 4,
        LC_LO0 = LC_HI + 4, LC_HI0 = LC_LO0 + 4, LC_SIZE = LC_HI0 + 4 };
 
-__device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+// 1/a for a normal, finite a (slacks, 1 + f'^2, pivots): hardware seed + two Newton steps.  Accurate to
+// ~1 ulp; a third of the instructions of the correctly-rounded division, which dominated the sweeps.
+__device__ __forceinline__ double rcp(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  return fma(x, e, x);
+}
+
+struct StageLin { double a13, a14, a23, a24, a34, b3, a51, a54, a56, a61; };
+struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa, gp, gv, gc, ge, gdp, gd, ga; };
 
 template <int NS>
 struct Lane {
-  // ---- per-stage data (thread-private memory) ----
-  double S[NS][6], U[NS][2], LAM[NS][6], ZL[NS][4], ZU[NS][4], IL[NS][4], IU[NS][4];
-  double TG[NS][8], CN[NS][6];            // sin/cos psi, sin/cos epsi, f', f'', a61, g3 and c_{i+1} at the iterate
-  double DS[NS][6], DU[NS][2], LN[NS][6]; // search direction and new multipliers
-  double KG[NS][12];                      // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
-  double TT[NS][8], CT[NS][6];            // the same at the trial point
-  double CS[NS][6];                       // second-order-correction right-hand side
+  // ---- per-stage data (thread-private memory): 70 doubles per stage are touched on the common path
+  double S[NS][6], U[NS][2], LAM[NS][6], ZL[NS][4], ZU[NS][4];   // iterate
+  double TG[NS][8], CN[NS][6];   // sin/cos psi, sin/cos epsi, f', f'', a61, g3 and c_{i+1} at the iterate
+  double DS[NS][6], DU[NS][2];   // primal search direction
+  double TT[NS][8], CT[NS][6];   // the same as TG / CN at the trial point (copied on acceptance)
+  double KG[NS][12];             // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
+  double CS[NS][6];              // second-order-correction right-hand side (rare path only)
   double PC[LC_SIZE];
   double FLT[2 * K_NFILT];
   double c0[6], c0t[6], cs0[6];
@@ -133,7 +156,9 @@ struct Lane {
 #pragma unroll 1
     for (int i = 0; i < N; i++) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) { S[i][k] = (i == 0) ? PC[LC_S0 + k] : 0.0; LAM[i][k] = 0.0; DS[i][k] = 0.0; LN[i][k] = 0.0; }
+      for (int k = 0; k < 6; k++) { S[i][k] = (i == 0) ? PC[LC_S0 + k] : 0.0; LAM[i][k] = 0.0; DS[i][k] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) TG[i][k] = 0.0;   // read (times alpha = 0) by the first advance sweep
       S[i][2] = i == 0 ? x00[0] : x0[0];
       S[i][3] = i == 0 ? x00[1] : x0[1];
       U[i][0] = x0[2]; U[i][1] = x0[3];
@@ -143,7 +168,6 @@ struct Lane {
         const bool valid = k < 2 || i < N - 1;
         ZL[i][k] = valid ? 1.0 : 0.0;
         ZU[i][k] = valid ? 1.0 : 0.0;
-        IL[i][k] = 1.0; IU[i][k] = 1.0;
       }
     }
     mu = 0.1;
@@ -154,13 +178,104 @@ struct Lane {
     mode = LM_EV0;
   }
 
-  // ------------------------------------------------------------------------------------------
-  // slot 1: residuals, scaled objective, log-barrier sum and ||c||_1 at x + a*dx; the trig /
-  // polynomial values of every stage are kept for the derivative build (MPC.cpp:144-152)
-  // ------------------------------------------------------------------------------------------
-  __device__ void eval_sweep(double a) {
+
+  // F(s, u): right-hand sides of MPC.cpp:144-152 with polyeval/polyder (utils.h:28-47), and the
+  // transcendental/polynomial values the derivatives need (App. A.4 of SURVEY.md)
+  __device__ __forceinline__ void point_eval(const double *s, double u0, double u1, double *tg, double *F) const {
     const double dt = PC[LC_DT], dtLf = PC[LC_DTLF];
     const double c0_ = PC[LC_C0], c1_ = PC[LC_C0 + 1], c2_ = PC[LC_C0 + 2], c3_ = PC[LC_C0 + 3], c4_ = PC[LC_C0 + 4];
+    double sp, cp, se, ce;
+    sincos(s[2], &sp, &cp);
+    sincos(s[5], &se, &ce);
+    const double x = s[0];
+    const double f = (((c4_ * x + c3_) * x + c2_) * x + c1_) * x + c0_;
+    const double f1 = ((4.0 * c4_ * x + 3.0 * c3_) * x + 2.0 * c2_) * x + c1_;
+    const double f2 = (12.0 * c4_ * x + 6.0 * c3_) * x + 2.0 * c2_;
+    const double f3 = 24.0 * c4_ * x + 6.0 * c3_;
+    const double q = fma(f1, f1, 1.0), iq = rcp(q);
+    tg[0] = sp; tg[1] = cp; tg[2] = se; tg[3] = ce; tg[4] = f1; tg[5] = f2;
+    tg[6] = -f2 * iq;                                    // d/dx of -atan(f')
+    tg[7] = (f3 * q - 2.0 * f1 * f2 * f2) * iq * iq;      // and its derivative
+    const double vdt = s[3] * dt;
+    F[0] = s[0] + cp * vdt;
+    F[1] = s[1] + sp * vdt;
+    F[2] = s[2] + u0 * s[3] * dtLf;
+    F[3] = s[3] + u1 * dt;
+    F[4] = (f - s[1]) + se * vdt;
+    F[5] = F[2] - atan(f1);
+  }
+  __device__ __forceinline__ void lin_at(const double *tg, double v, double d0, StageLin &L) const {
+    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], vdt = v * dt;
+    L.a13 = -vdt * tg[0]; L.a14 = dt * tg[1]; L.a23 = vdt * tg[1]; L.a24 = dt * tg[0];
+    L.a34 = d0 * dtLf; L.b3 = v * dtLf; L.a51 = tg[4]; L.a54 = dt * tg[2]; L.a56 = vdt * tg[3];
+    L.a61 = tg[6];
+  }
+  // slack reciprocals of psi, v, delta, a at a point
+  __device__ __forceinline__ void slack_rcp(double psi, double v, double u0, double u1, bool hasu, double *il, double *iu) const {
+    il[0] = rcp(psi - PC[LC_LO]); iu[0] = rcp(PC[LC_HI] - psi);
+    il[1] = rcp(v - PC[LC_LO + 1]); iu[1] = rcp(PC[LC_HI + 1] - v);
+    if (hasu) {
+      il[2] = rcp(u0 - PC[LC_LO + 2]); iu[2] = rcp(PC[LC_HI + 2] - u0);
+      il[3] = rcp(u1 - PC[LC_LO + 3]); iu[3] = rcp(PC[LC_HI + 3] - u1);
+    } else {
+      il[2] = iu[2] = il[3] = iu[3] = 0.0;
+    }
+  }
+  // Hessian of the Lagrangian + barrier Sigma + dw on the primal diagonal, gradient of the barrier
+  // objective, all from register values.  ls: the least-squares multiplier system (Hessian = I,
+  // gradient = grad f - zl + zu).  ln = multipliers of stage i+1, dprev = delta_{i-1}.
+  __device__ __forceinline__ void hess_at(int i, bool ls, double dwv, const double *tg, double v, double c, double e,
+                                          double d0, double dprev, const double *ln, const double *zl, const double *zu,
+                                          const double *il, const double *iu, StageHess &H) const {
+    const bool hasu = i < N - 1;
+    const bool cpl = hasu && i >= 1;
+    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    double sig[4], gb[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      sig[k] = zl[k] * il[k] + zu[k] * iu[k];
+      gb[k] = ls ? (zu[k] - zl[k]) : mu * (iu[k] - il[k]);
+    }
+    H.gp = gb[0];
+    H.gv = wv2 * (v - vref(i)) + nv2(i) * v + gb[1];
+    H.gc = wc2(i) * c;
+    H.ge = we2(i) * e;
+    H.gdp = 0.0; H.gd = 0.0; H.ga = 0.0;
+    if (hasu) {
+      const double dd = cpl ? d0 - dprev : 0.0;
+      H.gdp = -cw * dd;
+      H.gd = wd2 * d0 + cw * dd + gb[2];
+      H.ga = gb[3];
+    }
+    if (ls) {
+      H.qxx = 1.0; H.qyy = 1.0; H.qpp = 1.0; H.qpv = 0.0; H.qvv = 1.0; H.qve = 0.0; H.qcc = 1.0; H.qee = 1.0;
+      H.svd = 0.0; H.rdd = 1.0; H.raa = 1.0;
+      return;
+    }
+    H.qyy = dwv;
+    H.qvv = wv2 + nv2(i) + sig[1] + dwv;
+    H.qcc = wc2(i) + dwv;
+    if (hasu) {
+      const double vdt = v * dt;
+      H.qxx = -ln[4] * tg[5] + ln[5] * tg[7] + dwv;
+      H.qpp = (ln[0] * tg[1] + ln[1] * tg[0]) * vdt + sig[0] + dwv;
+      H.qpv = (ln[0] * tg[0] - ln[1] * tg[1]) * dt;
+      H.qve = -ln[4] * tg[3] * dt;
+      H.qee = ln[4] * tg[2] * vdt + we2(i) + dwv;
+      H.svd = -(ln[2] + ln[5]) * dtLf;
+      H.rdd = wd2 + (cpl ? cw : 0.0) + sig[2] + dwv;
+      H.raa = sig[3] + dwv;
+    } else {
+      H.qxx = dwv; H.qpp = sig[0] + dwv; H.qpv = 0.0; H.qve = 0.0; H.qee = we2(i) + dwv;
+      H.svd = 0.0; H.rdd = 0.0; H.raa = 0.0;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slot 1 (forward sweep): ||c||_1, scaled objective and log-barrier sum at x + a*dx; the residuals and
+  // trig/polynomial values of the trial point are kept (TT, CT) and become the iterate's on acceptance
+  // ------------------------------------------------------------------------------------------
+  __device__ void eval_sweep(double a) {
     const double lo_p = PC[LC_LO], hi_p = PC[LC_HI], lo_v = PC[LC_LO + 1], hi_v = PC[LC_HI + 1];
     const double lo_d = PC[LC_LO + 2], hi_d = PC[LC_HI + 2], lo_a = PC[LC_LO + 3], hi_a = PC[LC_HI + 3];
     double F[6] = {0, 0, 0, 0, 0, 0};
@@ -182,26 +297,10 @@ struct Lane {
       double prod = (s[2] - lo_p) * (hi_p - s[2]) * (s[3] - lo_v) * (hi_v - s[3]);
       if (i < N - 1) {
         const double u0 = fma(a, DU[i][0], U[i][0]), u1 = fma(a, DU[i][1], U[i][1]);
-        double sp, cp, se, ce;
-        sincos(s[2], &sp, &cp);
-        sincos(s[5], &se, &ce);
-        const double x = s[0];
-        const double f = (((c4_ * x + c3_) * x + c2_) * x + c1_) * x + c0_;
-        const double f1 = ((4.0 * c4_ * x + 3.0 * c3_) * x + 2.0 * c2_) * x + c1_;
-        const double f2 = (12.0 * c4_ * x + 6.0 * c3_) * x + 2.0 * c2_;
-        const double f3 = 24.0 * c4_ * x + 6.0 * c3_;
-        // d/dx of -atan(f') and its derivative (row epsi of App. A.4), once per point
-        const double q = fma(f1, f1, 1.0), iq = __drcp_rn(q);
-        TT[i][0] = sp; TT[i][1] = cp; TT[i][2] = se; TT[i][3] = ce; TT[i][4] = f1; TT[i][5] = f2;
-        TT[i][6] = -f2 * iq;
-        TT[i][7] = (f3 * q - 2.0 * f1 * f2 * f2) * iq * iq;
-        const double vdt = s[3] * dt;
-        F[0] = s[0] + cp * vdt;
-        F[1] = s[1] + sp * vdt;
-        F[2] = s[2] + u0 * s[3] * dtLf;
-        F[3] = s[3] + u1 * dt;
-        F[4] = (f - s[1]) + se * vdt;
-        F[5] = F[2] - atan(f1);
+        double tg[8];
+        point_eval(s, u0, u1, tg, F);
+#pragma unroll
+        for (int k = 0; k < 8; k++) TT[i][k] = tg[k];
         fl += 0.5 * PC[LC_WD2] * u0 * u0;
         if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * PC[LC_CW] * dd * dd; }
         dprev = u0;
@@ -211,88 +310,149 @@ struct Lane {
     }
     ft = fl; lt = ll; tht = th;
   }
+  // CS = a * (first ? CN : CS) + CT     (Ipopt's accumulated second-order-correction rhs)
+  __device__ void soc_rhs(bool first, double a) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) cs0[k] = a * (first ? c0[k] : cs0[k]) + c0t[k];
+#pragma unroll 1
+    for (int i = 0; i < N - 1; i++) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) CS[i][k] = a * (first ? CN[i][k] : CS[i][k]) + CT[i][k];
+    }
+  }
 
   // ------------------------------------------------------------------------------------------
-  // slot 2 (backward sweep): accept the trial point (x += alpha dx, lambda, z, slack reciprocals,
-  // residuals and trig of the new iterate) and/or evaluate Ipopt's optimality error terms
+  // slot 2 (backward sweep), three jobs in one pass over the stages:
+  //  (1) costate recursion at the OLD iterate: the new multipliers lambda+ of the step just tried
+  //      (or, ls: the least-squares multiplier estimate);
+  //  (2) do_update: accept the step -- x += alpha dx, lambda += alpha (lambda+ - lambda), z with Ipopt's
+  //      kappa_sigma safeguard -- and re-evaluate trig/polynomial values and residuals there;
+  //  (3) Ipopt's optimality error terms at the resulting iterate.
   // ------------------------------------------------------------------------------------------
-  __device__ void update_and_errors(bool do_update, bool take_lsq, bool lsq_bad) {
-    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+  __device__ void advance(bool do_update, bool ls, bool zero_lam) {
+    const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     const double a = alpha, az = alpha_z;
+    const double dwv = ls ? 0.0 : dw_used;
     const double zcap = K_KAPPA_SIGMA * mu, zfloor = mu / K_KAPPA_SIGMA;   // Ipopt's kappa_sigma safeguard
-    double ln[6] = {0, 0, 0, 0, 0, 0};
-    double dnext = 0.0;
-    double r = 0.0, cv = 0.0, l1 = 0.0, zz = 0.0, am = 1e300, aM = 0.0;
-    if (do_update) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) c0[k] = c0t[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 6; k++) cv = nanmax(cv, fabs(c0[k]));
+    const bool costate = do_update || ls;
+    double lo_n[6] = {0, 0, 0, 0, 0, 0};   // OLD multipliers of stage i+1
+    double lp_n[6] = {0, 0, 0, 0, 0, 0};   // lambda+ of stage i+1
+    double ln_n[6] = {0, 0, 0, 0, 0, 0};   // NEW multipliers of stage i+1
+    double dnext = 0.0;                    // NEW delta_{i+1}
+    double r = 0.0, cv = 0.0, l1 = 0.0, zz = 0.0, am = 1e300, aM = 0.0, lmax = 0.0;
 #pragma unroll 1
     for (int i = N - 1; i >= 0; i--) {
       const bool hasu = i < N - 1;
-      double s[6], u[2] = {0, 0}, lam[6], zl[4], zu[4];
+      double s[6], lam[6], zl[4], zu[4], tg[8], u0 = 0.0, u1 = 0.0;
 #pragma unroll
       for (int k = 0; k < 6; k++) { s[k] = S[i][k]; lam[k] = LAM[i][k]; }
-      if (hasu) { u[0] = U[i][0]; u[1] = U[i][1]; }
 #pragma unroll
       for (int k = 0; k < 4; k++) { zl[k] = ZL[i][k]; zu[k] = ZU[i][k]; }
-      double tg[8];
-      if (do_update) {
-        double dx[4];
-        dx[0] = DS[i][2]; dx[1] = DS[i][3]; dx[2] = hasu ? DU[i][0] : 0.0; dx[3] = hasu ? DU[i][1] : 0.0;
+      if (hasu) {
+        u0 = U[i][0]; u1 = U[i][1];
 #pragma unroll
-        for (int k = 0; k < 6; k++) { s[k] = fma(a, DS[i][k], s[k]); lam[k] += a * (LN[i][k] - lam[k]); S[i][k] = s[k]; LAM[i][k] = lam[k]; }
+        for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) tg[k] = 0.0;
+      }
+      const double dprev_old = (hasu && i >= 1) ? U[i - 1][0] : 0.0;
+      double dprev = dprev_old;            // NEW delta_{i-1}
+      double lp[6] = {0, 0, 0, 0, 0, 0};
+      StageLin L;
+      if (hasu) lin_at(tg, s[3], u0, L);
+      if (costate) {
+        double ds[6], du0 = 0.0, du1 = 0.0, il[4], iu[4];
+#pragma unroll
+        for (int k = 0; k < 6; k++) ds[k] = DS[i][k];
+        if (hasu) { du0 = DU[i][0]; du1 = DU[i][1]; }
+        slack_rcp(s[2], s[3], u0, u1, hasu, il, iu);
+        StageHess H;
+        hess_at(i, ls, dwv, tg, s[3], s[4], s[5], u0, dprev_old, lo_n, zl, zu, il, iu, H);
+        double h[6];
+        h[0] = H.qxx * ds[0];
+        h[1] = H.qyy * ds[1];
+        h[2] = H.qpp * ds[2] + H.qpv * ds[3] + H.gp;
+        h[3] = H.qpv * ds[2] + H.qvv * ds[3] + H.qve * ds[5] + H.gv + H.svd * du0;
+        h[4] = H.qcc * ds[4] + H.gc;
+        h[5] = H.qve * ds[3] + H.qee * ds[5] + H.ge;
         if (hasu) {
-          u[0] = fma(a, dx[2], u[0]); u[1] = fma(a, dx[3], u[1]);
-          U[i][0] = u[0]; U[i][1] = u[1];
+          const double l25 = lp_n[2] + lp_n[5];
+          lp[0] = lp_n[0] + L.a51 * lp_n[4] + L.a61 * lp_n[5] - h[0];
+          lp[1] = lp_n[1] - lp_n[4] - h[1];
+          lp[2] = L.a13 * lp_n[0] + L.a23 * lp_n[1] + l25 - h[2];
+          lp[3] = L.a14 * lp_n[0] + L.a24 * lp_n[1] + L.a34 * l25 + lp_n[3] + L.a54 * lp_n[4] - h[3];
+          lp[4] = -h[4];
+          lp[5] = L.a56 * lp_n[4] - h[5];
+        } else {
 #pragma unroll
-          for (int k = 0; k < 6; k++) CN[i][k] = CT[i][k];
+          for (int k = 0; k < 6; k++) lp[k] = -h[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) lmax = nanmax(lmax, fabs(lp[k]));
+#pragma unroll
+        for (int k = 0; k < 6; k++) lo_n[k] = lam[k];
+        if (do_update) {
+          const double dx[4] = {ds[2], ds[3], du0, du1};
+#pragma unroll
+          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] += a * (lp[k] - lam[k]); S[i][k] = s[k]; }
+          if (hasu) {
+            u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
+            U[i][0] = u0; U[i][1] = u1;
+          }
+          if (i >= 1 && hasu) dprev = fma(a, DU[i - 1][0], dprev_old);
+          double iln[4], iun[4];
+          slack_rcp(s[2], s[3], u0, u1, hasu, iln, iun);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < 2 || hasu) {
+              const double dzl = (mu - zl[k] * dx[k]) * il[k] - zl[k];
+              const double dzu = (mu + zu[k] * dx[k]) * iu[k] - zu[k];
+              zl[k] = fmax(fmin(zl[k] + az * dzl, zcap * iln[k]), zfloor * iln[k]);
+              zu[k] = fmax(fmin(zu[k] + az * dzu, zcap * iun[k]), zfloor * iun[k]);
+              ZL[i][k] = zl[k]; ZU[i][k] = zu[k];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) lam[k] = lp[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) LAM[i][k] = lam[k];
+      } else if (zero_lam) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { lam[k] = 0.0; LAM[i][k] = 0.0; }
+      }
+      // ---- residuals and trig/polynomial values at the (new) iterate
+      double cn[6] = {0, 0, 0, 0, 0, 0};
+      if (hasu) {
+        if (do_update) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) { cn[k] = CT[i][k]; CN[i][k] = cn[k]; }
 #pragma unroll
           for (int k = 0; k < 8; k++) { tg[k] = TT[i][k]; TG[i][k] = tg[k]; }
-        }
-        const double xv[4] = {s[2], s[3], u[0], u[1]};
+          lin_at(tg, s[3], u0, L);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (k < 2 || hasu) {
-            const double il = IL[i][k], iu = IU[i][k];
-            const double dzl = (mu - zl[k] * dx[k]) * il - zl[k];
-            const double dzu = (mu + zu[k] * dx[k]) * iu - zu[k];
-            const double iln = rcp(xv[k] - PC[LC_LO + k]), iun = rcp(PC[LC_HI + k] - xv[k]);
-            double t = zl[k] + az * dzl;
-            zl[k] = fmax(fmin(t, zcap * iln), zfloor * iln);
-            t = zu[k] + az * dzu;
-            zu[k] = fmax(fmin(t, zcap * iun), zfloor * iun);
-            IL[i][k] = iln; IU[i][k] = iun; ZL[i][k] = zl[k]; ZU[i][k] = zu[k];
-          }
+          for (int k = 0; k < 6; k++) cn[k] = CN[i][k];
         }
-      } else {
-        if (take_lsq) {
+      }
+      if (i == 0 && do_update) {
 #pragma unroll
-          for (int k = 0; k < 6; k++) { lam[k] = lsq_bad ? 0.0 : LN[i][k]; LAM[i][k] = lam[k]; }
-        }
-        if (hasu) {
-#pragma unroll
-          for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
-        }
+        for (int k = 0; k < 6; k++) c0[k] = c0t[k];
       }
       // ---- optimality error terms
       double os[6] = {0, 0, 0, 0, 0, 0}, ou0 = 0.0, ou1 = 0.0;
       const double v = s[3];
       if (hasu) {
-        const double vdt = v * dt;
-        const double a13 = -vdt * tg[0], a14 = dt * tg[1], a23 = vdt * tg[1], a24 = dt * tg[0];
-        const double a34 = u[0] * dtLf, b3 = v * dtLf, a51 = tg[4], a54 = dt * tg[2], a56 = vdt * tg[3];
-        const double a61 = tg[6];
-        const double l25 = ln[2] + ln[5];
-        os[0] = ln[0] + a51 * ln[4] + a61 * ln[5];
-        os[1] = ln[1] - ln[4];
-        os[2] = a13 * ln[0] + a23 * ln[1] + l25;
-        os[3] = a14 * ln[0] + a24 * ln[1] + a34 * l25 + ln[3] + a54 * ln[4];
-        os[5] = a56 * ln[4];
-        ou0 = b3 * l25;
-        ou1 = dt * ln[3];
+        const double l25 = ln_n[2] + ln_n[5];
+        os[0] = ln_n[0] + L.a51 * ln_n[4] + L.a61 * ln_n[5];
+        os[1] = ln_n[1] - ln_n[4];
+        os[2] = L.a13 * ln_n[0] + L.a23 * ln_n[1] + l25;
+        os[3] = L.a14 * ln_n[0] + L.a24 * ln_n[1] + L.a34 * l25 + ln_n[3] + L.a54 * ln_n[4];
+        os[5] = L.a56 * ln_n[4];
+        ou0 = L.b3 * l25;
+        ou1 = dt * ln_n[3];
       }
       double gs[6];
       gs[0] = 0.0; gs[1] = 0.0;
@@ -304,6 +464,7 @@ struct Lane {
       for (int k = 0; k < 6; k++) {
         r = nanmax(r, fabs(gs[k] + lam[k] - os[k]));
         l1 += fabs(lam[k]);
+        cv = nanmax(cv, fabs(cn[k]));
       }
       zz += fabs(zl[0]) + fabs(zu[0]) + fabs(zl[1]) + fabs(zu[1]);
       {
@@ -313,102 +474,27 @@ struct Lane {
         aM = fmax(aM, fmax(fmax(p0, p1), fmax(p2, p3)));
       }
       if (hasu) {
-        // delta_{i-1} of the NEW iterate (stage i-1 is updated after this one)
-        double dprev = 0.0;
-        if (i >= 1) dprev = do_update ? fma(a, DU[i - 1][0], U[i - 1][0]) : U[i - 1][0];
-        double gd = wd2 * u[0];
-        if (i >= 1) gd += cw * (u[0] - dprev);
-        if (i <= N - 3) gd -= cw * (dnext - u[0]);
+        double gd = wd2 * u0;
+        if (i >= 1) gd += cw * (u0 - dprev);
+        if (i <= N - 3) gd -= cw * (dnext - u0);
         r = nanmax(r, fabs(gd - ou0 - zl[2] + zu[2]));
         r = nanmax(r, fabs(-ou1 - zl[3] + zu[3]));
         zz += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
-        const double p0 = (u[0] - PC[LC_LO + 2]) * zl[2], p1 = (PC[LC_HI + 2] - u[0]) * zu[2];
-        const double p2 = (u[1] - PC[LC_LO + 3]) * zl[3], p3 = (PC[LC_HI + 3] - u[1]) * zu[3];
+        const double p0 = (u0 - PC[LC_LO + 2]) * zl[2], p1 = (PC[LC_HI + 2] - u0) * zu[2];
+        const double p2 = (u1 - PC[LC_LO + 3]) * zl[3], p3 = (PC[LC_HI + 3] - u1) * zu[3];
         am = fmin(am, fmin(fmin(p0, p1), fmin(p2, p3)));
         aM = fmax(aM, fmax(fmax(p0, p1), fmax(p2, p3)));
-#pragma unroll
-        for (int k = 0; k < 6; k++) cv = nanmax(cv, fabs(do_update ? CT[i][k] : CN[i][k]));
-        dnext = u[0];
+        dnext = u0;
       }
 #pragma unroll
-      for (int k = 0; k < 6; k++) ln[k] = lam[k];
+      for (int k = 0; k < 6; k++) { ln_n[k] = lam[k]; lp_n[k] = lp[k]; }
     }
-    dinf = r; cviol = cv; lam1 = l1; z1 = zz; amin = am; amax = aM;
+#pragma unroll
+    for (int k = 0; k < 6; k++) cv = nanmax(cv, fabs(c0[k]));
+    dinf = r; cviol = cv; lam1 = l1; z1 = zz; amin = am; amax = aM; lsq_lmax = lmax;
   }
   // max_i |slack_i * z_i - m|  from the extreme complementarity products
   __device__ __forceinline__ double compl_err(double m) const { return nanmax(fabs(amax - m), fabs(amin - m)); }
-
-  // ------------------------------------------------------------------------------------------
-  // derivative pieces of stage i at the iterate (App. A.4 of SURVEY.md)
-  // ------------------------------------------------------------------------------------------
-  struct StageLin { double a13, a14, a23, a24, a34, b3, a51, a54, a56, a61; };
-  struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa, gp, gv, gc, ge, gdp, gd, ga; };
-
-  __device__ __forceinline__ void stage_lin(int i, StageLin &L, double *tg) const {
-    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF];
-#pragma unroll
-    for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
-    const double v = S[i][3], vdt = v * dt;
-    L.a13 = -vdt * tg[0]; L.a14 = dt * tg[1]; L.a23 = vdt * tg[1]; L.a24 = dt * tg[0];
-    L.a34 = U[i][0] * dtLf; L.b3 = v * dtLf; L.a51 = tg[4]; L.a54 = dt * tg[2]; L.a56 = vdt * tg[3];
-    L.a61 = tg[6];
-  }
-  // Hessian of the Lagrangian + barrier Sigma + dw on the primal diagonal, gradient of the barrier
-  // objective.  ls: the least-squares multiplier system (Hessian = I, gradient = grad f - zl + zu).
-  __device__ __forceinline__ void stage_hess(int i, bool ls, double dwv, const double *tg, StageHess &H) const {
-    const bool hasu = i < N - 1;
-    const bool cpl = hasu && i >= 1;
-    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
-    double sig[4], gb[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (k < 2 || hasu) {
-        const double il = IL[i][k], iu = IU[i][k], zl = ZL[i][k], zu = ZU[i][k];
-        sig[k] = zl * il + zu * iu;
-        gb[k] = ls ? (zu - zl) : mu * (iu - il);
-      } else {
-        sig[k] = 0.0; gb[k] = 0.0;
-      }
-    }
-    const double v = S[i][3];
-    H.gp = gb[0];
-    H.gv = wv2 * (v - vref(i)) + nv2(i) * v + gb[1];
-    H.gc = wc2(i) * S[i][4];
-    H.ge = we2(i) * S[i][5];
-    H.gdp = 0.0; H.gd = 0.0; H.ga = 0.0;
-    if (hasu) {
-      const double d0 = U[i][0];
-      const double dd = cpl ? d0 - U[i - 1][0] : 0.0;
-      H.gdp = -cw * dd;
-      H.gd = wd2 * d0 + cw * dd + gb[2];
-      H.ga = gb[3];
-    }
-    if (ls) {
-      H.qxx = 1.0; H.qyy = 1.0; H.qpp = 1.0; H.qpv = 0.0; H.qvv = 1.0; H.qve = 0.0; H.qcc = 1.0; H.qee = 1.0;
-      H.svd = 0.0; H.rdd = 1.0; H.raa = 1.0;
-      return;
-    }
-    H.qyy = dwv;
-    H.qvv = wv2 + nv2(i) + sig[1] + dwv;
-    H.qcc = wc2(i) + dwv;
-    if (hasu) {
-      double ln[6];
-#pragma unroll
-      for (int k = 0; k < 6; k++) ln[k] = LAM[i + 1][k];
-      const double vdt = v * dt;
-      H.qxx = -ln[4] * tg[5] + ln[5] * tg[7] + dwv;
-      H.qpp = (ln[0] * tg[1] + ln[1] * tg[0]) * vdt + sig[0] + dwv;
-      H.qpv = (ln[0] * tg[0] - ln[1] * tg[1]) * dt;
-      H.qve = -ln[4] * tg[3] * dt;
-      H.qee = ln[4] * tg[2] * vdt + we2(i) + dwv;
-      H.svd = -(ln[2] + ln[5]) * dtLf;
-      H.rdd = wd2 + (cpl ? cw : 0.0) + sig[2] + dwv;
-      H.raa = sig[3] + dwv;
-    } else {
-      H.qxx = dwv; H.qpp = sig[0] + dwv; H.qpv = 0.0; H.qve = 0.0; H.qee = we2(i) + dwv;
-      H.svd = 0.0; H.rdd = 0.0; H.raa = 0.0;
-    }
-  }
 
   // ------------------------------------------------------------------------------------------
   // slot 3: backward Riccati sweep.  Cost-to-go over (x, y, psi, v, epsi, delta_prev) as a dense
@@ -420,10 +506,14 @@ struct Lane {
     const double dt = PC[LC_DT];
     const double cwv = ls ? 0.0 : PC[LC_CW];
     double Pm[6][6], pv[6], P44, p4;
+    double zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     {
+      const int t = N - 1;
+      double zl[4] = {ZL[t][0], ZL[t][1], 0.0, 0.0}, zu[4] = {ZU[t][0], ZU[t][1], 0.0, 0.0}, il[4], iu[4];
+      const double psi = S[t][2], v = S[t][3];
+      slack_rcp(psi, v, 0.0, 0.0, false, il, iu);
       StageHess H;
-      double tg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      stage_hess(N - 1, ls, dwv, tg, H);
+      hess_at(t, ls, dwv, zero8, v, S[t][4], S[t][5], 0.0, 0.0, zero8, zl, zu, il, iu, H);
 #pragma unroll
       for (int r = 0; r < 6; r++) {
 #pragma unroll
@@ -439,10 +529,21 @@ struct Lane {
     for (int i = N - 2; i >= 0; i--) {
       StageLin L;
       StageHess H;
-      double tg[8];
-      stage_lin(i, L, tg);
-      stage_hess(i, ls, dwv, tg, H);
       double d[6];
+      {
+        double tg[8], ln[6], zl[4], zu[4], il[4], iu[4];
+#pragma unroll
+        for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) ln[k] = LAM[i + 1][k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { zl[k] = ZL[i][k]; zu[k] = ZU[i][k]; }
+        const double psi = S[i][2], v = S[i][3], c = S[i][4], e = S[i][5], u0 = U[i][0], u1 = U[i][1];
+        const double dprev = i >= 1 ? U[i - 1][0] : 0.0;
+        slack_rcp(psi, v, u0, u1, true, il, iu);
+        lin_at(tg, v, u0, L);
+        hess_at(i, ls, dwv, tg, v, c, e, u0, dprev, ln, zl, zu, il, iu, H);
+      }
       if (ls) {
 #pragma unroll
         for (int k = 0; k < 6; k++) d[k] = 0.0;
@@ -520,7 +621,7 @@ struct Lane {
       // 2x2 control pivot
       const double det = Mdd * Maa - Mda * Mda;
       ok = ok && (Mdd > 0.0) && (det > 0.0);
-      const double idet = 1.0 / det;
+      const double idet = rcp(det);
       const double i11 = Maa * idet, i12 = -Mda * idet, i22 = Mdd * idet;
       // gains K0 (delta), K1 (a) over columns x, y, psi, v, delta_prev (epsi column is zero)
       const double cd[5] = {Mxd, Myd, Mpd, Mvd, -cwe};
@@ -575,126 +676,88 @@ struct Lane {
   }
 
   // ------------------------------------------------------------------------------------------
-  // slot 4a: forward sweep -> primal step
+  // slot 4 (forward sweep): primal step from the gains, fused with the step-length ratios (fraction
+  // to the boundary for x and for z) and grad(phi_mu)^T dx of the line search
   // ------------------------------------------------------------------------------------------
-  __device__ void forward(bool ls, bool soc) {
-    const double dt = PC[LC_DT];
+  __device__ void forward_and_ratios(bool ls, bool soc) {
+    const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     double t[6], dp = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; k++) t[k] = ls ? 0.0 : (soc ? -cs0[k] : -c0[k]);
-#pragma unroll 1
-    for (int i = 0; i < N - 1; i++) {
-      double kg[12];
-#pragma unroll
-      for (int k = 0; k < 12; k++) kg[k] = KG[i][k];
-      const double u0 = kg[10] + kg[0] * t[0] + kg[1] * t[1] + kg[2] * t[2] + kg[3] * t[3] + kg[4] * dp;
-      const double u1 = kg[11] + kg[5] * t[0] + kg[6] * t[1] + kg[7] * t[2] + kg[8] * t[3] + kg[9] * dp;
-#pragma unroll
-      for (int k = 0; k < 6; k++) DS[i][k] = t[k];
-      DU[i][0] = u0; DU[i][1] = u1;
-      StageLin L;
-      double tg[8];
-      stage_lin(i, L, tg);
-      double d[6];
-      if (ls) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) d[k] = 0.0;
-      } else if (soc) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) d[k] = -CS[i][k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 6; k++) d[k] = -CN[i][k];
-      }
-      const double n0 = t[0] + L.a13 * t[2] + L.a14 * t[3] + d[0];
-      const double n1 = t[1] + L.a23 * t[2] + L.a24 * t[3] + d[1];
-      const double n2 = t[2] + L.a34 * t[3] + L.b3 * u0 + d[2];
-      const double n3 = t[3] + dt * u1 + d[3];
-      const double n4 = L.a51 * t[0] - t[1] + L.a54 * t[3] + L.a56 * t[5] + d[4];
-      const double n5 = L.a61 * t[0] + t[2] + L.a34 * t[3] + L.b3 * u0 + d[5];
-      t[0] = n0; t[1] = n1; t[2] = n2; t[3] = n3; t[4] = n4; t[5] = n5;
-      dp = u0;
-    }
-#pragma unroll
-    for (int k = 0; k < 6; k++) DS[N - 1][k] = t[k];
-  }
-
-  // ------------------------------------------------------------------------------------------
-  // slot 4b: backward costate recursion -> new multipliers, fused with the step-length ratios
-  // (fraction to the boundary for x and z) and grad(phi_mu)^T dx
-  // ------------------------------------------------------------------------------------------
-  __device__ void costate_and_ratios(bool ls, double dwv) {
-    const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
-    double ln[6] = {0, 0, 0, 0, 0, 0};
     double rmax = 0.0;             // max over bounds of  -dx/(x-lo)  or  dx/(hi-x)
     double zn = 1.0, zd = 0.0;     // running minimum of z / (-dz) as a fraction zn / zd (zd > 0)
-    double acc = 0.0, dnext = 0.0, lmax = 0.0;
+    double acc = 0.0, dprev = 0.0;
 #pragma unroll 1
-    for (int i = N - 1; i >= 0; i--) {
+    for (int i = 0; i < N; i++) {
       const bool hasu = i < N - 1;
-      StageLin L;
-      StageHess H;
-      double tg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (hasu) stage_lin(i, L, tg);
-      stage_hess(i, ls, dwv, tg, H);
-      double ds[6], du0 = 0.0, du1 = 0.0;
+      double du0 = 0.0, du1 = 0.0, u0 = 0.0, u1 = 0.0;
+      const double psi = S[i][2], v = S[i][3];
 #pragma unroll
-      for (int k = 0; k < 6; k++) ds[k] = DS[i][k];
-      if (hasu) { du0 = DU[i][0]; du1 = DU[i][1]; }
-      double h[6];
-      h[0] = H.qxx * ds[0];
-      h[1] = H.qyy * ds[1];
-      h[2] = H.qpp * ds[2] + H.qpv * ds[3] + H.gp;
-      h[3] = H.qpv * ds[2] + H.qvv * ds[3] + H.qve * ds[5] + H.gv + H.svd * du0;
-      h[4] = H.qcc * ds[4] + H.gc;
-      h[5] = H.qve * ds[3] + H.qee * ds[5] + H.ge;
-      double out[6];
+      for (int k = 0; k < 6; k++) DS[i][k] = t[k];
+      double tn[6] = {0, 0, 0, 0, 0, 0};
       if (hasu) {
-        const double l25 = ln[2] + ln[5];
-        out[0] = ln[0] + L.a51 * ln[4] + L.a61 * ln[5] - h[0];
-        out[1] = ln[1] - ln[4] - h[1];
-        out[2] = L.a13 * ln[0] + L.a23 * ln[1] + l25 - h[2];
-        out[3] = L.a14 * ln[0] + L.a24 * ln[1] + L.a34 * l25 + ln[3] + L.a54 * ln[4] - h[3];
-        out[4] = -h[4];
-        out[5] = L.a56 * ln[4] - h[5];
-      } else {
+        double kg[12], tg[8], d[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) out[k] = -h[k];
-      }
+        for (int k = 0; k < 12; k++) kg[k] = KG[i][k];
 #pragma unroll
-      for (int k = 0; k < 6; k++) { LN[i][k] = out[k]; ln[k] = out[k]; lmax = nanmax(lmax, fabs(out[k])); }
-      if (!ls) {
-        const double v = S[i][3];
-        acc += (wv2 * (v - vref(i)) + nv2(i) * v) * ds[3] + wc2(i) * S[i][4] * ds[4] + we2(i) * S[i][5] * ds[5];
-        if (hasu) {
-          const double d0 = U[i][0];
-          double gd = wd2 * d0;
-          if (i >= 1) gd += cw * (d0 - U[i - 1][0]);
-          if (i <= N - 3) gd -= cw * (dnext - d0);
-          acc += gd * du0;
-          dnext = d0;
+        for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
+        u0 = U[i][0]; u1 = U[i][1];
+        du0 = kg[10] + kg[0] * t[0] + kg[1] * t[1] + kg[2] * t[2] + kg[3] * t[3] + kg[4] * dp;
+        du1 = kg[11] + kg[5] * t[0] + kg[6] * t[1] + kg[7] * t[2] + kg[8] * t[3] + kg[9] * dp;
+        DU[i][0] = du0; DU[i][1] = du1;
+        if (ls) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) d[k] = 0.0;
+        } else if (soc) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) d[k] = -CS[i][k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) d[k] = -CN[i][k];
         }
-        const double dx[4] = {ds[2], ds[3], du0, du1};
+        StageLin L;
+        lin_at(tg, v, u0, L);
+        tn[0] = t[0] + L.a13 * t[2] + L.a14 * t[3] + d[0];
+        tn[1] = t[1] + L.a23 * t[2] + L.a24 * t[3] + d[1];
+        tn[2] = t[2] + L.a34 * t[3] + L.b3 * du0 + d[2];
+        tn[3] = t[3] + dt * du1 + d[3];
+        tn[4] = L.a51 * t[0] - t[1] + L.a54 * t[3] + L.a56 * t[5] + d[4];
+        tn[5] = L.a61 * t[0] + t[2] + L.a34 * t[3] + L.b3 * du0 + d[5];
+      }
+      if (!ls) {
+        acc += (wv2 * (v - vref(i)) + nv2(i) * v) * t[3] + wc2(i) * S[i][4] * t[4] + we2(i) * S[i][5] * t[5];
+        if (hasu) {
+          double gd = wd2 * u0;
+          if (i >= 1) gd += cw * (u0 - dprev);
+          if (i <= N - 3) gd -= cw * (U[i + 1][0] - u0);
+          acc += gd * du0;
+          dprev = u0;
+        }
+        double il[4], iu[4];
+        slack_rcp(psi, v, u0, u1, hasu, il, iu);
+        const double dx[4] = {t[2], t[3], du0, du1};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           if (k < 2 || hasu) {
-            const double il = IL[i][k], iu = IU[i][k], zl = ZL[i][k], zu = ZU[i][k];
-            acc += mu * (iu - il) * dx[k];
-            rmax = fmax(rmax, fmax(-dx[k] * il, dx[k] * iu));
-            const double dzl = (mu - zl * dx[k]) * il - zl;
-            const double dzu = (mu + zu * dx[k]) * iu - zu;
+            const double zl = ZL[i][k], zu = ZU[i][k];
+            acc += mu * (iu[k] - il[k]) * dx[k];
+            rmax = fmax(rmax, fmax(-dx[k] * il[k], dx[k] * iu[k]));
+            const double dzl = (mu - zl * dx[k]) * il[k] - zl;
+            const double dzu = (mu + zu * dx[k]) * iu[k] - zu;
             // z/(-dz) < zn/zd  <=>  z*zd < zn*(-dz)   (all denominators positive)
             if (dzl < 0.0 && (zd == 0.0 || zl * zd < zn * (-dzl))) { zn = zl; zd = -dzl; }
             if (dzu < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu))) { zn = zu; zd = -dzu; }
           }
         }
       }
+#pragma unroll
+      for (int k = 0; k < 6; k++) t[k] = tn[k];
+      dp = du0;
     }
-    lsq_lmax = lmax;
     gbd_new = acc;
     if (ls) return;
     // alpha_max = min(1, tau / rmax),  alpha_z = min(1, tau * zn / zd)
-    alpha_soc = (rmax * 1.0 > tau) ? tau / rmax : 1.0;
+    alpha_soc = (rmax > tau) ? tau / rmax : 1.0;
     alpha_z = (zd > 0.0 && tau * zn < zd) ? tau * zn / zd : 1.0;
   }
 
@@ -816,21 +879,15 @@ struct Lane {
     if (P.iters) P.iters[b] = iter;
   }
 
-  // CS = a * (first ? CN : CS) + CT     (Ipopt's accumulated second-order-correction rhs)
-  __device__ void soc_rhs(bool first, double a) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) cs0[k] = a * (first ? c0[k] : cs0[k]) + c0t[k];
-#pragma unroll 1
-    for (int i = 0; i < N - 1; i++) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) CS[i][k] = a * (first ? CN[i][k] : CS[i][k]) + CT[i][k];
-    }
-  }
 };
 
-// Persistent grid; every lane pulls problems from the global counter until the batch is exhausted.
+// Persistent grid, one CTA per SM; every lane pulls problems from the global counter until the batch is
+// exhausted.  The warps of a CTA walk through the slots of a trip together (__syncthreads between
+// slots): the loop body is ~100 KB of code, and warps at different places in it thrash the instruction
+// cache (profiles/r01_v3_*: 3.3 issue slots lost per instruction to "no instruction"); in step, the
+// CTA's instruction footprint is one sweep at a time.
 template <int NS, int MINB>
-__global__ void __launch_bounds__(128, MINB) mpc_lane_kernel(const KParams P) {
+__global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
   Lane<NS> Z;
   Z.mode = LM_IDLE;
   Z.b = 0;
@@ -841,7 +898,7 @@ __global__ void __launch_bounds__(128, MINB) mpc_lane_kernel(const KParams P) {
       const int nb = atomicAdd(P.counter, 1);
       if (nb < P.B) Z.init(P, nb); else Z.mode = LM_DONE;
     }
-    if (__all_sync(0xffffffffu, Z.mode == LM_DONE)) break;
+    if (__syncthreads_and(Z.mode == LM_DONE)) break;
 
     // ---- slot 1: evaluate a point
     const int m1 = Z.mode;
@@ -849,17 +906,19 @@ __global__ void __launch_bounds__(128, MINB) mpc_lane_kernel(const KParams P) {
       const double a = m1 == LM_EV0 ? 0.0 : (m1 == LM_TRIAL ? Z.alpha : Z.alpha_soc);
       Z.eval_sweep(a);
     }
+    __syncthreads();
 
-    // ---- slot 2: acceptance logic, iterate update, KKT errors, barrier update
-    bool upd = false, err = false, take_lsq = false, lsq_bad = false;
+    // ---- slot 2: acceptance logic, then the sweep that accepts the step and measures the KKT error
+    bool upd = false, lsq = false, zero = false, err = false;
     if (m1 == LM_EV0) {
       Z.alpha = 0.0; Z.alpha_z = 0.0;
       Z.theta_max = 1e4 * fmax(1.0, Z.tht);
       Z.theta_min = 1e-4 * fmax(1.0, Z.tht);
       upd = true;
     } else if (m1 == LM_LSQ_DONE) {
-      err = true; take_lsq = true;
-      lsq_bad = !(Z.lsq_lmax <= K_CONSTR_MULT_INIT_MAX);
+      lsq = true; err = true;
+    } else if (m1 == LM_LSQ_ZERO) {
+      zero = true; err = true;
     } else if (m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
       const double phi_t = Z.ft - Z.mu * Z.lt;
       if (m1 == LM_TRIAL) Z.alpha_test = Z.alpha;
@@ -893,26 +952,32 @@ __global__ void __launch_bounds__(128, MINB) mpc_lane_kernel(const KParams P) {
     }
     // one copy of the sweep for every path: keep the compiler from cloning it per state (a clone run
     // by two or three lanes costs the warp a full pass)
-    int flags = (upd ? 1 : 0) | (err ? 2 : 0) | (take_lsq ? 4 : 0) | (lsq_bad ? 8 : 0);
+    int flags = (upd ? 1 : 0) | (lsq ? 2 : 0) | (zero ? 4 : 0) | (err ? 8 : 0);
     asm volatile("" : "+r"(flags));
-    upd = flags & 1; err = flags & 2; take_lsq = flags & 4; lsq_bad = flags & 8;
-    if (upd || err) {
-      Z.update_and_errors(upd, take_lsq, lsq_bad);
+    upd = flags & 1; lsq = flags & 2; zero = flags & 4; err = flags & 8;
+    if (flags) {
+      Z.advance(upd, lsq, zero);
       if (upd) { Z.fx = Z.ft; Z.lsum = Z.lt; Z.theta = Z.tht; }
       if (m1 == LM_EV0) {
         Z.mode = LM_LSQ;
+      } else if (lsq && !(Z.lsq_lmax <= K_CONSTR_MULT_INIT_MAX)) {
+        Z.mode = LM_LSQ_ZERO;
       } else {
-        if (m1 != LM_LSQ_DONE) Z.iter++;
+        if (upd) Z.iter++;
         Z.check_and_update_mu(P);
       }
     }
+    __syncthreads();
 
     // ---- slot 3 + 4: factor and solve
     const int m3 = Z.mode;
-    if (m3 == LM_LSQ || m3 == LM_NEWTON || m3 == LM_SOC || m3 == LM_RESOLVE) {
-      const bool ls = m3 == LM_LSQ, soc = m3 == LM_SOC;
-      const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? Z.dw : Z.dw_used);
-      bool ok = Z.riccati(ls, soc, dwv);
+    const bool solve = m3 == LM_LSQ || m3 == LM_NEWTON || m3 == LM_SOC || m3 == LM_RESOLVE;
+    const bool ls = m3 == LM_LSQ, soc = m3 == LM_SOC;
+    const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? Z.dw : Z.dw_used);
+    bool ok = true;
+    if (solve) ok = Z.riccati(ls, soc, dwv);
+    __syncthreads();
+    if (solve) {
       if (m3 == LM_NEWTON && !ok) {
         // Ipopt's inertia correction schedule (delta_w)
         double d = Z.dw;
@@ -921,9 +986,9 @@ __global__ void __launch_bounds__(128, MINB) mpc_lane_kernel(const KParams P) {
         Z.dw = d;
         if (d > K_DW_MAX) { Z.status = 10; Z.mode = LM_FINISH; }
       } else {
-        Z.forward(ls, soc);
-        Z.costate_and_ratios(ls, dwv);
+        Z.forward_and_ratios(ls, soc);
         if (m3 == LM_LSQ) {
+          Z.dw_used = 0.0;
           Z.mode = LM_LSQ_DONE;
         } else if (m3 == LM_NEWTON) {
           if (Z.dw > 0.0) Z.dw_last = Z.dw;

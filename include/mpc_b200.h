@@ -134,8 +134,8 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
 
 /* Kernel selection.  MPC_KERNEL_AUTO (default): batches of at least MPC_LANE_MIN_BATCH problems, or
  * horizons above 32, run the throughput kernel (one problem per lane); smaller batches run the
- * latency kernel (one problem per warp).  lane_threads (32..128, multiple of 32; 0 = keep) and
- * lane_ctas_per_sm (0 = as many as fit) tune the persistent grid of the lane kernel. */
+ * latency kernel (one problem per warp).  lane_threads (CTA size 32..256, multiple of 32; 0 = automatic,
+ * balanced over the SMs) and lane_ctas_per_sm (0 = one) tune the persistent grid of the lane kernel. */
 #define MPC_KERNEL_AUTO 0
 #define MPC_KERNEL_WARP 1
 #define MPC_KERNEL_LANE 2

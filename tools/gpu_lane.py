@@ -46,7 +46,7 @@ def run(reps=5):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-for thr, ctas in ((32, 0), (32, 10), (32, 9), (32, 8), (32, 7), (32, 6), (32, 5), (32, 4), (128, 2)):
+for thr, ctas in ((0, 0), (256, 1), (224, 1), (192, 1), (160, 1), (128, 1), (128, 2), (96, 2), (64, 3), (32, 7)):
     S.set_kernel(mpc.KERNEL_LANE, thr, ctas)
     ms = run()
     print('lane threads=%d ctas/sm=%d  B=%d  %.3f ms  %.0f solves/s  ok=%.4f iters=%.2f' % (thr, ctas, B, ms, B / ms * 1e3, (status == 1).float().mean().item(), iters.float().mean().item()))

@@ -7,7 +7,7 @@ srcname = sys.argv[4] if len(sys.argv) > 4 else "mpc_kernel.cuh"
 ntop = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 tmp = tempfile.mkdtemp()
 subprocess.check_call("cd %s && cuobjdump -xelf all %s > /dev/null" % (tmp, os.path.abspath(lib)), shell=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+cubin = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 line_of = {}
 cur = None
