@@ -50,18 +50,20 @@ enum { LC_DT = 0, LC_DTLF, LC_SF, LC_CW, LC_WC2, LC_WE2, LC_WV2, LC_VREF, LC_WD2
        LC_VREF_0, LC_NV2_0, LC_C0, LC_S0 = LC_C0 + 5, LC_LO = LC_S0 + 6, LC_HI = LC_LO + 4,
        LC_LO0 = LC_HI + 4, LC_HI0 = LC_LO0 + 4, LC_SIZE = LC_HI0 + 4 };
 
-// 1/a for a normal, finite a (slacks, 1 + f'^2, pivots): hardware seed + two Newton steps.  Accurate to
-// ~1 ulp; a third of the instructions of the correctly-rounded division, which dominated the sweeps.
+// 1/a for a normal, finite a (slacks, 1 + f'^2, pivots): hardware seed (20 bits) + two Newton steps.  Accurate to
+// ~1 ulp (measured on B200: seed 1e-6, one step 1e-12, two steps exact to rounding); a third of the instructions of the correctly-rounded division, which dominated the sweeps.
 __device__ __forceinline__ double rcp(double a) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
   double e = fma(-a, x, 1.0);
   x = fma(x, e, x);
   e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
   return fma(x, e, x);
 }
+// min / max without fmin/fmax's NaN handling: FP64 has no min/max instruction and the library versions
+// expand to ~13 instructions each; the sweeps take ~50 of them per stage.  NaN in `b` is returned.
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 
 struct StageLin { double a13, a14, a23, a24, a34, b3, a51, a54, a56, a61; };
 struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa, gp, gv, gc, ge, gdp, gd, ga; };
@@ -69,14 +71,22 @@ struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa,
 template <int NS>
 struct Lane {
   // ---- per-stage data (thread-private memory): 70 doubles per stage are touched on the common path
-  double S[NS][6], U[NS][2], LAM[NS][6], ZL[NS][4], ZU[NS][4];   // iterate
-  double TG[NS][8], CN[NS][6];   // sin/cos psi, sin/cos epsi, f', f'', a61, g3 and c_{i+1} at the iterate
-  double DS[NS][6], DU[NS][2];   // primal search direction
-  double TT[NS][8], CT[NS][6];   // the same as TG / CN at the trial point (copied on acceptance)
-  double KG[NS][12];             // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
-  double CS[NS][6];              // second-order-correction right-hand side (rare path only)
-  double PC[LC_SIZE];
-  double FLT[2 * K_NFILT];
+  // (16-byte aligned rows: the compiler pairs neighbouring doubles into 128-bit local loads/stores)
+  alignas(16) double S[NS][6];     // iterate: x, y, psi, v, cte, epsi
+  alignas(16) double U[NS][2];     //          delta, a
+  alignas(16) double LAM[NS][6];   //          multipliers of the constraint defining s_i
+  alignas(16) double ZL[NS][4];    //          bound multipliers of psi, v, delta, a
+  alignas(16) double ZU[NS][4];
+  alignas(16) double TG[NS][8];    // sin/cos psi, sin/cos epsi, f', f'', a61, g3 at the iterate
+  alignas(16) double CN[NS][6];    // c_{i+1} at the iterate
+  alignas(16) double DS[NS][6];    // primal search direction
+  alignas(16) double DU[NS][2];
+  alignas(16) double TT[NS][8];    // TG / CN at the trial point (copied on acceptance)
+  alignas(16) double CT[NS][6];
+  alignas(16) double KG[NS][12];   // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
+  alignas(16) double CS[NS][6];    // second-order-correction right-hand side (rare path only)
+  alignas(16) double PC[LC_SIZE];
+  alignas(16) double FLT[2 * K_NFILT];
   double c0[6], c0t[6], cs0[6];
   // ---- scalars ----
   int b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt;
@@ -408,8 +418,8 @@ struct Lane {
             if (k < 2 || hasu) {
               const double dzl = (mu - zl[k] * dx[k]) * il[k] - zl[k];
               const double dzu = (mu + zu[k] * dx[k]) * iu[k] - zu[k];
-              zl[k] = fmax(fmin(zl[k] + az * dzl, zcap * iln[k]), zfloor * iln[k]);
-              zu[k] = fmax(fmin(zu[k] + az * dzu, zcap * iun[k]), zfloor * iun[k]);
+              zl[k] = dmax(dmin(zl[k] + az * dzl, zcap * iln[k]), zfloor * iln[k]);
+              zu[k] = dmax(dmin(zu[k] + az * dzu, zcap * iun[k]), zfloor * iun[k]);
               ZL[i][k] = zl[k]; ZU[i][k] = zu[k];
             }
           }
@@ -470,8 +480,8 @@ struct Lane {
       {
         const double p0 = (s[2] - PC[LC_LO]) * zl[0], p1 = (PC[LC_HI] - s[2]) * zu[0];
         const double p2 = (s[3] - PC[LC_LO + 1]) * zl[1], p3 = (PC[LC_HI + 1] - s[3]) * zu[1];
-        am = fmin(am, fmin(fmin(p0, p1), fmin(p2, p3)));
-        aM = fmax(aM, fmax(fmax(p0, p1), fmax(p2, p3)));
+        am = dmin(am, dmin(dmin(p0, p1), dmin(p2, p3)));
+        aM = dmax(aM, dmax(dmax(p0, p1), dmax(p2, p3)));
       }
       if (hasu) {
         double gd = wd2 * u0;
@@ -482,8 +492,8 @@ struct Lane {
         zz += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
         const double p0 = (u0 - PC[LC_LO + 2]) * zl[2], p1 = (PC[LC_HI + 2] - u0) * zu[2];
         const double p2 = (u1 - PC[LC_LO + 3]) * zl[3], p3 = (PC[LC_HI + 3] - u1) * zu[3];
-        am = fmin(am, fmin(fmin(p0, p1), fmin(p2, p3)));
-        aM = fmax(aM, fmax(fmax(p0, p1), fmax(p2, p3)));
+        am = dmin(am, dmin(dmin(p0, p1), dmin(p2, p3)));
+        aM = dmax(aM, dmax(dmax(p0, p1), dmax(p2, p3)));
         dnext = u0;
       }
 #pragma unroll
@@ -741,7 +751,7 @@ struct Lane {
           if (k < 2 || hasu) {
             const double zl = ZL[i][k], zu = ZU[i][k];
             acc += mu * (iu[k] - il[k]) * dx[k];
-            rmax = fmax(rmax, fmax(-dx[k] * il[k], dx[k] * iu[k]));
+            rmax = dmax(rmax, dmax(-dx[k] * il[k], dx[k] * iu[k]));
             const double dzl = (mu - zl * dx[k]) * il[k] - zl;
             const double dzu = (mu + zu * dx[k]) * iu[k] - zu;
             // z/(-dz) < zn/zd  <=>  z*zd < zn*(-dz)   (all denominators positive)
