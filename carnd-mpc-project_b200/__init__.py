@@ -32,7 +32,8 @@ STATUS_NAMES = {0: "not_defined", 1: "success", 2: "maxiter_exceeded", 3: "stop_
 EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json", "mpc_create",
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
-           "mpc_run_prepare", "mpc_run_finish"]
+           "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
+           "mpc_rollout"]
 
 
 class MpcError(RuntimeError):
@@ -114,6 +115,12 @@ def lib():
     L.mpc_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.mpc_run_prepare.argtypes = [cfgp, dp, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, C.POINTER(MpcRunAux)]
     L.mpc_run_finish.argtypes = [cfgp, C.POINTER(MpcRunAux), C.c_double, dp, dp]
+    L.mpc_compute_throttle.argtypes = [cfgp, C.c_double, C.c_double]
+    L.mpc_compute_throttle.restype = C.c_double
+    L.mpc_vehicle_move.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.mpc_vehicle_move.restype = None
+    L.mpc_run_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int] + [vp] * 8 + [vp]
+    L.mpc_rollout.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double, vp, vp]
     L.mpc_launch_count.argtypes = [vp]
     L.mpc_launch_count.restype = C.c_longlong
     L.mpc_last_error.restype = C.c_char_p
@@ -180,6 +187,18 @@ def run_finish(cfg, aux, v, result9):
     _check(lib().mpc_run_finish(C.byref(cfg), C.byref(aux), float(v), r.ctypes.data_as(dp), out.ctypes.data_as(dp)),
            "mpc_run_finish")
     return out
+
+
+def compute_throttle(cfg, accel, target):
+    """Vehicle::computeThrottle (Vehicle.cpp:81-103)."""
+    return lib().mpc_compute_throttle(C.byref(cfg), float(accel), float(target))
+
+
+def vehicle_move(pose4, steering, accel, length, dt):
+    """Vehicle::move (Vehicle.cpp:145-168): (x, y, psi, v) -> moved copy."""
+    p = np.array(pose4, dtype=np.float64)
+    lib().mpc_vehicle_move(p.ctypes.data_as(C.POINTER(C.c_double)), float(steering), float(accel), float(length), float(dt))
+    return p
 
 
 def _ptr(t):
@@ -265,6 +284,26 @@ class Solver:
         if want_full:
             out["full"] = full.T.copy()
         return out
+
+    def run_batch_device(self, B, pose, ptsx, ptsy, npts, out8, steering=None, traj_x=None, traj_y=None,
+                         coeffs_out=None, ptsx_v=None, ptsy_v=None, status=None, iters=None, stream=None):
+        """MPC::run for a batch on the device; every array a DEVICE tensor ([k][B] layout)."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        _check(lib().mpc_run_batch(self._h, B, _ptr(pose), _ptr(steering), _ptr(ptsx), _ptr(ptsy), npts, _ptr(out8),
+                                   _ptr(traj_x), _ptr(traj_y), _ptr(coeffs_out), _ptr(ptsx_v), _ptr(ptsy_v),
+                                   _ptr(status), _ptr(iters), stream), "mpc_run_batch")
+
+    def rollout_device(self, V, T, track_x, track_y, veh, seg, pending, dt_ctrl=0.1, tau_solve=0.0, rec=None,
+                       stream=None):
+        """Closed loop, V vehicles x T control steps (BASELINE config 5); DEVICE tensors, asynchronous."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        _check(lib().mpc_rollout(self._h, V, T, _ptr(track_x), _ptr(track_y), int(track_x.numel()), _ptr(veh),
+                                 _ptr(seg), _ptr(pending), float(dt_ctrl), float(tau_solve), _ptr(rec), stream),
+               "mpc_rollout")
 
     def solve_one(self, state, coeffs, yaw_lo, yaw_hi):
         N = self.cfg.N

@@ -17,6 +17,7 @@
 
 #include "mpc_kernel.cuh"
 #include "mpc_lane_kernel.cuh"
+#include "mpc_rollout.cuh"
 
 using namespace mpcb200;
 
@@ -48,6 +49,9 @@ struct mpc_handle {
   size_t cap_B;
   int cap_N;
   bool cap_w;
+  double *d_run;        // device workspace of the run()/rollout entry points
+  int *d_run_i;
+  size_t cap_run;
   cudaStream_t stream;
 };
 
@@ -266,6 +270,8 @@ extern "C" void mpc_destroy(mpc_handle *h) {
   cudaFree(h->d_out);
   cudaFree(h->d_iout);
   cudaFreeHost(h->h_pin);
+  cudaFree(h->d_run);
+  cudaFree(h->d_run_i);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -441,6 +447,81 @@ extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *c
   if (!h || !state || !coeffs || !result) return MPC_EINVAL;
   return mpc_solve_batch_host(h, 1, state, coeffs, &yaw_lo, &yaw_hi, nullptr, nullptr, nullptr, result, traj_x,
                               traj_y, nullptr, status, iters);
+}
+
+// ---- whole control steps on the device ------------------------------------------------------------
+// workspace: state 6, coeffs 5, yaw 2, aux 4, result 9 doubles per vehicle; status, iters ints
+static int ensure_run_ws(mpc_handle *h, size_t B) {
+  if (h->d_run && h->cap_run >= B) return MPC_OK;
+  cudaFree(h->d_run); cudaFree(h->d_run_i);
+  h->d_run = nullptr; h->d_run_i = nullptr;
+  size_t cap = B < 1024 ? 1024 : B;
+  CK(cudaMalloc(&h->d_run, 26 * cap * sizeof(double)));
+  CK(cudaMalloc(&h->d_run_i, 2 * cap * sizeof(int)));
+  h->cap_run = cap;
+  return MPC_OK;
+}
+
+extern "C" int mpc_run_batch(mpc_handle *h, int B, const double *pose, const double *steering, const double *ptsx,
+                             const double *ptsy, int npts, double *out8, double *traj_x, double *traj_y,
+                             double *coeffs_out, double *ptsx_v, double *ptsy_v, int *status, int *iters,
+                             void *cuda_stream) {
+  if (!h || B < 0 || !pose || !ptsx || !ptsy || !out8 || npts < 3 || npts > MPC_MAX_WAYPOINTS) return MPC_EINVAL;
+  if (B == 0) return MPC_OK;
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_run_ws(h, (size_t)B);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double *w = h->d_run;               // packed at stride B: state 6, yaw 2, aux 4, result 9, coeffs 5
+  RunBatch R;
+  R.B = B; R.npts = npts; R.pose = pose; R.steering = steering; R.ptsx = ptsx; R.ptsy = ptsy;
+  R.ptsx_v = ptsx_v; R.ptsy_v = ptsy_v;
+  R.state = w; R.yaw_lo = w + 6 * (size_t)B; R.yaw_hi = R.yaw_lo + B; R.aux = R.yaw_hi + B;
+  double *result = R.aux + 4 * (size_t)B;
+  R.coeffs = coeffs_out ? coeffs_out : result + 9 * (size_t)B;
+  int *d_status = status ? status : h->d_run_i, *d_iters = iters ? iters : h->d_run_i + B;
+  const int thr = 128, grid = (B + thr - 1) / thr;
+  mpc_run_pre_kernel<<<grid, thr, 0, st>>>(h->cfg, R);
+  CK(cudaGetLastError());
+  rc = mpc_solve_batch(h, B, R.state, R.coeffs, R.yaw_lo, R.yaw_hi, nullptr, nullptr, nullptr, result, traj_x, traj_y,
+                       nullptr, d_status, d_iters, st);
+  if (rc) return rc;
+  mpc_run_post_kernel<<<grid, thr, 0, st>>>(h->cfg, B, R.aux, result, out8);
+  CK(cudaGetLastError());
+  h->launches += 2;
+  return MPC_OK;
+}
+
+extern "C" int mpc_rollout(mpc_handle *h, int V, int T, const double *track_x, const double *track_y, int n_track,
+                           double *veh, int *seg, double *pending, double dt_ctrl, double tau_solve, double *rec,
+                           void *cuda_stream) {
+  if (!h || V < 0 || T < 0 || !track_x || !track_y || n_track < 6 || !veh || !seg || !(dt_ctrl > 0)) return MPC_EINVAL;
+  if (h->cfg.latency_ms && !pending) return MPC_EINVAL;
+  if (V == 0 || T == 0) return MPC_OK;
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_run_ws(h, (size_t)V);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double *w = h->d_run;
+  LoopArgs A;
+  A.V = V; A.n_track = n_track; A.track_x = track_x; A.track_y = track_y; A.veh = veh; A.seg = seg; A.pending = pending;
+  A.dt_ctrl = dt_ctrl; A.tau_solve = tau_solve; A.rec = rec;
+  A.state = w; A.coeffs = w + 6 * (size_t)V; A.yaw_lo = w + 11 * (size_t)V; A.yaw_hi = w + 12 * (size_t)V;
+  A.aux = w + 13 * (size_t)V; A.result = w + 17 * (size_t)V;
+  int *d_status = h->d_run_i, *d_iters = h->d_run_i + V;
+  A.status = d_status; A.iters = d_iters;
+  const int thr = 128, grid = (V + thr - 1) / thr;
+  for (int k = 0; k < T; k++) {
+    A.step = k;
+    mpc_loop_pre_kernel<<<grid, thr, 0, st>>>(h->cfg, A);
+    rc = mpc_solve_batch(h, V, A.state, A.coeffs, A.yaw_lo, A.yaw_hi, nullptr, nullptr, nullptr, A.result, nullptr,
+                         nullptr, nullptr, d_status, d_iters, st);
+    if (rc) return rc;
+    mpc_loop_post_kernel<<<grid, thr, 0, st>>>(h->cfg, A);
+    h->launches += 2;
+  }
+  CK(cudaGetLastError());
+  return MPC_OK;
 }
 
 // ---- FP64 FMA peak micro-benchmark (roofline denominator) -----------------------------------------

@@ -166,6 +166,35 @@ int mpc_run_prepare(const mpc_config *cfg, const double *pose, double steering, 
  * (sharp-turn steering adjustment, acceleration clamp, normalisation: MPC.cpp:361-381).  v = pose[3]. */
 int mpc_run_finish(const mpc_config *cfg, const mpc_run_aux *aux, double v, const double *result9, double *out8);
 
+/* Vehicle::computeThrottle (Vehicle.cpp:81-103) and Vehicle::move (Vehicle.cpp:145-168, pose4 = x, y, psi, v in/out) */
+double mpc_compute_throttle(const mpc_config *cfg, double accel, double target);
+void mpc_vehicle_move(double *pose4, double steering, double accel, double length, double dt);
+
+/* MPC::run for a batch, entirely on the device (DEVICE pointers, async on cuda_stream): one kernel does the
+ * pre-processing of mpc_run_prepare for every vehicle, the solve follows, one kernel does mpc_run_finish.
+ *   pose [4][B] x, y, psi, v;  steering [B] or NULL;  ptsx, ptsy [npts][B] global waypoints (3..16)
+ *   out8 [8][B]  MPC::run's return vector;  traj_x/traj_y [N][B] or NULL;  coeffs_out [5][B] or NULL;
+ *   ptsx_v, ptsy_v [npts][B] or NULL: the waypoints in the vehicle frame (what MPC.cpp:329 leaves behind) */
+int mpc_run_batch(mpc_handle *h, int B, const double *pose, const double *steering, const double *ptsx,
+                  const double *ptsy, int npts, double *out8, double *traj_x, double *traj_y, double *coeffs_out,
+                  double *ptsx_v, double *ptsy_v, int *status, int *iters, void *cuda_stream);
+
+/* Closed loop for V vehicles x T control steps on the device (BASELINE config 5): the message handler of
+ * src/mpc_main.cpp:113-214 with the simulator replaced by the reference's own kinematic plant.  Per step and
+ * vehicle: 6-waypoint window starting at the last waypoint behind the car; psi normalised; acceleration
+ * estimate (throttle - v/50)*6; if cfg.latency_ms != 0 the pose is moved ahead by lookahead + tau_solve
+ * (tau_solve replaces the reference's running mean of measured solve times, which is not reproducible);
+ * MPC::run; throttle = computeThrottle; the command reaches the actuators one control interval later when
+ * cfg.latency_ms != 0 (the reference sleeps `latency` ms before answering), immediately otherwise; the
+ * plant advances dt_ctrl with Vehicle::move and acceleration (throttle - v/50)*6.
+ *   track_x, track_y [n_track] closed centre line;  veh [6][V] in/out: x, y, psi, v, steering angle [rad],
+ *   last throttle;  seg [V] in/out: first waypoint of the window;  pending [2][V] in/out: command in flight
+ *   (delta, throttle), required when cfg.latency_ms != 0;  rec [T][8][V] or NULL: per step cte, epsi, v,
+ *   steer in [-1,1], throttle, cost, status, iterations.  DEVICE pointers; async on cuda_stream. */
+int mpc_rollout(mpc_handle *h, int V, int T, const double *track_x, const double *track_y, int n_track,
+                double *veh, int *seg, double *pending, double dt_ctrl, double tau_solve, double *rec,
+                void *cuda_stream);
+
 /* Measure the device's FP64 FMA peak with a dependent-chain-free DFMA micro-kernel (8 independent
  * chains per thread, every SM full): the roofline denominator bench.py reports against, since
  * MEASURED_PEAKS.json holds no FP64 figure.  *tflops = 2 * FMAs / seconds / 1e12. */

@@ -86,5 +86,24 @@ for (Ng, dtg) in [(10, 0.1), (20, 0.1), (30, 0.1), (10, 0.05), (20, 0.05), (30, 
                             "traj_x": L(s["traj_x"]), "traj_y": L(s["traj_y"])})
     print("grid", Ng, dtg, [c["status"] for c in out["grid"][-3:]], [c["iters"] for c in out["grid"][-3:]])
 pr.set_horizon(js["N"], js["dt"])
+
+# (e) plant and actuation map: Vehicle::move, Vehicle::computeThrottle (Vehicle.cpp:81-103,145-168)
+out["plant"] = {"move": [], "throttle": []}
+rng = np.random.default_rng(11)
+for name in ("stable", "fast"):
+    js = rd["configs"][name]
+    pr.config_load(js)
+    cd = po.load_config_dict(js)
+    for _ in range(20):
+        pose = [rng.uniform(-200, 200), rng.uniform(-200, 200), rng.uniform(-4, 4), rng.uniform(0, 70), rng.uniform(-0.4, 0.4), rng.uniform(-9, 5)]
+        dt = float(rng.choice([0.02, 0.1, 0.12]))
+        p6 = np.array(pose)
+        pr.lib().ref_vehicle_move(p6.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)), cd["Lf"], dt)
+        out["plant"]["move"].append({"config": name, "pose": pose, "dt": dt, "moved": L(p6[:4])})
+    for accel in [-20, -15, -12, -10, -7, -5, -3, -0.5, 0.0, 0.0005, 0.001, 0.5, 2.0, 4.4, 6.0]:
+        target = float(rng.uniform(0, 60))
+        t = pr.lib().ref_compute_throttle(float(accel), target, cd["max_accel"], cd["max_decel"])
+        out["plant"]["throttle"].append({"config": name, "accel": float(accel), "target": target, "throttle": t})
+pr.config_load(rd["configs"]["stable"])
 json.dump(out, open(os.path.join(HERE, "ref_golden.json"), "w"), indent=0)
 print("wrote ref_golden.json", os.path.getsize(os.path.join(HERE, "ref_golden.json")), "bytes")

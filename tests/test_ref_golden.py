@@ -131,3 +131,19 @@ def test_live_reference_build_agrees_with_oracle(po, refdata):
         o = po.solve(cfg, po.make_problem(st, co, -0.1, 0.4))
         assert r["status"] == o["status"] == 1
         _cmp(o["result"], r["result"])
+
+
+def test_plant_and_throttle_map_match_reference(gold, mpc, refdata):
+    """mpc_vehicle_move / mpc_compute_throttle (product, shared host/device code) == Vehicle::move /
+    Vehicle::computeThrottle of the reference; so does the test-side restatement used for the rollout oracle."""
+    import closed_loop_restated as clr
+    for c in gold["plant"]["move"]:
+        cfg = mpc.config_from_json_text(json.dumps(refdata["configs"][c["config"]]))
+        p = c["pose"]
+        got = mpc.vehicle_move(p[:4], p[4], p[5], cfg.Lf, c["dt"])
+        assert np.allclose(got, c["moved"], rtol=0, atol=1e-12)
+        assert np.allclose(clr.vehicle_move(p[0], p[1], p[2], p[3], p[4], p[5], cfg.Lf, c["dt"]), c["moved"], rtol=0, atol=1e-12)
+    for c in gold["plant"]["throttle"]:
+        cfg = mpc.config_from_json_text(json.dumps(refdata["configs"][c["config"]]))
+        assert mpc.compute_throttle(cfg, c["accel"], c["target"]) == pytest.approx(c["throttle"], abs=1e-14)
+        assert clr.compute_throttle(cfg.as_dict(), c["accel"], c["target"]) == pytest.approx(c["throttle"], abs=1e-14)
