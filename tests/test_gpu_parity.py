@@ -213,14 +213,14 @@ def test_auto_dispatch_and_kernels_agree(mpc, stable_cfg, stable_cd):
     """MPC_KERNEL_AUTO: small batches take the warp kernel, large ones the lane kernel; both give the
     same optimum (they differ only in the order of the floating-point reductions)."""
     S = mpc.Solver(stable_cfg, 0)
-    b = mpc.workloads.batch_perturbed_states(2048, 77, stable_cd)
+    b = mpc.workloads.batch_perturbed_states(mpc.LANE_MIN_BATCH, 77, stable_cd)
     args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
     auto = S.solve_batch_host(*args)
     S.set_kernel(mpc.KERNEL_LANE)
     lane = S.solve_batch_host(*args)
     S.set_kernel(mpc.KERNEL_WARP)
     warp = S.solve_batch_host(*args)
-    assert np.array_equal(auto["result"], lane["result"])          # 2048 >= MPC_LANE_MIN_BATCH
+    assert np.array_equal(auto["result"], lane["result"])          # B >= MPC_LANE_MIN_BATCH
     ok = (lane["status"] == 1) & (warp["status"] == 1)
     assert ok.mean() > 0.99
     assert np.abs(lane["result"][ok, :8] - warp["result"][ok, :8]).max() < 1e-5
