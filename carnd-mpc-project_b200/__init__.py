@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 NCOEF, NTAB, NWEIGHTS, NMAX = 5, 16, 12, 64
-KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE = 0, 1, 2
+KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE, KERNEL_COOP = 0, 1, 2, 3
 LANE_MIN_BATCH = 3072
 
 STATUS_SUCCESS = 1

@@ -343,8 +343,34 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   return MPC_OK;
 }
 
+// The coop kernel: one problem per group of 16 or 32 lanes, per-stage rows in shared memory.
+template <int NS>
+static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
+  const int threads = 128;
+  const int G = NS <= 16 ? 16 : 32;
+  const int groups = threads / G;
+  const size_t smem = (size_t)groups * NS * ST_ROW * sizeof(double);
+  static thread_local int cached_dev = -1;
+  if (cached_dev != h->device) {
+    CK(cudaFuncSetAttribute(mpc_coop_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cached_dev = h->device;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<NS>, threads, smem));
+  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "coop kernel does not fit on an SM (smem %zu)", smem); return MPC_ECUDA; }
+  long long want = ((long long)kp.B + groups - 1) / groups;
+  long long grid = (long long)h->sm_count * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
+  mpc_coop_kernel<NS><<<(unsigned)grid, threads, smem, st>>>(kp);
+  CK(cudaGetLastError());
+  h->launches++;
+  return MPC_OK;
+}
+
 extern "C" int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm) {
-  if (!h || kind < MPC_KERNEL_AUTO || kind > MPC_KERNEL_LANE) return MPC_EINVAL;
+  if (!h || kind < MPC_KERNEL_AUTO || kind > MPC_KERNEL_COOP) return MPC_EINVAL;
   if (lane_threads != 0 && (lane_threads < 32 || lane_threads > 256 || lane_threads % 32)) return MPC_EINVAL;
   h->kernel_kind = kind;
   h->lane_threads = lane_threads;
@@ -380,6 +406,12 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   if (kind == MPC_KERNEL_WARP) {
     if (c.N > 32) { snprintf(g_err, sizeof(g_err), "warp kernel handles N <= 32"); return MPC_EINVAL; }
     return launch<32>(h, kp, (cudaStream_t)cuda_stream);
+  }
+  if (kind == MPC_KERNEL_COOP) {
+    if (c.N > 32) { snprintf(g_err, sizeof(g_err), "coop kernel handles N <= 32"); return MPC_EINVAL; }
+    if (c.N <= 10) return launch_coop<10>(h, kp, (cudaStream_t)cuda_stream);
+    if (c.N <= 16) return launch_coop<16>(h, kp, (cudaStream_t)cuda_stream);
+    return launch_coop<32>(h, kp, (cudaStream_t)cuda_stream);
   }
   if (c.N <= 10) return launch_lane<10, 1>(h, kp, (cudaStream_t)cuda_stream);
   if (c.N <= 20) return launch_lane<20, 1>(h, kp, (cudaStream_t)cuda_stream);

@@ -65,30 +65,47 @@ __device__ __forceinline__ double rcp(double a) {
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 
+// per-stage row layout (doubles)
+enum { ST_S = 0,      // iterate: x, y, psi, v, cte, epsi
+       ST_U = 6,      //          delta, a
+       ST_LAM = 8,    //          multipliers of the constraint defining s_i
+       ST_ZL = 14,    //          bound multipliers of psi, v, delta, a
+       ST_ZU = 18,
+       ST_TG = 22,    // sin/cos psi, sin/cos epsi, f', f'', a61, g3 at the iterate
+       ST_CN = 30,    // c_{i+1} at the iterate
+       ST_DS = 36,    // primal search direction
+       ST_DU = 42,
+       ST_TT = 44,    // TG / CN at the trial point (copied on acceptance)
+       ST_CT = 52,
+       ST_KG = 58,    // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
+       ST_CS = 70,    // second-order-correction right-hand side (rare path only)
+       ST_ROW = 78 }; // 76 used; 78 keeps shared-memory rows of neighbouring lanes 2-way bank-conflict free
+template <int NS, bool SH> struct LaneRows { typedef double type[NS][ST_ROW]; };
+template <int NS> struct LaneRows<NS, true> { typedef double (*type)[ST_ROW]; };
+
 struct StageLin { double a13, a14, a23, a24, a34, b3, a51, a54, a56, a61; };
 struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa, gp, gv, gc, ge, gdp, gd, ga; };
 
-template <int NS>
+template <int NS, bool SH>
 struct Lane {
   // ---- per-stage data (thread-private memory): 70 doubles per stage are touched on the common path
-  // (16-byte aligned rows: the compiler pairs neighbouring doubles into 128-bit local loads/stores)
-  alignas(16) double S[NS][6];     // iterate: x, y, psi, v, cte, epsi
-  alignas(16) double U[NS][2];     //          delta, a
-  alignas(16) double LAM[NS][6];   //          multipliers of the constraint defining s_i
-  alignas(16) double ZL[NS][4];    //          bound multipliers of psi, v, delta, a
-  alignas(16) double ZU[NS][4];
-  alignas(16) double TG[NS][8];    // sin/cos psi, sin/cos epsi, f', f'', a61, g3 at the iterate
-  alignas(16) double CN[NS][6];    // c_{i+1} at the iterate
-  alignas(16) double DS[NS][6];    // primal search direction
-  alignas(16) double DU[NS][2];
-  alignas(16) double TT[NS][8];    // TG / CN at the trial point (copied on acceptance)
-  alignas(16) double CT[NS][6];
-  alignas(16) double KG[NS][12];   // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
-  alignas(16) double CS[NS][6];    // second-order-correction right-hand side (rare path only)
+  // Per-stage data: one row of ST_ROW doubles per horizon stage (offsets ST_*).  SH = false: thread-private
+  // memory (one problem per lane; rows 16-byte aligned, so neighbouring doubles pair into 128-bit local
+  // accesses).  SH = true: a pointer into shared memory (one problem per lane GROUP, mpc_coop_kernel).
+  enum { NS_GROUP = SH ? (NS <= 16 ? 16 : 32) : 1 };
+  typedef typename LaneRows<NS, SH>::type Rows;
+  alignas(16) Rows ST;
   alignas(16) double PC[LC_SIZE];
   alignas(16) double FLT[2 * K_NFILT];
   double c0[6], c0t[6], cs0[6];
+  // ---- lane group (coop kernel): this lane's index in its group, group size, member mask; (0, 1, -) for
+  // the one-problem-per-lane kernel
+  int g0, gstep;
+  unsigned gm;
+  __device__ __forceinline__ void gsync() const { if (SH) __syncwarp(gm); }
   // ---- scalars ----
+  int m1, m3;
+  bool solve_ok;
   int b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt;
   double mu, tau, theta_min, theta_max, dw, dw_last, dw_used;
   double alpha, alpha_z, alpha_test, alpha_soc, alpha_min;
@@ -164,20 +181,20 @@ struct Lane {
       }
     }
 #pragma unroll 1
-    for (int i = 0; i < N; i++) {
+    for (int i = g0; i < N; i += gstep) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) { S[i][k] = (i == 0) ? PC[LC_S0 + k] : 0.0; LAM[i][k] = 0.0; DS[i][k] = 0.0; }
+      for (int k = 0; k < 6; k++) { ST[i][ST_S + k] = (i == 0) ? PC[LC_S0 + k] : 0.0; ST[i][ST_LAM + k] = 0.0; ST[i][ST_DS + k] = 0.0; }
 #pragma unroll
-      for (int k = 0; k < 8; k++) TG[i][k] = 0.0;   // read (times alpha = 0) by the first advance sweep
-      S[i][2] = i == 0 ? x00[0] : x0[0];
-      S[i][3] = i == 0 ? x00[1] : x0[1];
-      U[i][0] = x0[2]; U[i][1] = x0[3];
-      DU[i][0] = 0.0; DU[i][1] = 0.0;
+      for (int k = 0; k < 8; k++) ST[i][ST_TG + k] = 0.0;   // read (times alpha = 0) by the first advance sweep
+      ST[i][ST_S + 2] = i == 0 ? x00[0] : x0[0];
+      ST[i][ST_S + 3] = i == 0 ? x00[1] : x0[1];
+      ST[i][ST_U + 0] = x0[2]; ST[i][ST_U + 1] = x0[3];
+      ST[i][ST_DU + 0] = 0.0; ST[i][ST_DU + 1] = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const bool valid = k < 2 || i < N - 1;
-        ZL[i][k] = valid ? 1.0 : 0.0;
-        ZU[i][k] = valid ? 1.0 : 0.0;
+        ST[i][ST_ZL + k] = valid ? 1.0 : 0.0;
+        ST[i][ST_ZU + k] = valid ? 1.0 : 0.0;
       }
     }
     mu = 0.1;
@@ -186,6 +203,7 @@ struct Lane {
     nfilt = 0; iter = 0; accept_cnt = 0; status = 0; ntrial = 0; soc_cnt = 0;
     alpha = 0.0; alpha_z = 0.0;
     mode = LM_EV0;
+    gsync();
   }
 
 
@@ -286,6 +304,7 @@ struct Lane {
   // trig/polynomial values of the trial point are kept (TT, CT) and become the iterate's on acceptance
   // ------------------------------------------------------------------------------------------
   __device__ void eval_sweep(double a) {
+    if (SH) { eval_par(a); return; }
     const double lo_p = PC[LC_LO], hi_p = PC[LC_HI], lo_v = PC[LC_LO + 1], hi_v = PC[LC_HI + 1];
     const double lo_d = PC[LC_LO + 2], hi_d = PC[LC_HI + 2], lo_a = PC[LC_LO + 3], hi_a = PC[LC_HI + 3];
     double F[6] = {0, 0, 0, 0, 0, 0};
@@ -294,23 +313,23 @@ struct Lane {
     for (int i = 0; i < N; i++) {
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) s[k] = fma(a, DS[i][k], S[i][k]);
+      for (int k = 0; k < 6; k++) s[k] = fma(a, ST[i][ST_DS + k], ST[i][ST_S + k]);
       if (i == 0) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { const double c = s[k] - PC[LC_S0 + k]; c0t[k] = c; th += fabs(c); }
       } else {
 #pragma unroll
-        for (int k = 0; k < 6; k++) { const double c = s[k] - F[k]; CT[i - 1][k] = c; th += fabs(c); }
+        for (int k = 0; k < 6; k++) { const double c = s[k] - F[k]; ST[i - 1][ST_CT + k] = c; th += fabs(c); }
       }
       const double dv = s[3] - vref(i);
       fl += 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + PC[LC_WV2] * dv * dv + nv2(i) * s[3] * s[3]);
       double prod = (s[2] - lo_p) * (hi_p - s[2]) * (s[3] - lo_v) * (hi_v - s[3]);
       if (i < N - 1) {
-        const double u0 = fma(a, DU[i][0], U[i][0]), u1 = fma(a, DU[i][1], U[i][1]);
+        const double u0 = fma(a, ST[i][ST_DU + 0], ST[i][ST_U + 0]), u1 = fma(a, ST[i][ST_DU + 1], ST[i][ST_U + 1]);
         double tg[8];
         point_eval(s, u0, u1, tg, F);
 #pragma unroll
-        for (int k = 0; k < 8; k++) TT[i][k] = tg[k];
+        for (int k = 0; k < 8; k++) ST[i][ST_TT + k] = tg[k];
         fl += 0.5 * PC[LC_WD2] * u0 * u0;
         if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * PC[LC_CW] * dd * dd; }
         dprev = u0;
@@ -320,15 +339,57 @@ struct Lane {
     }
     ft = fl; lt = ll; tht = th;
   }
+  // the same evaluation with one stage per lane of the group: the residual of the constraint that defines
+  // s_i needs F(s_{i-1}, u_{i-1}) from the lane below; the three sums are butterfly reductions
+  __device__ void eval_par(double a) {
+    const int G = SH ? NS_GROUP : 1;
+    const int i = g0;
+    const bool act = i < N, hasu = i < N - 1;
+    const int ii = act ? i : 0;
+    double s[6], F[6] = {0, 0, 0, 0, 0, 0}, tg[8], u0 = 0.0, u1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s[k] = fma(a, ST[ii][ST_DS + k], ST[ii][ST_S + k]);
+    double fl = 0.0, ll = 0.0, th = 0.0;
+    if (hasu) {
+      u0 = fma(a, ST[i][ST_DU + 0], ST[i][ST_U + 0]);
+      u1 = fma(a, ST[i][ST_DU + 1], ST[i][ST_U + 1]);
+      point_eval(s, u0, u1, tg, F);
+#pragma unroll
+      for (int k = 0; k < 8; k++) ST[i][ST_TT + k] = tg[k];
+    }
+    const double dprev = __shfl_up_sync(gm, u0, 1, G);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const double Fp = __shfl_up_sync(gm, F[k], 1, G);
+      // every lane keeps the stage-0 residual (it is part of the uniform per-problem state)
+      c0t[k] = fma(a, ST[0][ST_DS + k], ST[0][ST_S + k]) - PC[LC_S0 + k];
+      if (act && i >= 1) { const double c = s[k] - Fp; ST[i - 1][ST_CT + k] = c; th += fabs(c); }
+      if (i == 0) th += fabs(c0t[k]);
+    }
+    if (act) {
+      const double dv = s[3] - vref(i);
+      fl = 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + PC[LC_WV2] * dv * dv + nv2(i) * s[3] * s[3]);
+      double prod = (s[2] - PC[LC_LO]) * (PC[LC_HI] - s[2]) * (s[3] - PC[LC_LO + 1]) * (PC[LC_HI + 1] - s[3]);
+      if (hasu) {
+        fl += 0.5 * PC[LC_WD2] * u0 * u0;
+        if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * PC[LC_CW] * dd * dd; }
+        prod *= (u0 - PC[LC_LO + 2]) * (PC[LC_HI + 2] - u0) * (u1 - PC[LC_LO + 3]) * (PC[LC_HI + 3] - u1);
+      }
+      ll = log(prod);
+    }
+    ft = gsum<NS_GROUP>(fl, gm); lt = gsum<NS_GROUP>(ll, gm); tht = gsum<NS_GROUP>(th, gm);
+    gsync();
+  }
   // CS = a * (first ? CN : CS) + CT     (Ipopt's accumulated second-order-correction rhs)
   __device__ void soc_rhs(bool first, double a) {
 #pragma unroll
     for (int k = 0; k < 6; k++) cs0[k] = a * (first ? c0[k] : cs0[k]) + c0t[k];
 #pragma unroll 1
-    for (int i = 0; i < N - 1; i++) {
+    for (int i = g0; i < N - 1; i += gstep) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) CS[i][k] = a * (first ? CN[i][k] : CS[i][k]) + CT[i][k];
+      for (int k = 0; k < 6; k++) ST[i][ST_CS + k] = a * (first ? ST[i][ST_CN + k] : ST[i][ST_CS + k]) + ST[i][ST_CT + k];
     }
+    gsync();
   }
 
   // ------------------------------------------------------------------------------------------
@@ -340,6 +401,7 @@ struct Lane {
   //  (3) Ipopt's optimality error terms at the resulting iterate.
   // ------------------------------------------------------------------------------------------
   __device__ void advance(bool do_update, bool ls, bool zero_lam) {
+    if (SH) { advance_par(do_update, ls, zero_lam); return; }
     const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     const double a = alpha, az = alpha_z;
     const double dwv = ls ? 0.0 : dw_used;
@@ -355,18 +417,18 @@ struct Lane {
       const bool hasu = i < N - 1;
       double s[6], lam[6], zl[4], zu[4], tg[8], u0 = 0.0, u1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; k++) { s[k] = S[i][k]; lam[k] = LAM[i][k]; }
+      for (int k = 0; k < 6; k++) { s[k] = ST[i][ST_S + k]; lam[k] = ST[i][ST_LAM + k]; }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { zl[k] = ZL[i][k]; zu[k] = ZU[i][k]; }
+      for (int k = 0; k < 4; k++) { zl[k] = ST[i][ST_ZL + k]; zu[k] = ST[i][ST_ZU + k]; }
       if (hasu) {
-        u0 = U[i][0]; u1 = U[i][1];
+        u0 = ST[i][ST_U + 0]; u1 = ST[i][ST_U + 1];
 #pragma unroll
-        for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
+        for (int k = 0; k < 8; k++) tg[k] = ST[i][ST_TG + k];
       } else {
 #pragma unroll
         for (int k = 0; k < 8; k++) tg[k] = 0.0;
       }
-      const double dprev_old = (hasu && i >= 1) ? U[i - 1][0] : 0.0;
+      const double dprev_old = (hasu && i >= 1) ? ST[i - 1][ST_U + 0] : 0.0;
       double dprev = dprev_old;            // NEW delta_{i-1}
       double lp[6] = {0, 0, 0, 0, 0, 0};
       StageLin L;
@@ -374,8 +436,8 @@ struct Lane {
       if (costate) {
         double ds[6], du0 = 0.0, du1 = 0.0, il[4], iu[4];
 #pragma unroll
-        for (int k = 0; k < 6; k++) ds[k] = DS[i][k];
-        if (hasu) { du0 = DU[i][0]; du1 = DU[i][1]; }
+        for (int k = 0; k < 6; k++) ds[k] = ST[i][ST_DS + k];
+        if (hasu) { du0 = ST[i][ST_DU + 0]; du1 = ST[i][ST_DU + 1]; }
         slack_rcp(s[2], s[3], u0, u1, hasu, il, iu);
         StageHess H;
         hess_at(i, ls, dwv, tg, s[3], s[4], s[5], u0, dprev_old, lo_n, zl, zu, il, iu, H);
@@ -405,12 +467,12 @@ struct Lane {
         if (do_update) {
           const double dx[4] = {ds[2], ds[3], du0, du1};
 #pragma unroll
-          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] += a * (lp[k] - lam[k]); S[i][k] = s[k]; }
+          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] += a * (lp[k] - lam[k]); ST[i][ST_S + k] = s[k]; }
           if (hasu) {
             u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
-            U[i][0] = u0; U[i][1] = u1;
+            ST[i][ST_U + 0] = u0; ST[i][ST_U + 1] = u1;
           }
-          if (i >= 1 && hasu) dprev = fma(a, DU[i - 1][0], dprev_old);
+          if (i >= 1 && hasu) dprev = fma(a, ST[i - 1][ST_DU + 0], dprev_old);
           double iln[4], iun[4];
           slack_rcp(s[2], s[3], u0, u1, hasu, iln, iun);
 #pragma unroll
@@ -420,7 +482,7 @@ struct Lane {
               const double dzu = (mu + zu[k] * dx[k]) * iu[k] - zu[k];
               zl[k] = dmax(dmin(zl[k] + az * dzl, zcap * iln[k]), zfloor * iln[k]);
               zu[k] = dmax(dmin(zu[k] + az * dzu, zcap * iun[k]), zfloor * iun[k]);
-              ZL[i][k] = zl[k]; ZU[i][k] = zu[k];
+              ST[i][ST_ZL + k] = zl[k]; ST[i][ST_ZU + k] = zu[k];
             }
           }
         } else {
@@ -428,23 +490,23 @@ struct Lane {
           for (int k = 0; k < 6; k++) lam[k] = lp[k];
         }
 #pragma unroll
-        for (int k = 0; k < 6; k++) LAM[i][k] = lam[k];
+        for (int k = 0; k < 6; k++) ST[i][ST_LAM + k] = lam[k];
       } else if (zero_lam) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) { lam[k] = 0.0; LAM[i][k] = 0.0; }
+        for (int k = 0; k < 6; k++) { lam[k] = 0.0; ST[i][ST_LAM + k] = 0.0; }
       }
       // ---- residuals and trig/polynomial values at the (new) iterate
       double cn[6] = {0, 0, 0, 0, 0, 0};
       if (hasu) {
         if (do_update) {
 #pragma unroll
-          for (int k = 0; k < 6; k++) { cn[k] = CT[i][k]; CN[i][k] = cn[k]; }
+          for (int k = 0; k < 6; k++) { cn[k] = ST[i][ST_CT + k]; ST[i][ST_CN + k] = cn[k]; }
 #pragma unroll
-          for (int k = 0; k < 8; k++) { tg[k] = TT[i][k]; TG[i][k] = tg[k]; }
+          for (int k = 0; k < 8; k++) { tg[k] = ST[i][ST_TT + k]; ST[i][ST_TG + k] = tg[k]; }
           lin_at(tg, s[3], u0, L);
         } else {
 #pragma unroll
-          for (int k = 0; k < 6; k++) cn[k] = CN[i][k];
+          for (int k = 0; k < 6; k++) cn[k] = ST[i][ST_CN + k];
         }
       }
       if (i == 0 && do_update) {
@@ -503,6 +565,184 @@ struct Lane {
     for (int k = 0; k < 6; k++) cv = nanmax(cv, fabs(c0[k]));
     dinf = r; cviol = cv; lam1 = l1; z1 = zz; amin = am; amax = aM; lsq_lmax = lmax;
   }
+  // the same sweep with one stage per lane of the group.  The costate recursion is the only sequential
+  // part: N steps of a 6-vector handed down the lanes by shuffle; neighbours' new values (lambda_{i+1},
+  // delta_{i+-1}) travel by shuffle too, the six error terms are butterfly reductions.
+  __device__ void advance_par(bool do_update, bool ls, bool zero_lam) {
+    const int G = SH ? NS_GROUP : 1;
+    const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    const double a = alpha, az = alpha_z;
+    const double dwv = ls ? 0.0 : dw_used;
+    const double zcap = K_KAPPA_SIGMA * mu, zfloor = mu / K_KAPPA_SIGMA;
+    const bool costate = do_update || ls;
+    const int i = g0;
+    const bool act = i < N, hasu = i < N - 1;
+    const int ii = act ? i : 0;
+    double s[6], lam[6], zl[4], zu[4], tg[8], u0 = 0.0, u1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { s[k] = ST[ii][ST_S + k]; lam[k] = act ? ST[ii][ST_LAM + k] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { zl[k] = act ? ST[ii][ST_ZL + k] : 0.0; zu[k] = act ? ST[ii][ST_ZU + k] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) tg[k] = hasu ? ST[ii][ST_TG + k] : 0.0;
+    if (hasu) { u0 = ST[i][ST_U + 0]; u1 = ST[i][ST_U + 1]; }
+    const double dprev_old = __shfl_up_sync(gm, u0, 1, G);
+    double lo_n[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const double t = __shfl_down_sync(gm, lam[k], 1, G); lo_n[k] = hasu ? t : 0.0; }
+    StageLin L;
+    lin_at(tg, s[3], u0, L);
+    double lp[6] = {0, 0, 0, 0, 0, 0}, lmax = 0.0;
+    double ds[6] = {0, 0, 0, 0, 0, 0}, du0 = 0.0, du1 = 0.0, il[4], iu[4];
+    if (costate) {
+      double h[6] = {0, 0, 0, 0, 0, 0};
+      if (act) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ds[k] = ST[i][ST_DS + k];
+        if (hasu) { du0 = ST[i][ST_DU + 0]; du1 = ST[i][ST_DU + 1]; }
+        slack_rcp(s[2], s[3], u0, u1, hasu, il, iu);
+        StageHess H;
+        hess_at(i, ls, dwv, tg, s[3], s[4], s[5], u0, (hasu && i >= 1) ? dprev_old : 0.0, lo_n, zl, zu, il, iu, H);
+        h[0] = H.qxx * ds[0];
+        h[1] = H.qyy * ds[1];
+        h[2] = H.qpp * ds[2] + H.qpv * ds[3] + H.gp;
+        h[3] = H.qpv * ds[2] + H.qvv * ds[3] + H.qve * ds[5] + H.gv + H.svd * du0;
+        h[4] = H.qcc * ds[4] + H.gc;
+        h[5] = H.qve * ds[3] + H.qee * ds[5] + H.ge;
+      }
+      // lambda+_i = A_i^T lambda+_{i+1} - h_i, from the last stage down
+#pragma unroll 1
+      for (int j = N - 1; j >= 0; j--) {
+        double n[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) n[k] = __shfl_down_sync(gm, lp[k], 1, G);
+        if (i == j) {
+          if (hasu) {
+            const double l25 = n[2] + n[5];
+            lp[0] = n[0] + L.a51 * n[4] + L.a61 * n[5] - h[0];
+            lp[1] = n[1] - n[4] - h[1];
+            lp[2] = L.a13 * n[0] + L.a23 * n[1] + l25 - h[2];
+            lp[3] = L.a14 * n[0] + L.a24 * n[1] + L.a34 * l25 + n[3] + L.a54 * n[4] - h[3];
+            lp[4] = -h[4];
+            lp[5] = L.a56 * n[4] - h[5];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) lp[k] = -h[k];
+          }
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) lmax = nanmax(lmax, fabs(lp[k]));
+      }
+      if (do_update) {
+        if (act) {
+          const double dx[4] = {ds[2], ds[3], du0, du1};
+#pragma unroll
+          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] += a * (lp[k] - lam[k]); ST[i][ST_S + k] = s[k]; }
+          if (hasu) {
+            u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
+            ST[i][ST_U + 0] = u0; ST[i][ST_U + 1] = u1;
+          }
+          double iln[4], iun[4];
+          slack_rcp(s[2], s[3], u0, u1, hasu, iln, iun);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < 2 || hasu) {
+              const double dzl = (mu - zl[k] * dx[k]) * il[k] - zl[k];
+              const double dzu = (mu + zu[k] * dx[k]) * iu[k] - zu[k];
+              zl[k] = dmax(dmin(zl[k] + az * dzl, zcap * iln[k]), zfloor * iln[k]);
+              zu[k] = dmax(dmin(zu[k] + az * dzu, zcap * iun[k]), zfloor * iun[k]);
+              ST[i][ST_ZL + k] = zl[k]; ST[i][ST_ZU + k] = zu[k];
+            }
+          }
+        }
+      } else if (act) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) lam[k] = lp[k];
+      }
+      if (act) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ST[i][ST_LAM + k] = lam[k];
+      }
+    } else if (zero_lam && act) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) { lam[k] = 0.0; ST[i][ST_LAM + k] = 0.0; }
+    }
+    // ---- residuals and trig/polynomial values at the (new) iterate
+    double cn[6] = {0, 0, 0, 0, 0, 0};
+    if (hasu) {
+      if (do_update) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { cn[k] = ST[i][ST_CT + k]; ST[i][ST_CN + k] = cn[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { tg[k] = ST[i][ST_TT + k]; ST[i][ST_TG + k] = tg[k]; }
+        lin_at(tg, s[3], u0, L);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cn[k] = ST[i][ST_CN + k];
+      }
+    }
+    if (do_update) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) c0[k] = c0t[k];
+    }
+    // ---- optimality error terms
+    const double dprev = __shfl_up_sync(gm, u0, 1, G), dnext = __shfl_down_sync(gm, u0, 1, G);
+    double ln_n[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const double t = __shfl_down_sync(gm, lam[k], 1, G); ln_n[k] = hasu ? t : 0.0; }
+    double r = 0.0, cv = 0.0, l1 = 0.0, zz = 0.0, am = 1e300, aM = 0.0;
+    if (act) {
+      double os[6] = {0, 0, 0, 0, 0, 0}, ou0 = 0.0, ou1 = 0.0;
+      const double v = s[3];
+      if (hasu) {
+        const double l25 = ln_n[2] + ln_n[5];
+        os[0] = ln_n[0] + L.a51 * ln_n[4] + L.a61 * ln_n[5];
+        os[1] = ln_n[1] - ln_n[4];
+        os[2] = L.a13 * ln_n[0] + L.a23 * ln_n[1] + l25;
+        os[3] = L.a14 * ln_n[0] + L.a24 * ln_n[1] + L.a34 * l25 + ln_n[3] + L.a54 * ln_n[4];
+        os[5] = L.a56 * ln_n[4];
+        ou0 = L.b3 * l25;
+        ou1 = dt * ln_n[3];
+      }
+      double gs[6];
+      gs[0] = 0.0; gs[1] = 0.0;
+      gs[2] = -zl[0] + zu[0];
+      gs[3] = wv2 * (v - vref(i)) + nv2(i) * v - zl[1] + zu[1];
+      gs[4] = wc2(i) * s[4];
+      gs[5] = we2(i) * s[5];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        r = nanmax(r, fabs(gs[k] + lam[k] - os[k]));
+        l1 += fabs(lam[k]);
+        cv = nanmax(cv, fabs(cn[k]));
+        if (i == 0) cv = nanmax(cv, fabs(c0[k]));
+      }
+      zz = fabs(zl[0]) + fabs(zu[0]) + fabs(zl[1]) + fabs(zu[1]);
+      {
+        const double p0 = (s[2] - PC[LC_LO]) * zl[0], p1 = (PC[LC_HI] - s[2]) * zu[0];
+        const double p2 = (s[3] - PC[LC_LO + 1]) * zl[1], p3 = (PC[LC_HI + 1] - s[3]) * zu[1];
+        am = dmin(dmin(p0, p1), dmin(p2, p3));
+        aM = dmax(dmax(p0, p1), dmax(p2, p3));
+      }
+      if (hasu) {
+        double gd = wd2 * u0;
+        if (i >= 1) gd += cw * (u0 - dprev);
+        if (i <= N - 3) gd -= cw * (dnext - u0);
+        r = nanmax(r, fabs(gd - ou0 - zl[2] + zu[2]));
+        r = nanmax(r, fabs(-ou1 - zl[3] + zu[3]));
+        zz += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
+        const double p0 = (u0 - PC[LC_LO + 2]) * zl[2], p1 = (PC[LC_HI + 2] - u0) * zu[2];
+        const double p2 = (u1 - PC[LC_LO + 3]) * zl[3], p3 = (PC[LC_HI + 3] - u1) * zu[3];
+        am = dmin(am, dmin(dmin(p0, p1), dmin(p2, p3)));
+        aM = dmax(aM, dmax(dmax(p0, p1), dmax(p2, p3)));
+      }
+    }
+    dinf = gmax<NS_GROUP>(r, gm); cviol = gmax<NS_GROUP>(cv, gm); lam1 = gsum<NS_GROUP>(l1, gm); z1 = gsum<NS_GROUP>(zz, gm);
+    amin = gmin<NS_GROUP>(am, gm); amax = gmax<NS_GROUP>(aM, gm); lsq_lmax = gmax<NS_GROUP>(lmax, gm);
+    gsync();
+  }
   // max_i |slack_i * z_i - m|  from the extreme complementarity products
   __device__ __forceinline__ double compl_err(double m) const { return nanmax(fabs(amax - m), fabs(amin - m)); }
 
@@ -519,11 +759,11 @@ struct Lane {
     double zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     {
       const int t = N - 1;
-      double zl[4] = {ZL[t][0], ZL[t][1], 0.0, 0.0}, zu[4] = {ZU[t][0], ZU[t][1], 0.0, 0.0}, il[4], iu[4];
-      const double psi = S[t][2], v = S[t][3];
+      double zl[4] = {ST[t][ST_ZL + 0], ST[t][ST_ZL + 1], 0.0, 0.0}, zu[4] = {ST[t][ST_ZU + 0], ST[t][ST_ZU + 1], 0.0, 0.0}, il[4], iu[4];
+      const double psi = ST[t][ST_S + 2], v = ST[t][ST_S + 3];
       slack_rcp(psi, v, 0.0, 0.0, false, il, iu);
       StageHess H;
-      hess_at(t, ls, dwv, zero8, v, S[t][4], S[t][5], 0.0, 0.0, zero8, zl, zu, il, iu, H);
+      hess_at(t, ls, dwv, zero8, v, ST[t][ST_S + 4], ST[t][ST_S + 5], 0.0, 0.0, zero8, zl, zu, il, iu, H);
 #pragma unroll
       for (int r = 0; r < 6; r++) {
 #pragma unroll
@@ -543,13 +783,13 @@ struct Lane {
       {
         double tg[8], ln[6], zl[4], zu[4], il[4], iu[4];
 #pragma unroll
-        for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
+        for (int k = 0; k < 8; k++) tg[k] = ST[i][ST_TG + k];
 #pragma unroll
-        for (int k = 0; k < 6; k++) ln[k] = LAM[i + 1][k];
+        for (int k = 0; k < 6; k++) ln[k] = ST[i + 1][ST_LAM + k];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { zl[k] = ZL[i][k]; zu[k] = ZU[i][k]; }
-        const double psi = S[i][2], v = S[i][3], c = S[i][4], e = S[i][5], u0 = U[i][0], u1 = U[i][1];
-        const double dprev = i >= 1 ? U[i - 1][0] : 0.0;
+        for (int k = 0; k < 4; k++) { zl[k] = ST[i][ST_ZL + k]; zu[k] = ST[i][ST_ZU + k]; }
+        const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3], c = ST[i][ST_S + 4], e = ST[i][ST_S + 5], u0 = ST[i][ST_U + 0], u1 = ST[i][ST_U + 1];
+        const double dprev = i >= 1 ? ST[i - 1][ST_U + 0] : 0.0;
         slack_rcp(psi, v, u0, u1, true, il, iu);
         lin_at(tg, v, u0, L);
         hess_at(i, ls, dwv, tg, v, c, e, u0, dprev, ln, zl, zu, il, iu, H);
@@ -559,10 +799,10 @@ struct Lane {
         for (int k = 0; k < 6; k++) d[k] = 0.0;
       } else if (soc) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) d[k] = -CS[i][k];
+        for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CS + k];
       } else {
 #pragma unroll
-        for (int k = 0; k < 6; k++) d[k] = -CN[i][k];
+        for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CN + k];
       }
       const bool cpl = i >= 1;
       const double cwe = cpl ? cwv : 0.0;
@@ -641,11 +881,11 @@ struct Lane {
       for (int c = 0; c < 5; c++) {
         K0[c] = -(i11 * cd[c] + i12 * ca[c]);
         K1[c] = -(i12 * cd[c] + i22 * ca[c]);
-        KG[i][c] = K0[c];
-        KG[i][5 + c] = K1[c];
+        ST[i][ST_KG + c] = K0[c];
+        ST[i][ST_KG + 5 + c] = K1[c];
       }
       const double k0 = -(i11 * md + i12 * ma), k1 = -(i12 * md + i22 * ma);
-      KG[i][10] = k0; KG[i][11] = k1;
+      ST[i][ST_KG + 10] = k0; ST[i][ST_KG + 11] = k1;
       // Schur complement -> new cost-to-go (index order X, Y, PSI, V, E, DP)
       Pm[0][0] = Mxx + Mxd * K0[0] + Mxa * K1[0];
       Pm[0][1] = Mxy + Mxd * K0[1] + Mxa * K1[1];
@@ -682,6 +922,7 @@ struct Lane {
       P44 = H.qcc;
       p4 = H.gc;
     }
+    gsync();   // coop kernel: every lane of the group ran the same recursion and stored the same gains
     return ok;
   }
 
@@ -701,29 +942,29 @@ struct Lane {
     for (int i = 0; i < N; i++) {
       const bool hasu = i < N - 1;
       double du0 = 0.0, du1 = 0.0, u0 = 0.0, u1 = 0.0;
-      const double psi = S[i][2], v = S[i][3];
+      const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3];
 #pragma unroll
-      for (int k = 0; k < 6; k++) DS[i][k] = t[k];
+      for (int k = 0; k < 6; k++) ST[i][ST_DS + k] = t[k];
       double tn[6] = {0, 0, 0, 0, 0, 0};
       if (hasu) {
         double kg[12], tg[8], d[6];
 #pragma unroll
-        for (int k = 0; k < 12; k++) kg[k] = KG[i][k];
+        for (int k = 0; k < 12; k++) kg[k] = ST[i][ST_KG + k];
 #pragma unroll
-        for (int k = 0; k < 8; k++) tg[k] = TG[i][k];
-        u0 = U[i][0]; u1 = U[i][1];
+        for (int k = 0; k < 8; k++) tg[k] = ST[i][ST_TG + k];
+        u0 = ST[i][ST_U + 0]; u1 = ST[i][ST_U + 1];
         du0 = kg[10] + kg[0] * t[0] + kg[1] * t[1] + kg[2] * t[2] + kg[3] * t[3] + kg[4] * dp;
         du1 = kg[11] + kg[5] * t[0] + kg[6] * t[1] + kg[7] * t[2] + kg[8] * t[3] + kg[9] * dp;
-        DU[i][0] = du0; DU[i][1] = du1;
+        ST[i][ST_DU + 0] = du0; ST[i][ST_DU + 1] = du1;
         if (ls) {
 #pragma unroll
           for (int k = 0; k < 6; k++) d[k] = 0.0;
         } else if (soc) {
 #pragma unroll
-          for (int k = 0; k < 6; k++) d[k] = -CS[i][k];
+          for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CS + k];
         } else {
 #pragma unroll
-          for (int k = 0; k < 6; k++) d[k] = -CN[i][k];
+          for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CN + k];
         }
         StageLin L;
         lin_at(tg, v, u0, L);
@@ -735,11 +976,11 @@ struct Lane {
         tn[5] = L.a61 * t[0] + t[2] + L.a34 * t[3] + L.b3 * du0 + d[5];
       }
       if (!ls) {
-        acc += (wv2 * (v - vref(i)) + nv2(i) * v) * t[3] + wc2(i) * S[i][4] * t[4] + we2(i) * S[i][5] * t[5];
+        acc += (wv2 * (v - vref(i)) + nv2(i) * v) * t[3] + wc2(i) * ST[i][ST_S + 4] * t[4] + we2(i) * ST[i][ST_S + 5] * t[5];
         if (hasu) {
           double gd = wd2 * u0;
           if (i >= 1) gd += cw * (u0 - dprev);
-          if (i <= N - 3) gd -= cw * (U[i + 1][0] - u0);
+          if (i <= N - 3) gd -= cw * (ST[i + 1][ST_U + 0] - u0);
           acc += gd * du0;
           dprev = u0;
         }
@@ -749,7 +990,7 @@ struct Lane {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           if (k < 2 || hasu) {
-            const double zl = ZL[i][k], zu = ZU[i][k];
+            const double zl = ST[i][ST_ZL + k], zu = ST[i][ST_ZU + k];
             acc += mu * (iu[k] - il[k]) * dx[k];
             rmax = dmax(rmax, dmax(-dx[k] * il[k], dx[k] * iu[k]));
             const double dzl = (mu - zl * dx[k]) * il[k] - zl;
@@ -764,6 +1005,7 @@ struct Lane {
       for (int k = 0; k < 6; k++) t[k] = tn[k];
       dp = du0;
     }
+    gsync();
     gbd_new = acc;
     if (ls) return;
     // alpha_max = min(1, tau / rmax),  alpha_z = min(1, tau * zn / zd)
@@ -854,15 +1096,15 @@ struct Lane {
       const bool hasu = i < N - 1;
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) s[k] = S[i][k];
+      for (int k = 0; k < 6; k++) s[k] = ST[i][ST_S + k];
       s[2] = fmin(fmax(s[2], PC[LC_LO0]), PC[LC_HI0]);
       s[3] = fmin(fmax(s[3], PC[LC_LO0 + 1]), PC[LC_HI0 + 1]);
       const double dv = s[3] - vref(i);
       fl += 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + wv2 * dv * dv + nv2(i) * s[3] * s[3]);
       double u0 = 0.0, u1 = 0.0;
       if (hasu) {
-        u0 = fmin(fmax(U[i][0], PC[LC_LO0 + 2]), PC[LC_HI0 + 2]);
-        u1 = fmin(fmax(U[i][1], PC[LC_LO0 + 3]), PC[LC_HI0 + 3]);
+        u0 = fmin(fmax(ST[i][ST_U + 0], PC[LC_LO0 + 2]), PC[LC_HI0 + 2]);
+        u1 = fmin(fmax(ST[i][ST_U + 1], PC[LC_LO0 + 3]), PC[LC_HI0 + 3]);
         fl += 0.5 * wd2 * u0 * u0;
         if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * cw * dd * dd; }
         dprev = u0;
@@ -889,74 +1131,56 @@ struct Lane {
     if (P.iters) P.iters[b] = iter;
   }
 
-};
 
-// Persistent grid, one CTA per SM; every lane pulls problems from the global counter until the batch is
-// exhausted.  The warps of a CTA walk through the slots of a trip together (__syncthreads between
-// slots): the loop body is ~100 KB of code, and warps at different places in it thrash the instruction
-// cache (profiles/r01_v3_*: 3.3 issue slots lost per instruction to "no instruction"); in step, the
-// CTA's instruction footprint is one sweep at a time.
-template <int NS, int MINB>
-__global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
-  Lane<NS> Z;
-  Z.mode = LM_IDLE;
-  Z.b = 0;
-  for (;;) {
-    // ---- slot 0: retire / fetch
-    if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
-    if (Z.mode == LM_IDLE) {
-      const int nb = atomicAdd(P.counter, 1);
-      if (nb < P.B) Z.init(P, nb); else Z.mode = LM_DONE;
-    }
-    if (__syncthreads_and(Z.mode == LM_DONE)) break;
-
-    // ---- slot 1: evaluate a point
-    const int m1 = Z.mode;
+  // ---- one trip of the state machine, in four slots (shared by the lane kernel and the coop kernel) -------
+  // slot 1: evaluate a point
+  __device__ __forceinline__ void trip_eval() {
+    m1 = mode;
     if (m1 == LM_EV0 || m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
-      const double a = m1 == LM_EV0 ? 0.0 : (m1 == LM_TRIAL ? Z.alpha : Z.alpha_soc);
-      Z.eval_sweep(a);
+      const double a = m1 == LM_EV0 ? 0.0 : (m1 == LM_TRIAL ? alpha : alpha_soc);
+      eval_sweep(a);
     }
-    __syncthreads();
-
-    // ---- slot 2: acceptance logic, then the sweep that accepts the step and measures the KKT error
+  }
+  // slot 2: acceptance logic, then the sweep that accepts the step and measures the KKT error
+  __device__ __forceinline__ void trip_accept(const KParams &P) {
     bool upd = false, lsq = false, zero = false, err = false;
     if (m1 == LM_EV0) {
-      Z.alpha = 0.0; Z.alpha_z = 0.0;
-      Z.theta_max = 1e4 * fmax(1.0, Z.tht);
-      Z.theta_min = 1e-4 * fmax(1.0, Z.tht);
+      alpha = 0.0; alpha_z = 0.0;
+      theta_max = 1e4 * fmax(1.0, tht);
+      theta_min = 1e-4 * fmax(1.0, tht);
       upd = true;
     } else if (m1 == LM_LSQ_DONE) {
       lsq = true; err = true;
     } else if (m1 == LM_LSQ_ZERO) {
       zero = true; err = true;
     } else if (m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
-      const double phi_t = Z.ft - Z.mu * Z.lt;
-      if (m1 == LM_TRIAL) Z.alpha_test = Z.alpha;
-      if (Z.ls_accept(Z.alpha_test, Z.tht, phi_t)) {
-        if (m1 == LM_SOC_TRIAL) Z.alpha = Z.alpha_soc;
-        if (!Z.is_ftype(Z.alpha_test) || !Z.armijo(Z.alpha_test, phi_t))
-          Z.filter_add((1.0 - K_GAMMA_THETA) * Z.ls_theta, Z.ls_phi - K_GAMMA_PHI * Z.ls_theta);
+      const double phi_t = ft - mu * lt;
+      if (m1 == LM_TRIAL) alpha_test = alpha;
+      if (ls_accept(alpha_test, tht, phi_t)) {
+        if (m1 == LM_SOC_TRIAL) alpha = alpha_soc;
+        if (!is_ftype(alpha_test) || !armijo(alpha_test, phi_t))
+          filter_add((1.0 - K_GAMMA_THETA) * ls_theta, ls_phi - K_GAMMA_PHI * ls_theta);
         upd = true; err = true;
       } else if (m1 == LM_TRIAL) {
-        if (Z.ntrial == 0 && Z.tht >= Z.ls_theta) {
+        if (ntrial == 0 && tht >= ls_theta) {
           // second-order correction (Ipopt max_soc = 4): same matrix, corrected constraint rhs
-          Z.soc_cnt = 0;
-          Z.theta_soc_old = Z.tht;
-          Z.soc_rhs(true, Z.alpha);
-          Z.mode = LM_SOC;
+          soc_cnt = 0;
+          theta_soc_old = tht;
+          soc_rhs(true, alpha);
+          mode = LM_SOC;
         } else {
-          Z.alpha *= 0.5;
-          Z.ntrial++;
-          if (Z.alpha < Z.alpha_min) { Z.status = 9; Z.mode = LM_FINISH; }   // Ipopt would enter restoration
+          alpha *= 0.5;
+          ntrial++;
+          if (alpha < alpha_min) { status = 9; mode = LM_FINISH; }   // Ipopt would enter restoration
         }
       } else {   // rejected SOC trial
-        Z.soc_cnt++;
-        if (Z.soc_cnt < K_MAX_SOC && Z.tht <= K_KAPPA_SOC * Z.theta_soc_old) {
-          Z.theta_soc_old = Z.tht;
-          Z.soc_rhs(false, Z.alpha_soc);
-          Z.mode = LM_SOC;
+        soc_cnt++;
+        if (soc_cnt < K_MAX_SOC && tht <= K_KAPPA_SOC * theta_soc_old) {
+          theta_soc_old = tht;
+          soc_rhs(false, alpha_soc);
+          mode = LM_SOC;
         } else {
-          Z.mode = LM_RESOLVE;
+          mode = LM_RESOLVE;
         }
       }
     }
@@ -966,67 +1190,135 @@ __global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
     asm volatile("" : "+r"(flags));
     upd = flags & 1; lsq = flags & 2; zero = flags & 4; err = flags & 8;
     if (flags) {
-      Z.advance(upd, lsq, zero);
-      if (upd) { Z.fx = Z.ft; Z.lsum = Z.lt; Z.theta = Z.tht; }
+      advance(upd, lsq, zero);
+      if (upd) { fx = ft; lsum = lt; theta = tht; }
       if (m1 == LM_EV0) {
-        Z.mode = LM_LSQ;
-      } else if (lsq && !(Z.lsq_lmax <= K_CONSTR_MULT_INIT_MAX)) {
-        Z.mode = LM_LSQ_ZERO;
+        mode = LM_LSQ;
+      } else if (lsq && !(lsq_lmax <= K_CONSTR_MULT_INIT_MAX)) {
+        mode = LM_LSQ_ZERO;
       } else {
-        if (upd) Z.iter++;
-        Z.check_and_update_mu(P);
+        if (upd) iter++;
+        check_and_update_mu(P);
       }
     }
-    __syncthreads();
-
-    // ---- slot 3 + 4: factor and solve
-    const int m3 = Z.mode;
+  }
+  // slot 3: factor
+  __device__ __forceinline__ void trip_factor() {
+    m3 = mode;
     const bool solve = m3 == LM_LSQ || m3 == LM_NEWTON || m3 == LM_SOC || m3 == LM_RESOLVE;
-    const bool ls = m3 == LM_LSQ, soc = m3 == LM_SOC;
-    const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? Z.dw : Z.dw_used);
-    bool ok = true;
-    if (solve) ok = Z.riccati(ls, soc, dwv);
-    __syncthreads();
+    solve_ok = true;
     if (solve) {
-      if (m3 == LM_NEWTON && !ok) {
-        // Ipopt's inertia correction schedule (delta_w)
-        double d = Z.dw;
-        if (d == 0.0) d = (Z.dw_last == 0.0) ? K_DW_FIRST : fmax(K_DW_MIN, Z.dw_last * K_DW_DEC);
-        else d = (Z.dw_last == 0.0) ? d * K_DW_INC_FIRST : d * K_DW_INC;
-        Z.dw = d;
-        if (d > K_DW_MAX) { Z.status = 10; Z.mode = LM_FINISH; }
-      } else {
-        Z.forward_and_ratios(ls, soc);
-        if (m3 == LM_LSQ) {
-          Z.dw_used = 0.0;
-          Z.mode = LM_LSQ_DONE;
-        } else if (m3 == LM_NEWTON) {
-          if (Z.dw > 0.0) Z.dw_last = Z.dw;
-          Z.dw_used = Z.dw;
-          Z.alpha = Z.alpha_soc;   // alpha_max
-          Z.ls_gbd = Z.gbd_new;
-          Z.ls_theta = Z.theta;
-          Z.ls_phi = Z.fx - Z.mu * Z.lsum;
-          Z.pow_gbd = Z.ls_gbd < 0.0 ? pow(-Z.ls_gbd, K_S_PHI) : 0.0;
-          Z.pow_theta = pow(Z.ls_theta, K_S_THETA);
-          double amin_ = K_GAMMA_THETA;
-          if (Z.ls_gbd < 0.0) {
-            amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * Z.ls_theta / (-Z.ls_gbd));
-            if (Z.ls_theta <= Z.theta_min) amin_ = fmin(amin_, Z.pow_theta / Z.pow_gbd);
-          }
-          Z.alpha_min = amin_ * K_ALPHA_MIN_FRAC;
-          Z.ntrial = 0;
-          Z.mode = LM_TRIAL;
-        } else if (m3 == LM_SOC) {
-          Z.mode = LM_SOC_TRIAL;
-        } else {   // LM_RESOLVE: the uncorrected direction is back; continue backtracking
-          Z.alpha *= 0.5;
-          Z.ntrial++;
-          Z.mode = (Z.alpha < Z.alpha_min) ? LM_FINISH : LM_TRIAL;
-          if (Z.mode == LM_FINISH) Z.status = 9;
-        }
-      }
+      const bool ls = m3 == LM_LSQ;
+      const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? dw : dw_used);
+      solve_ok = riccati(ls, m3 == LM_SOC, dwv);
+    } else {
+      m3 = LM_IDLE;
     }
+  }
+  // slot 4: solve, step lengths, line-search set-up
+  __device__ __forceinline__ void trip_solve() {
+    if (m3 == LM_IDLE) return;
+    if (m3 == LM_NEWTON && !solve_ok) {
+      // Ipopt's inertia correction schedule (delta_w)
+      double d = dw;
+      if (d == 0.0) d = (dw_last == 0.0) ? K_DW_FIRST : fmax(K_DW_MIN, dw_last * K_DW_DEC);
+      else d = (dw_last == 0.0) ? d * K_DW_INC_FIRST : d * K_DW_INC;
+      dw = d;
+      if (d > K_DW_MAX) { status = 10; mode = LM_FINISH; }
+      return;
+    }
+    forward_and_ratios(m3 == LM_LSQ, m3 == LM_SOC);
+    if (m3 == LM_LSQ) {
+      dw_used = 0.0;
+      mode = LM_LSQ_DONE;
+    } else if (m3 == LM_NEWTON) {
+      if (dw > 0.0) dw_last = dw;
+      dw_used = dw;
+      alpha = alpha_soc;   // alpha_max
+      ls_gbd = gbd_new;
+      ls_theta = theta;
+      ls_phi = fx - mu * lsum;
+      pow_gbd = ls_gbd < 0.0 ? pow(-ls_gbd, K_S_PHI) : 0.0;
+      pow_theta = pow(ls_theta, K_S_THETA);
+      double amin_ = K_GAMMA_THETA;
+      if (ls_gbd < 0.0) {
+        amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * ls_theta / (-ls_gbd));
+        if (ls_theta <= theta_min) amin_ = fmin(amin_, pow_theta / pow_gbd);
+      }
+      alpha_min = amin_ * K_ALPHA_MIN_FRAC;
+      ntrial = 0;
+      mode = LM_TRIAL;
+    } else if (m3 == LM_SOC) {
+      mode = LM_SOC_TRIAL;
+    } else {   // LM_RESOLVE: the uncorrected direction is back; continue backtracking
+      alpha *= 0.5;
+      ntrial++;
+      mode = (alpha < alpha_min) ? LM_FINISH : LM_TRIAL;
+      if (mode == LM_FINISH) status = 9;
+    }
+  }
+};
+
+// Persistent grid, one CTA per SM; every lane pulls problems from the global counter until the batch is
+// exhausted.  The warps of a CTA walk through the slots of a trip together (__syncthreads between
+// slots): the loop body is ~100 KB of code, and warps at different places in it thrash the instruction
+// cache (profiles/r01_v3_*: 3.3 issue slots lost per instruction to "no instruction"); in step, the
+// CTA's instruction footprint is one sweep at a time.
+template <int NS, int MINB>
+__global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
+  Lane<NS, false> Z;
+  Z.mode = LM_IDLE;
+  Z.b = 0;
+  Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;
+  for (;;) {
+    // ---- slot 0: retire / fetch
+    if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
+    if (Z.mode == LM_IDLE) {
+      const int nb = atomicAdd(P.counter, 1);
+      if (nb < P.B) Z.init(P, nb); else Z.mode = LM_DONE;
+    }
+    if (__syncthreads_and(Z.mode == LM_DONE)) break;
+    Z.trip_eval();
+    __syncthreads();
+    Z.trip_accept(P);
+    __syncthreads();
+    Z.trip_factor();
+    __syncthreads();
+    Z.trip_solve();
+  }
+}
+
+// The same solver with one problem per GROUP of 16 (N <= 16) or 32 lanes and the per-stage rows in shared
+// memory: the two sweeps that are parallel over the horizon (point evaluation; step acceptance + KKT
+// errors) run one stage per lane with shuffles for the neighbours and butterfly reductions, the two
+// recursions (Riccati, forward) run identically in every lane of the group on broadcast shared-memory
+// reads.  A trip takes a fraction of the time a lone lane needs, which is what matters when there are
+// fewer problems than lanes: single solves (MPC::solve called once per telemetry message), closed-loop
+// steps of a few thousand vehicles, and the last long-running problems of a big batch.
+template <int NS>
+__global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
+  extern __shared__ double coop_smem[];
+  const int G = Lane<NS, true>::NS_GROUP;
+  const int lane = threadIdx.x & 31;
+  Lane<NS, true> Z;
+  Z.g0 = lane % G; Z.gstep = G;
+  Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
+  Z.ST = reinterpret_cast<double (*)[ST_ROW]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW);
+  for (;;) {
+    int nb = 0;
+    if (Z.g0 == 0) nb = atomicAdd(P.counter, 1);
+    nb = __shfl_sync(Z.gm, nb, 0, G);
+    if (nb >= P.B) break;
+    Z.init(P, nb);
+    while (Z.mode != LM_FINISH) {
+      Z.trip_eval();
+      Z.trip_accept(P);
+      if (Z.mode == LM_FINISH) break;
+      Z.trip_factor();
+      Z.trip_solve();
+    }
+    if (Z.g0 == 0) Z.write_outputs(P);
+    Z.gsync();
   }
 }
 

@@ -139,6 +139,7 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
 #define MPC_KERNEL_AUTO 0
 #define MPC_KERNEL_WARP 1
 #define MPC_KERNEL_LANE 2
+#define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory (N <= 32) */
 #define MPC_LANE_MIN_BATCH 3072
 int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm);
 

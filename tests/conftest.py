@@ -46,10 +46,11 @@ def stable_cfg(mpc, refdata):
     return mpc.config_from_json_text(json.dumps(refdata["configs"]["stable"]))
 
 
-@pytest.fixture(scope="session", params=[1, 2], ids=["warp-kernel", "lane-kernel"])
+@pytest.fixture(scope="session", params=[1, 2, 3], ids=["warp-kernel", "lane-kernel", "coop-kernel"])
 def kernel_kind(request):
-    """Both CUDA kernels are held to the same parity bar: 1 = one problem per warp (latency path),
-    2 = one problem per lane (throughput path)."""
+    """Every CUDA kernel is held to the same parity bar: 1 = one problem per warp (first version, kept as a
+    cross-check), 2 = one problem per lane (throughput path), 3 = one problem per lane group with the rows in
+    shared memory (latency / small-batch / tail path)."""
     return request.param
 
 
