@@ -349,7 +349,7 @@ static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
   const int threads = 128;
   const int G = NS <= 16 ? 16 : 32;
   const int groups = threads / G;
-  const size_t smem = (size_t)groups * NS * ST_ROW * sizeof(double);
+  const size_t smem = (size_t)groups * NS * ST_ROW_SH * sizeof(double);
   static thread_local int cached_dev = -1;
   if (cached_dev != h->device) {
     CK(cudaFuncSetAttribute(mpc_coop_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -399,10 +399,12 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   kp.N_pp = N_per; kp.dt_pp = dt_per;
   kp.result = result; kp.traj_x = traj_x; kp.traj_y = traj_y; kp.full = full; kp.status = status; kp.iters = iters;
   kp.counter = h->d_counter;
-  // Kernel choice: the warp kernel (one problem per warp, N <= 32) minimises the latency of a
-  // handful of problems; the lane kernel (one problem per lane) maximises batch throughput.
+  // Kernel choice (crossovers measured on B200, profiles/r01_kernel_crossover.txt): below MPC_LANE_MIN_BATCH
+  // problems there are fewer problems than lanes and the time is set by the longest-running problem, so the
+  // coop kernel (one problem per group of 16/32 lanes) wins; above it the lane kernel (one problem per lane)
+  // has the throughput.  The warp kernel is the first version, kept selectable as a cross-check.
   int kind = h->kernel_kind;
-  if (kind == MPC_KERNEL_AUTO) kind = (B >= MPC_LANE_MIN_BATCH || c.N > 32) ? MPC_KERNEL_LANE : MPC_KERNEL_WARP;
+  if (kind == MPC_KERNEL_AUTO) kind = (B >= MPC_LANE_MIN_BATCH || c.N > 32) ? MPC_KERNEL_LANE : MPC_KERNEL_COOP;
   if (kind == MPC_KERNEL_WARP) {
     if (c.N > 32) { snprintf(g_err, sizeof(g_err), "warp kernel handles N <= 32"); return MPC_EINVAL; }
     return launch<32>(h, kp, (cudaStream_t)cuda_stream);

@@ -79,9 +79,11 @@ enum { ST_S = 0,      // iterate: x, y, psi, v, cte, epsi
        ST_CT = 52,
        ST_KG = 58,    // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
        ST_CS = 70,    // second-order-correction right-hand side (rare path only)
-       ST_ROW = 78 }; // 76 used; 78 keeps shared-memory rows of neighbouring lanes 2-way bank-conflict free
-template <int NS, bool SH> struct LaneRows { typedef double type[NS][ST_ROW]; };
-template <int NS> struct LaneRows<NS, true> { typedef double (*type)[ST_ROW]; };
+       ST_ROW = 78,   // thread-private rows (76 used, padded to a multiple of 16 bytes that is not one of 64)
+       ST_LH = 76,    // coop kernel only: StageLin (10) + StageHess (18) of the stage, built one stage per lane
+       ST_ROW_SH = 106 };   // shared-memory rows: 104 used; 106 keeps neighbouring lanes' rows 2-way bank-conflict free
+template <int NS, bool SH> struct LaneRows { typedef double type[NS][ST_ROW]; enum { ROW = ST_ROW }; };
+template <int NS> struct LaneRows<NS, true> { typedef double (*type)[ST_ROW_SH]; enum { ROW = ST_ROW_SH }; };
 
 struct StageLin { double a13, a14, a23, a24, a34, b3, a51, a54, a56, a61; };
 struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa, gp, gv, gc, ge, gdp, gd, ga; };
@@ -746,6 +748,49 @@ struct Lane {
   // max_i |slack_i * z_i - m|  from the extreme complementarity products
   __device__ __forceinline__ double compl_err(double m) const { return nanmax(fabs(amax - m), fabs(amin - m)); }
 
+  // coop kernel: derivative pieces of every stage at the iterate, one stage per lane, into the shared row
+  // (dw is added by the Riccati sweep, so an inertia-correction retry does not rebuild them)
+  __device__ void build_lh(bool ls) {
+    const int i = g0;
+    if (i < N) {
+      const bool hasu = i < N - 1;
+      double tg[8], ln[6], zl[4], zu[4], il[4], iu[4];
+#pragma unroll
+      for (int k = 0; k < 8; k++) tg[k] = hasu ? ST[i][ST_TG + k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) ln[k] = hasu ? ST[i + 1][ST_LAM + k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { zl[k] = (k < 2 || hasu) ? ST[i][ST_ZL + k] : 0.0; zu[k] = (k < 2 || hasu) ? ST[i][ST_ZU + k] : 0.0; }
+      const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3], c = ST[i][ST_S + 4], e = ST[i][ST_S + 5];
+      const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+      const double dprev = (hasu && i >= 1) ? ST[i - 1][ST_U + 0] : 0.0;
+      slack_rcp(psi, v, u0, u1, hasu, il, iu);
+      StageLin L;
+      StageHess H;
+      lin_at(tg, v, u0, L);
+      hess_at(i, ls, 0.0, tg, v, c, e, u0, dprev, ln, zl, zu, il, iu, H);
+      double *q = &ST[i][ST_LH];
+      q[0] = L.a13; q[1] = L.a14; q[2] = L.a23; q[3] = L.a24; q[4] = L.a34; q[5] = L.b3; q[6] = L.a51; q[7] = L.a54;
+      q[8] = L.a56; q[9] = L.a61;
+      q[10] = H.qxx; q[11] = H.qyy; q[12] = H.qpp; q[13] = H.qpv; q[14] = H.qvv; q[15] = H.qve; q[16] = H.qcc; q[17] = H.qee;
+      q[18] = H.svd; q[19] = H.rdd; q[20] = H.raa; q[21] = H.gp; q[22] = H.gv; q[23] = H.gc; q[24] = H.ge; q[25] = H.gdp;
+      q[26] = H.gd; q[27] = H.ga;
+    }
+    gsync();
+  }
+  __device__ __forceinline__ void load_lin(int i, StageLin &L) const {
+    const double *q = &ST[i][SH ? ST_LH : 0];
+    L.a13 = q[0]; L.a14 = q[1]; L.a23 = q[2]; L.a24 = q[3]; L.a34 = q[4]; L.b3 = q[5]; L.a51 = q[6]; L.a54 = q[7];
+    L.a56 = q[8]; L.a61 = q[9];
+  }
+  // ls: H = I has no dw (the least-squares system is not regularised)
+  __device__ __forceinline__ void load_hess(int i, double dwv, StageHess &H) const {
+    const double *q = &ST[i][SH ? ST_LH : 0];
+    H.qxx = q[10] + dwv; H.qyy = q[11] + dwv; H.qpp = q[12] + dwv; H.qpv = q[13]; H.qvv = q[14] + dwv; H.qve = q[15];
+    H.qcc = q[16] + dwv; H.qee = q[17] + dwv; H.svd = q[18]; H.rdd = q[19] + dwv; H.raa = q[20] + dwv;
+    H.gp = q[21]; H.gv = q[22]; H.gc = q[23]; H.ge = q[24]; H.gdp = q[25]; H.gd = q[26]; H.ga = q[27];
+  }
+
   // ------------------------------------------------------------------------------------------
   // slot 3: backward Riccati sweep.  Cost-to-go over (x, y, psi, v, epsi, delta_prev) as a dense
   // symmetric 6x6 in registers; cte enters only its own stage cost and the next cte linearly, so
@@ -759,11 +804,15 @@ struct Lane {
     double zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     {
       const int t = N - 1;
-      double zl[4] = {ST[t][ST_ZL + 0], ST[t][ST_ZL + 1], 0.0, 0.0}, zu[4] = {ST[t][ST_ZU + 0], ST[t][ST_ZU + 1], 0.0, 0.0}, il[4], iu[4];
-      const double psi = ST[t][ST_S + 2], v = ST[t][ST_S + 3];
-      slack_rcp(psi, v, 0.0, 0.0, false, il, iu);
       StageHess H;
-      hess_at(t, ls, dwv, zero8, v, ST[t][ST_S + 4], ST[t][ST_S + 5], 0.0, 0.0, zero8, zl, zu, il, iu, H);
+      if (SH) {
+        load_hess(t, dwv, H);
+      } else {
+        double zl[4] = {ST[t][ST_ZL + 0], ST[t][ST_ZL + 1], 0.0, 0.0}, zu[4] = {ST[t][ST_ZU + 0], ST[t][ST_ZU + 1], 0.0, 0.0}, il[4], iu[4];
+        const double psi = ST[t][ST_S + 2], v = ST[t][ST_S + 3];
+        slack_rcp(psi, v, 0.0, 0.0, false, il, iu);
+        hess_at(t, ls, dwv, zero8, v, ST[t][ST_S + 4], ST[t][ST_S + 5], 0.0, 0.0, zero8, zl, zu, il, iu, H);
+      }
 #pragma unroll
       for (int r = 0; r < 6; r++) {
 #pragma unroll
@@ -780,7 +829,10 @@ struct Lane {
       StageLin L;
       StageHess H;
       double d[6];
-      {
+      if (SH) {
+        load_lin(i, L);
+        load_hess(i, ls ? 0.0 : dwv, H);
+      } else {
         double tg[8], ln[6], zl[4], zu[4], il[4], iu[4];
 #pragma unroll
         for (int k = 0; k < 8; k++) tg[k] = ST[i][ST_TG + k];
@@ -931,6 +983,7 @@ struct Lane {
   // to the boundary for x and for z) and grad(phi_mu)^T dx of the line search
   // ------------------------------------------------------------------------------------------
   __device__ void forward_and_ratios(bool ls, bool soc) {
+    if (SH) { forward_par(ls, soc); return; }
     const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     double t[6], dp = 0.0;
 #pragma unroll
@@ -1009,6 +1062,98 @@ struct Lane {
     gbd_new = acc;
     if (ls) return;
     // alpha_max = min(1, tau / rmax),  alpha_z = min(1, tau * zn / zd)
+    alpha_soc = (rmax > tau) ? tau / rmax : 1.0;
+    alpha_z = (zd > 0.0 && tau * zn < zd) ? tau * zn / zd : 1.0;
+  }
+
+  // coop kernel: the recursion runs identically in every lane of the group (on the derivative pieces of
+  // build_lh); each lane keeps the step of its own stage and computes that stage's step-length ratios
+  __device__ void forward_par(bool ls, bool soc) {
+    const int G = SH ? NS_GROUP : 1;
+    const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    double t[6], dp = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) t[k] = ls ? 0.0 : (soc ? -cs0[k] : -c0[k]);
+    double mt[6] = {0, 0, 0, 0, 0, 0}, mdu0 = 0.0, mdu1 = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+      const bool hasu = i < N - 1;
+      double du0 = 0.0, du1 = 0.0, tn[6] = {0, 0, 0, 0, 0, 0};
+      if (hasu) {
+        double kg[12], d[6];
+#pragma unroll
+        for (int k = 0; k < 12; k++) kg[k] = ST[i][ST_KG + k];
+        du0 = kg[10] + kg[0] * t[0] + kg[1] * t[1] + kg[2] * t[2] + kg[3] * t[3] + kg[4] * dp;
+        du1 = kg[11] + kg[5] * t[0] + kg[6] * t[1] + kg[7] * t[2] + kg[8] * t[3] + kg[9] * dp;
+        if (ls) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) d[k] = 0.0;
+        } else if (soc) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CS + k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CN + k];
+        }
+        StageLin L;
+        load_lin(i, L);
+        tn[0] = t[0] + L.a13 * t[2] + L.a14 * t[3] + d[0];
+        tn[1] = t[1] + L.a23 * t[2] + L.a24 * t[3] + d[1];
+        tn[2] = t[2] + L.a34 * t[3] + L.b3 * du0 + d[2];
+        tn[3] = t[3] + dt * du1 + d[3];
+        tn[4] = L.a51 * t[0] - t[1] + L.a54 * t[3] + L.a56 * t[5] + d[4];
+        tn[5] = L.a61 * t[0] + t[2] + L.a34 * t[3] + L.b3 * du0 + d[5];
+      }
+      if (i == g0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { mt[k] = t[k]; ST[i][ST_DS + k] = t[k]; }
+        mdu0 = du0; mdu1 = du1;
+        if (hasu) { ST[i][ST_DU + 0] = du0; ST[i][ST_DU + 1] = du1; }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) t[k] = tn[k];
+      dp = du0;
+    }
+    double rmax = 0.0, zn = 1.0, zd = 0.0, acc = 0.0;
+    const int i = g0;
+    if (!ls && i < N) {
+      const bool hasu = i < N - 1;
+      const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3];
+      const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+      acc = (wv2 * (v - vref(i)) + nv2(i) * v) * mt[3] + wc2(i) * ST[i][ST_S + 4] * mt[4] + we2(i) * ST[i][ST_S + 5] * mt[5];
+      if (hasu) {
+        double gd = wd2 * u0;
+        if (i >= 1) gd += cw * (u0 - ST[i - 1][ST_U + 0]);
+        if (i <= N - 3) gd -= cw * (ST[i + 1][ST_U + 0] - u0);
+        acc += gd * mdu0;
+      }
+      double il[4], iu[4];
+      slack_rcp(psi, v, u0, u1, hasu, il, iu);
+      const double dx[4] = {mt[2], mt[3], mdu0, mdu1};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k < 2 || hasu) {
+          const double zl = ST[i][ST_ZL + k], zu = ST[i][ST_ZU + k];
+          acc += mu * (iu[k] - il[k]) * dx[k];
+          rmax = dmax(rmax, dmax(-dx[k] * il[k], dx[k] * iu[k]));
+          const double dzl = (mu - zl * dx[k]) * il[k] - zl;
+          const double dzu = (mu + zu * dx[k]) * iu[k] - zu;
+          if (dzl < 0.0 && (zd == 0.0 || zl * zd < zn * (-dzl))) { zn = zl; zd = -dzl; }
+          if (dzu < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu))) { zn = zu; zd = -dzu; }
+        }
+      }
+    }
+    gsync();
+    // group minimum of zn / zd (zd == 0 stands for +infinity), maximum of rmax, sum of acc
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double on = __shfl_xor_sync(gm, zn, o, G), od = __shfl_xor_sync(gm, zd, o, G);
+      const bool take = od > 0.0 && (zd == 0.0 || on * zd < zn * od || (on * zd == zn * od && on < zn));
+      if (take) { zn = on; zd = od; }
+    }
+    rmax = gmax<NS_GROUP>(rmax, gm);
+    gbd_new = gsum<NS_GROUP>(acc, gm);
+    if (ls) return;
     alpha_soc = (rmax > tau) ? tau / rmax : 1.0;
     alpha_z = (zd > 0.0 && tau * zn < zd) ? tau * zn / zd : 1.0;
   }
@@ -1210,6 +1355,7 @@ struct Lane {
     if (solve) {
       const bool ls = m3 == LM_LSQ;
       const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? dw : dw_used);
+      if (SH && (ls || (m3 == LM_NEWTON && dw == 0.0))) build_lh(ls);
       solve_ok = riccati(ls, m3 == LM_SOC, dwv);
     } else {
       m3 = LM_IDLE;
@@ -1303,7 +1449,7 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
   Lane<NS, true> Z;
   Z.g0 = lane % G; Z.gstep = G;
   Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
-  Z.ST = reinterpret_cast<double (*)[ST_ROW]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW);
+  Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
   for (;;) {
     int nb = 0;
     if (Z.g0 == 0) nb = atomicAdd(P.counter, 1);

@@ -133,14 +133,16 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
                          int *status, int *iters);
 
 /* Kernel selection.  MPC_KERNEL_AUTO (default): batches of at least MPC_LANE_MIN_BATCH problems, or
- * horizons above 32, run the throughput kernel (one problem per lane); smaller batches run the
- * latency kernel (one problem per warp); the crossover was measured on B200 (profiles/r01_kernel_crossover.txt).  lane_threads (CTA size 32..256, multiple of 32; 0 = automatic,
- * balanced over the SMs) and lane_ctas_per_sm (0 = one) tune the persistent grid of the lane kernel. */
+ * horizons above 32, run the throughput kernel (one problem per lane); smaller batches -- where the time is
+ * set by the longest-running problem, not by throughput -- run the coop kernel (one problem per group of
+ * 16/32 lanes, rows in shared memory).  The crossover was measured on B200 (profiles/r01_kernel_crossover.txt).
+ * lane_threads (CTA size 32..256, multiple of 32; 0 = automatic, balanced over the SMs) and
+ * lane_ctas_per_sm (0 = one) tune the persistent grid of the lane kernel. */
 #define MPC_KERNEL_AUTO 0
-#define MPC_KERNEL_WARP 1
+#define MPC_KERNEL_WARP 1   /* one problem per warp, stage per lane: the first version, kept as a cross-check (N <= 32) */
 #define MPC_KERNEL_LANE 2
 #define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory (N <= 32) */
-#define MPC_LANE_MIN_BATCH 3072
+#define MPC_LANE_MIN_BATCH 12288
 int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm);
 
 /* One problem, host pointers: state[6], coeffs[5] -> result[9], traj_x/traj_y[N] (or NULL).
