@@ -42,6 +42,10 @@ struct mpc_handle {
   int kernel_kind;      // MPC_KERNEL_AUTO / WARP / LANE
   int lane_threads;     // threads per CTA of the lane kernel
   int lane_ctas_per_sm; // CTAs per SM of the lane kernel (0 = occupancy maximum)
+  int handoff_iter;     // lane kernel parks problems still running after this many iterations for the coop kernel (0 = never)
+  double *d_ckpt;       // migration records
+  size_t cap_ckpt;      // records
+  int ckpt_ns;
   // staging buffers for the host-pointer entry points (grown on demand)
   double *d_in, *d_out;
   int *d_iout;
@@ -253,11 +257,12 @@ extern "C" int mpc_create(const mpc_config *cfg, int device, mpc_handle **out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
-  CK(cudaMalloc(&h->d_counter, sizeof(int)));
+  CK(cudaMalloc(&h->d_counter, 4 * sizeof(int)));   // work-queue counter, records written, records taken
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->kernel_kind = MPC_KERNEL_AUTO;
   h->lane_threads = 0;
   h->lane_ctas_per_sm = 0;
+  h->handoff_iter = 13;
   *out = h;
   return MPC_OK;
 }
@@ -266,6 +271,7 @@ extern "C" void mpc_destroy(mpc_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_counter);
+  cudaFree(h->d_ckpt);
   cudaFree(h->d_in);
   cudaFree(h->d_out);
   cudaFree(h->d_iout);
@@ -336,10 +342,44 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   long long grid = (long long)h->sm_count * (h->lane_ctas_per_sm > 0 ? h->lane_ctas_per_sm : 1);
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
+  // migration of the long runners to the coop kernel (same NS => same record layout); N <= 32 only
+  // (measured, profiles/r01_handoff_sweep.txt: 13% on the 64K batch; beyond a few rounds per lane the tail no
+  // longer matters and the coop kernel's lower throughput costs more than it saves)
+  const bool handoff = h->handoff_iter > 0 && NS <= 32 && kp.B >= MPC_LANE_MIN_BATCH && kp.B <= MPC_HANDOFF_MAX_BATCH;
+  kp.ckpt = nullptr; kp.ckpt_count = h->d_counter + 1; kp.ckpt_next = h->d_counter + 2; kp.ckpt_cap = 0;
+  kp.handoff_iter = h->handoff_iter;
+  if (handoff) {
+    size_t cap = (size_t)kp.B / 8;
+    if (cap > 32768) cap = 32768;
+    if (!h->d_ckpt || h->cap_ckpt < cap || h->ckpt_ns != NS) {
+      cudaFree(h->d_ckpt);
+      h->d_ckpt = nullptr;
+      CK(cudaMalloc(&h->d_ckpt, cap * Lane<NS, false>::CK_SIZE * sizeof(double)));
+      h->cap_ckpt = cap; h->ckpt_ns = NS;
+    }
+    kp.ckpt = h->d_ckpt; kp.ckpt_cap = (int)cap;
+  }
+  CK(cudaMemsetAsync(kp.counter, 0, 3 * sizeof(int), st));
   mpc_lane_kernel<NS, MINB><<<(unsigned)grid, threads, 0, st>>>(kp);
   CK(cudaGetLastError());
   h->launches++;
+  if (handoff) {
+    const int ct = 128, G = NS <= 16 ? 16 : 32, groups = ct / G;
+    const size_t smem = (size_t)groups * NS * ST_ROW_SH * sizeof(double);
+    static thread_local int cached_dev2 = -1;
+    if (cached_dev2 != h->device) {
+      CK(cudaFuncSetAttribute(mpc_coop_resume_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cached_dev2 = h->device;
+    }
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_resume_kernel<NS>, ct, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long g2 = (long long)h->sm_count * per_sm, w2 = ((long long)kp.ckpt_cap + groups - 1) / groups;
+    if (g2 > w2) g2 = w2;
+    mpc_coop_resume_kernel<NS><<<(unsigned)g2, ct, smem, st>>>(kp);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
   return MPC_OK;
 }
 
@@ -362,10 +402,17 @@ static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
   long long grid = (long long)h->sm_count * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
+  kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = 0; kp.ckpt_count = h->d_counter + 1; kp.ckpt_next = h->d_counter + 2;
   CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
   mpc_coop_kernel<NS><<<(unsigned)grid, threads, smem, st>>>(kp);
   CK(cudaGetLastError());
   h->launches++;
+  return MPC_OK;
+}
+
+extern "C" int mpc_set_handoff(mpc_handle *h, int iterations) {
+  if (!h || iterations < 0) return MPC_EINVAL;
+  h->handoff_iter = iterations;
   return MPC_OK;
 }
 
@@ -412,7 +459,7 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   if (kind == MPC_KERNEL_COOP) {
     if (c.N > 32) { snprintf(g_err, sizeof(g_err), "coop kernel handles N <= 32"); return MPC_EINVAL; }
     if (c.N <= 10) return launch_coop<10>(h, kp, (cudaStream_t)cuda_stream);
-    if (c.N <= 16) return launch_coop<16>(h, kp, (cudaStream_t)cuda_stream);
+    if (c.N <= 20) return launch_coop<20>(h, kp, (cudaStream_t)cuda_stream);
     return launch_coop<32>(h, kp, (cudaStream_t)cuda_stream);
   }
   if (c.N <= 10) return launch_lane<10, 1>(h, kp, (cudaStream_t)cuda_stream);
@@ -432,7 +479,7 @@ static int ensure_staging(mpc_handle *h, size_t B, int N, bool with_w) {
   CK(cudaMalloc(&h->d_in, nin * sizeof(double)));
   CK(cudaMalloc(&h->d_out, nout * sizeof(double)));
   CK(cudaMalloc(&h->d_iout, 3 * cap * sizeof(int)));
-  CK(cudaMallocHost(&h->h_pin, 64 * sizeof(double) + (9 + 2 * (size_t)N) * sizeof(double)));
+  CK(cudaMallocHost(&h->h_pin, 64 * sizeof(double) + (9 + 2 * (size_t)MPC_NMAX) * sizeof(double)));
   h->cap_B = cap; h->cap_N = N; h->cap_w = true;
   return MPC_OK;
 }
@@ -475,12 +522,37 @@ extern "C" int mpc_solve_batch_host(mpc_handle *h, int B, const double *state, c
   return MPC_OK;
 }
 
+// One problem: the inputs travel in ONE host-to-device copy from a pinned staging block and the outputs
+// come back in two (doubles, ints) -- a single solve is latency-bound, every API call counts.
 extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs, double yaw_lo,
                              double yaw_hi, double *result, double *traj_x, double *traj_y, int *status,
                              int *iters) {
   if (!h || !state || !coeffs || !result) return MPC_EINVAL;
-  return mpc_solve_batch_host(h, 1, state, coeffs, &yaw_lo, &yaw_hi, nullptr, nullptr, nullptr, result, traj_x,
-                              traj_y, nullptr, status, iters);
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.N;
+  int rc = ensure_staging(h, 1, N, false);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  double *hp = h->h_pin;                       // [13 inputs | 9 + 2N outputs | 2 ints]
+  for (int k = 0; k < 6; k++) hp[k] = state[k];
+  for (int k = 0; k < MPC_NCOEF; k++) hp[6 + k] = coeffs[k];
+  hp[11] = yaw_lo; hp[12] = yaw_hi;
+  double *d_in = h->d_in, *d_out = h->d_out;   // with B = 1 the [k][B] arrays are contiguous
+  CK(cudaMemcpyAsync(d_in, hp, 13 * sizeof(double), cudaMemcpyHostToDevice, st));
+  rc = mpc_solve_batch(h, 1, d_in, d_in + 6, d_in + 11, d_in + 12, nullptr, nullptr, nullptr, d_out, d_out + 9,
+                       d_out + 9 + N, nullptr, h->d_iout, h->d_iout + 1, st);
+  if (rc) return rc;
+  double *ho = hp + 16;
+  int *hi = reinterpret_cast<int *>(hp + 16 + 9 + 2 * (size_t)N);
+  CK(cudaMemcpyAsync(ho, d_out, (9 + 2 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hi, h->d_iout, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < 9; k++) result[k] = ho[k];
+  if (traj_x) for (int k = 0; k < N; k++) traj_x[k] = ho[9 + k];
+  if (traj_y) for (int k = 0; k < N; k++) traj_y[k] = ho[9 + N + k];
+  if (status) *status = hi[0];
+  if (iters) *iters = hi[1];
+  return MPC_OK;
 }
 
 // ---- whole control steps on the device ------------------------------------------------------------

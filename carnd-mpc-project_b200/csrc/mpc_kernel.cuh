@@ -83,6 +83,11 @@ struct KParams {
   int *status, *iters;
   int *counter;
   int ws_stride;   // doubles of shared memory per problem
+  // migration of long-running problems from the lane kernel to the coop kernel (mpc_lane_kernel.cuh)
+  double *ckpt;      // [ckpt_cap] records of lane_ckpt_doubles(NS) doubles, or NULL
+  int *ckpt_count;   // records written (may run past ckpt_cap: the surplus problems simply stay where they are)
+  int *ckpt_next;    // next record the coop kernel takes
+  int ckpt_cap, handoff_iter;
 };
 
 __host__ __device__ inline int workspace_doubles(int Nmax) {

@@ -107,7 +107,7 @@ struct Lane {
   __device__ __forceinline__ void gsync() const { if (SH) __syncwarp(gm); }
   // ---- scalars ----
   int m1, m3;
-  bool solve_ok;
+  bool solve_ok, lh_stale, no_handoff;
   int b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt;
   double mu, tau, theta_min, theta_max, dw, dw_last, dw_used;
   double alpha, alpha_z, alpha_test, alpha_soc, alpha_min;
@@ -1277,6 +1277,47 @@ struct Lane {
   }
 
 
+  // ---- migration: the complete state of a problem at a trip boundary as a flat record of doubles.  The
+  // lane kernel and the coop kernel run the same arithmetic on the same state, so a problem can be moved
+  // from one to the other between any two trips without changing a single bit of its result.
+  enum { CK_ROWS = NS * 76, CK_PC = CK_ROWS, CK_FLT = CK_PC + LC_SIZE, CK_C = CK_FLT + 2 * K_NFILT, CK_D = CK_C + 18,
+         CK_I = CK_D + 32, CK_SIZE = CK_I + 12 };
+  __device__ void save(double *r) const {
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep)
+      for (int k = 0; k < 76; k++) r[i * 76 + k] = ST[i][k];
+    if (g0 != 0) return;
+    for (int k = 0; k < LC_SIZE; k++) r[CK_PC + k] = PC[k];
+    for (int k = 0; k < 2 * K_NFILT; k++) r[CK_FLT + k] = FLT[k];
+    for (int k = 0; k < 6; k++) { r[CK_C + k] = c0[k]; r[CK_C + 6 + k] = c0t[k]; r[CK_C + 12 + k] = cs0[k]; }
+    const double d[32] = {mu, tau, theta_min, theta_max, dw, dw_last, dw_used, alpha, alpha_z, alpha_test, alpha_soc,
+                          alpha_min, ls_theta, ls_phi, ls_gbd, pow_gbd, pow_theta, fx, lsum, theta, ft, lt, tht,
+                          theta_soc_old, dinf, cviol, amin, amax, lam1, z1, lsq_lmax, gbd_new};
+    for (int k = 0; k < 32; k++) r[CK_D + k] = d[k];
+    const int n[12] = {b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt, 0, 0, 0};
+    for (int k = 0; k < 12; k++) r[CK_I + k] = (double)n[k];
+  }
+  __device__ void load(const double *r) {
+    N = (int)r[CK_I + 1];
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep)
+      for (int k = 0; k < 76; k++) ST[i][k] = r[i * 76 + k];
+    for (int k = 0; k < LC_SIZE; k++) PC[k] = r[CK_PC + k];
+    for (int k = 0; k < 2 * K_NFILT; k++) FLT[k] = r[CK_FLT + k];
+    for (int k = 0; k < 6; k++) { c0[k] = r[CK_C + k]; c0t[k] = r[CK_C + 6 + k]; cs0[k] = r[CK_C + 12 + k]; }
+    const double *d = r + CK_D;
+    mu = d[0]; tau = d[1]; theta_min = d[2]; theta_max = d[3]; dw = d[4]; dw_last = d[5]; dw_used = d[6]; alpha = d[7];
+    alpha_z = d[8]; alpha_test = d[9]; alpha_soc = d[10]; alpha_min = d[11]; ls_theta = d[12]; ls_phi = d[13];
+    ls_gbd = d[14]; pow_gbd = d[15]; pow_theta = d[16]; fx = d[17]; lsum = d[18]; theta = d[19]; ft = d[20]; lt = d[21];
+    tht = d[22]; theta_soc_old = d[23]; dinf = d[24]; cviol = d[25]; amin = d[26]; amax = d[27]; lam1 = d[28];
+    z1 = d[29]; lsq_lmax = d[30]; gbd_new = d[31];
+    const double *n = r + CK_I;
+    b = (int)n[0]; mode = (int)n[2]; status = (int)n[3]; iter = (int)n[4]; accept_cnt = (int)n[5]; nfilt = (int)n[6];
+    ntrial = (int)n[7]; soc_cnt = (int)n[8];
+    lh_stale = true;
+    gsync();
+  }
+
   // ---- one trip of the state machine, in four slots (shared by the lane kernel and the coop kernel) -------
   // slot 1: evaluate a point
   __device__ __forceinline__ void trip_eval() {
@@ -1355,7 +1396,7 @@ struct Lane {
     if (solve) {
       const bool ls = m3 == LM_LSQ;
       const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? dw : dw_used);
-      if (SH && (ls || (m3 == LM_NEWTON && dw == 0.0))) build_lh(ls);
+      if (SH && (lh_stale || ls || (m3 == LM_NEWTON && dw == 0.0))) { build_lh(ls); lh_stale = false; }
       solve_ok = riccati(ls, m3 == LM_SOC, dwv);
     } else {
       m3 = LM_IDLE;
@@ -1416,9 +1457,19 @@ __global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
   Z.mode = LM_IDLE;
   Z.b = 0;
   Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;
+  Z.lh_stale = false; Z.no_handoff = false;
   for (;;) {
-    // ---- slot 0: retire / fetch
+    // ---- slot 0: retire / migrate / fetch
     if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
+    // A problem that is still running after handoff_iter iterations is one of the few that set the length of
+    // the batch's tail; a lone lane needs ~47 us per trip for it.  Park it for the coop kernel, which runs
+    // after this one and takes ~19 us per trip, and pull the next problem.
+    if (P.ckpt && Z.mode != LM_IDLE && Z.mode != LM_DONE && Z.iter >= P.handoff_iter && !Z.no_handoff) {
+      const int slot = atomicAdd(P.ckpt_count, 1);
+      if (slot < P.ckpt_cap) { Z.save(P.ckpt + (size_t)slot * Lane<NS, false>::CK_SIZE); Z.mode = LM_IDLE; }
+      else Z.no_handoff = true;
+    }
+    if (Z.mode == LM_IDLE) Z.no_handoff = false;
     if (Z.mode == LM_IDLE) {
       const int nb = atomicAdd(P.counter, 1);
       if (nb < P.B) Z.init(P, nb); else Z.mode = LM_DONE;
@@ -1450,12 +1501,45 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
   Z.g0 = lane % G; Z.gstep = G;
   Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
   Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
+  Z.lh_stale = false; Z.no_handoff = false;
   for (;;) {
     int nb = 0;
     if (Z.g0 == 0) nb = atomicAdd(P.counter, 1);
     nb = __shfl_sync(Z.gm, nb, 0, G);
     if (nb >= P.B) break;
     Z.init(P, nb);
+    while (Z.mode != LM_FINISH) {
+      Z.trip_eval();
+      Z.trip_accept(P);
+      if (Z.mode == LM_FINISH) break;
+      Z.trip_factor();
+      Z.trip_solve();
+    }
+    if (Z.g0 == 0) Z.write_outputs(P);
+    Z.gsync();
+  }
+}
+
+// The coop kernel on the problems the lane kernel parked: each group takes a record, restores the state and
+// carries on from the trip where the lane stopped.
+template <int NS>
+__global__ void __launch_bounds__(128, 2) mpc_coop_resume_kernel(const KParams P) {
+  extern __shared__ double coop_smem[];
+  const int G = Lane<NS, true>::NS_GROUP;
+  const int lane = threadIdx.x & 31;
+  Lane<NS, true> Z;
+  Z.g0 = lane % G; Z.gstep = G;
+  Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
+  Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
+  Z.no_handoff = true;
+  int n = *P.ckpt_count;
+  if (n > P.ckpt_cap) n = P.ckpt_cap;
+  for (;;) {
+    int k = 0;
+    if (Z.g0 == 0) k = atomicAdd(P.ckpt_next, 1);
+    k = __shfl_sync(Z.gm, k, 0, G);
+    if (k >= n) break;
+    Z.load(P.ckpt + (size_t)k * Lane<NS, true>::CK_SIZE);
     while (Z.mode != LM_FINISH) {
       Z.trip_eval();
       Z.trip_accept(P);

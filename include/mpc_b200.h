@@ -144,6 +144,14 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
 #define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory (N <= 32) */
 #define MPC_LANE_MIN_BATCH 12288
 int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm);
+#define MPC_HANDOFF_MAX_BATCH 300000
+/* Batches of MPC_LANE_MIN_BATCH .. MPC_HANDOFF_MAX_BATCH problems with N <= 32: the lane kernel parks the
+ * problems that are still running after `iterations` interior-point iterations (default 13; ~6 % of the
+ * config-stable workload) and the coop
+ * kernel finishes them right after on the same stream -- they are the ones that set the length of the batch's
+ * tail and the coop kernel takes 40 % of the time per iteration on them.  The two kernels run identical
+ * arithmetic, so results do not depend on this setting.  0 disables the migration. */
+int mpc_set_handoff(mpc_handle *h, int iterations);
 
 /* One problem, host pointers: state[6], coeffs[5] -> result[9], traj_x/traj_y[N] (or NULL).
  * What `MPC::solve` calls once per telemetry message. */

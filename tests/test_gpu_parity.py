@@ -266,3 +266,25 @@ def test_rare_paths_regularisation_and_long_runs(mpc, po, refdata, kernel_kind):
         assert g["status"][i] == 1
         assert np.abs(g["result"][i, :8] - np.array(o.result[:8])).max() < ABS_TOL
         assert g["result"][i, 8] == pytest.approx(o.result[8], rel=REL_TOL)
+
+
+def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
+    """Large batches: the lane kernel parks long-running problems and the coop kernel finishes them.  Both run
+    the same arithmetic on the same state, so the results are bit-identical whatever the threshold -- including
+    thresholds that migrate most of the batch or overflow the record buffer."""
+    S = mpc.Solver(stable_cfg, 0)
+    b = mpc.workloads.batch_perturbed_states(16384, 91, stable_cd)
+    args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.set_kernel(mpc.KERNEL_LANE)
+    S.set_handoff(0)
+    ref = S.solve_batch_host(*args, want_full=True)
+    for it in (1, 5, 10, 13, 25):
+        S.set_handoff(it)
+        n0 = S.launches
+        got = S.solve_batch_host(*args, want_full=True)
+        assert S.launches - n0 == 2                                   # lane kernel + coop finisher
+        for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
+            assert np.array_equal(got[k], ref[k]), (it, k)
+    with pytest.raises(mpc.MpcError):
+        S.set_handoff(-1)
+    S.close()

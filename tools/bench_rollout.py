@@ -12,12 +12,12 @@ cd = cfg.as_dict()
 wx, wy = up(np.array(rd['waypoints']['x'])), up(np.array(rd['waypoints']['y']))
 S = mpc.Solver(cfg, 0)
 if 'crossover' in sys.argv:
-    for B in (256, 512, 1024, 2048, 4096, 8192, 16384):
+    for B in (1, 256, 1024, 2048, 4096, 8192, 12288, 16384, 32768):
         b = mpc.workloads.batch_perturbed_states(B, 0, cd)
         ins = [up(b['state'].T), up(b['coeffs'].T), up(b['yaw_lo']), up(b['yaw_hi'])]
         outs = [torch.zeros(9, B, dtype=torch.float64, device=dev), None, None, None, torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)]
         line = 'B=%6d ' % B
-        for kind, nm in ((mpc.KERNEL_WARP, 'warp'), (mpc.KERNEL_LANE, 'lane')):
+        for kind, nm in ((mpc.KERNEL_WARP, 'warp'), (mpc.KERNEL_LANE, 'lane'), (mpc.KERNEL_COOP, 'coop')):
             S.set_kernel(kind)
             best = 1e9
             for _ in range(4):
