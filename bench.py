@@ -135,6 +135,83 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def extras(mpc, torch, dev, rd, local_rank):
+    """The other BASELINE.json configs on ONE GPU, informational (the headline stays configs[1]): a 1M batch (the
+    steady-state rate without the tail), the N x dt grid in one ragged launch (config 3), a per-problem weight
+    sweep (config 4), and closed-loop rollouts with 100 ms latency (config 5, one GPU's share: 1024 vehicles)."""
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def timed(fn, reps=3):
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    out = {}
+    js = rd["configs"]["stable"]
+    cfg = mpc.config_from_json_text(json.dumps(js))
+    cd = cfg.as_dict()
+    # 1M batch
+    B = 1 << 20
+    b = mpc.workloads.batch_perturbed_states(B, 0, cd)
+    ins = [up(b["state"].T), up(b["coeffs"].T), up(b["yaw_lo"]), up(b["yaw_hi"])]
+    res = torch.zeros(9, B, dtype=torch.float64, device=dev)
+    st = torch.zeros(B, dtype=torch.int32, device=dev); it = torch.zeros(B, dtype=torch.int32, device=dev)
+    S = mpc.Solver(cfg, local_rank)
+    ms = timed(lambda: S.solve_batch_device(B, *ins, res, None, None, None, st, it))
+    out["batch_1M"] = {"solves_per_s": B / ms * 1e3, "ms": ms, "status_ok_frac": float((st == 1).float().mean().item()),
+                       "fp64_flops_frac_of_measured_peak": None}
+    out["batch_1M"]["tflops"] = f_iter(cfg.N) * float(it.sum().item()) / (ms * 1e-3) / 1e12
+    # config 4: per-problem weights, 128K problems
+    B4 = 131072
+    rng = np.random.default_rng(2)
+    sel = rng.integers(0, 4096, B4)
+    W = np.tile(np.array(cd["weights"]), (B4, 1))
+    W[:, 3] = np.exp(rng.uniform(np.log(1), np.log(5000), B4)); W[:, 4] = np.exp(rng.uniform(np.log(1), np.log(5000), B4))
+    W[:, 1] = np.exp(rng.uniform(np.log(1), np.log(1000), B4)); W[:, 2] = rng.choice([0.01, 0.1, 1, 10, 100], B4)
+    ins4 = [up(b["state"][sel].T), up(b["coeffs"][sel].T), up(b["yaw_lo"][sel]), up(b["yaw_hi"][sel])]
+    Wd = up(W.T)
+    ms = timed(lambda: S.solve_batch_device(B4, *ins4, res[:, :B4].contiguous(), None, None, None, st[:B4], it[:B4], weights=Wd), 2)
+    out["config4_weight_sweep_128K"] = {"solves_per_s": B4 / ms * 1e3, "ms": ms, "status_ok_frac": float((st[:B4] == 1).float().mean().item()),
+                                        "iters_max": int(it[:B4].max().item())}
+    S.close()
+    # config 3: N x dt grid, one ragged launch of 256K problems
+    PAIRS = [(10, .1), (20, .1), (30, .1), (40, .1), (10, .05), (20, .05), (30, .05), (40, .05), (50, .05), (10, .02), (20, .02), (30, .02), (40, .02), (50, .02)]
+    B3 = 262144
+    rng = np.random.default_rng(1)
+    pick = rng.integers(0, len(PAIRS), B3)
+    Np = up(np.array([PAIRS[k][0] for k in pick], dtype=np.int32)); dtp = up(np.array([PAIRS[k][1] for k in pick]))
+    cfg3 = mpc.config_from_json_text(json.dumps(dict(js, N=50)))
+    S3 = mpc.Solver(cfg3, local_rank)
+    ins3 = [t[..., :B3].contiguous() for t in ins]
+    ms = timed(lambda: S3.solve_batch_device(B3, *ins3, res[:, :B3].contiguous(), None, None, None, st[:B3], it[:B3], N_per=Np, dt_per=dtp), 1)
+    out["config3_horizon_grid_256K"] = {"solves_per_s": B3 / ms * 1e3, "ms": ms, "status_ok_frac": float((st[:B3] == 1).float().mean().item()),
+                                        "iters_max": int(it[:B3].max().item()), "note": "N in 10..50 x dt in {0.1,0.05,0.02}; long horizons extrapolate the fit and a few percent end without success, as in the reference (SURVEY App. C)"}
+    S3.close()
+    # config 5: closed loop, config-fast (100 ms latency), 1024 vehicles (one GPU's share of 8192) x 200 steps
+    cfgf = mpc.config_from_json_text(json.dumps(rd["configs"]["fast"]))
+    cdf = cfgf.as_dict()
+    V, T = 1024, 200
+    bv = mpc.workloads.batch_perturbed_states(V, 3, cdf)
+    veh = up(np.stack([bv["px"], bv["py"], bv["psi"], np.clip(bv["v"], 8, 30), np.zeros(V), np.zeros(V)]))
+    seg = up(bv["segment"].astype(np.int32))
+    pend = torch.zeros(2, V, dtype=torch.float64, device=dev)
+    rec = torch.zeros(T, 8, V, dtype=torch.float64, device=dev)
+    wx, wy = up(np.array(rd["waypoints"]["x"])), up(np.array(rd["waypoints"]["y"]))
+    S5 = mpc.Solver(cfgf, local_rank)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); S5.rollout_device(V, T, wx, wy, veh, seg, pend, 0.1, 0.02, rec); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out["config5_closed_loop_1024x200"] = {"vehicle_steps_per_s": V * T / ms * 1e3, "ms_per_control_step": ms / T,
+                                           "status_ok_frac": float((rec[:, 6] == 1).float().mean().item()),
+                                           "median_abs_cte_final_m": float(rec[-1, 0].abs().median().item())}
+    S5.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,6 +221,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (1M batch, sweeps, rollouts)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -318,6 +396,8 @@ def main():
             line["latency"] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)),
                                "what": "mpc_solve_one host call -> result (B=1, H2D+kernel+D2H)", "batch_ms": ms_per_step}
             one.close()
+        if world == 1 and not args.no_extras:
+            line["extras"] = extras(mpc, torch, dev, rd, local_rank)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             t_pilot, _ = cpu_port(rd, batch, min(B, 4 * cores), cores)
