@@ -33,7 +33,7 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
-           "mpc_rollout", "mpc_set_handoff"]
+           "mpc_rollout", "mpc_set_handoff", "mpc_set_dual_outputs"]
 
 
 class MpcError(RuntimeError):
@@ -110,6 +110,7 @@ def lib():
     L.mpc_set_config.argtypes = [vp, cfgp]
     L.mpc_set_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_set_handoff.argtypes = [vp, C.c_int]
+    L.mpc_set_dual_outputs.argtypes = [vp, vp, vp, vp]
     L.mpc_solve_batch.argtypes = [vp, C.c_int] + [vp] * 13 + [vp]
     L.mpc_solve_batch_host.argtypes = [vp, C.c_int] + [vp] * 13
     L.mpc_solve_one.argtypes = [vp, dp, dp, C.c_double, C.c_double, dp, dp, dp, ip, ip]
@@ -243,6 +244,11 @@ class Solver:
     def set_handoff(self, iterations):
         """Iteration count after which the lane kernel hands a problem to the coop kernel (0 = never)."""
         _check(lib().mpc_set_handoff(self._h, iterations), "mpc_set_handoff")
+
+    def set_dual_outputs(self, lam=None, zl=None, zu=None):
+        """Device tensors lam [6N][B], zl, zu [8N-2][B] receiving the multipliers of later solves (None = off)."""
+        self._dual = (lam, zl, zu)   # keep them alive
+        _check(lib().mpc_set_dual_outputs(self._h, _ptr(lam), _ptr(zl), _ptr(zu)), "mpc_set_dual_outputs")
 
     @property
     def launches(self):

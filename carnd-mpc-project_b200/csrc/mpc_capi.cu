@@ -46,6 +46,7 @@ struct mpc_handle {
   double *d_ckpt;       // migration records
   size_t cap_ckpt;      // records
   int ckpt_ns;
+  double *dual_lam, *dual_zl, *dual_zu;   // caller's device buffers for the multipliers (or NULL)
   // staging buffers for the host-pointer entry points (grown on demand)
   double *d_in, *d_out;
   int *d_iout;
@@ -410,6 +411,12 @@ static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
   return MPC_OK;
 }
 
+extern "C" int mpc_set_dual_outputs(mpc_handle *h, double *lambda, double *zl, double *zu) {
+  if (!h || ((lambda != nullptr) != (zl != nullptr)) || ((lambda != nullptr) != (zu != nullptr))) return MPC_EINVAL;
+  h->dual_lam = lambda; h->dual_zl = zl; h->dual_zu = zu;
+  return MPC_OK;
+}
+
 extern "C" int mpc_set_handoff(mpc_handle *h, int iterations) {
   if (!h || iterations < 0) return MPC_EINVAL;
   h->handoff_iter = iterations;
@@ -446,6 +453,7 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   kp.N_pp = N_per; kp.dt_pp = dt_per;
   kp.result = result; kp.traj_x = traj_x; kp.traj_y = traj_y; kp.full = full; kp.status = status; kp.iters = iters;
   kp.counter = h->d_counter;
+  kp.dual_lam = h->dual_lam; kp.dual_zl = h->dual_zl; kp.dual_zu = h->dual_zu;
   // Kernel choice (crossovers measured on B200, profiles/r01_kernel_crossover.txt): below MPC_LANE_MIN_BATCH
   // problems there are fewer problems than lanes and the time is set by the longest-running problem, so the
   // coop kernel (one problem per group of 16/32 lanes) wins; above it the lane kernel (one problem per lane)

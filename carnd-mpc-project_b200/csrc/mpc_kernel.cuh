@@ -88,6 +88,8 @@ struct KParams {
   int *ckpt_count;   // records written (may run past ckpt_cap: the surplus problems simply stay where they are)
   int *ckpt_next;    // next record the coop kernel takes
   int ckpt_cap, handoff_iter;
+  // optional multiplier outputs (solution.lambda / zl / zu of CppAD::ipopt::solve_result), unscaled
+  double *dual_lam, *dual_zl, *dual_zu;
 };
 
 __host__ __device__ inline int workspace_doubles(int Nmax) {

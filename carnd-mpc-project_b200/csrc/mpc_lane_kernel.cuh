@@ -1259,6 +1259,18 @@ struct Lane {
         for (int k = 0; k < 6; k++) P.result[(size_t)k * B + b] = s[k];
       }
       if (i == 0) { P.result[6 * B + b] = u0; P.result[7 * B + b] = u1; }
+      if (P.dual_lam) {   // multipliers of the reference's NLP (objective unscaled): rows k*N+i, variables as MPC.cpp:189-196
+        const int Nf = P.Nmax;
+        const double isf = 1.0 / PC[LC_SF];
+#pragma unroll
+        for (int k = 0; k < 6; k++) P.dual_lam[(size_t)(k * Nf + i) * B + b] = ST[i][ST_LAM + k] * isf;
+        P.dual_zl[(size_t)(2 * Nf + i) * B + b] = ST[i][ST_ZL + 0] * isf; P.dual_zu[(size_t)(2 * Nf + i) * B + b] = ST[i][ST_ZU + 0] * isf;
+        P.dual_zl[(size_t)(3 * Nf + i) * B + b] = ST[i][ST_ZL + 1] * isf; P.dual_zu[(size_t)(3 * Nf + i) * B + b] = ST[i][ST_ZU + 1] * isf;
+        if (hasu) {
+          P.dual_zl[(size_t)(6 * Nf + i) * B + b] = ST[i][ST_ZL + 2] * isf; P.dual_zu[(size_t)(6 * Nf + i) * B + b] = ST[i][ST_ZU + 2] * isf;
+          P.dual_zl[(size_t)(7 * Nf - 1 + i) * B + b] = ST[i][ST_ZL + 3] * isf; P.dual_zu[(size_t)(7 * Nf - 1 + i) * B + b] = ST[i][ST_ZU + 3] * isf;
+        }
+      }
       if (P.traj_x) P.traj_x[(size_t)i * B + b] = s[0];
       if (P.traj_y) P.traj_y[(size_t)i * B + b] = s[1];
       if (P.full) {

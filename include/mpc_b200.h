@@ -153,6 +153,13 @@ int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_
  * arithmetic, so results do not depend on this setting.  0 disables the migration. */
 int mpc_set_handoff(mpc_handle *h, int iterations);
 
+/* Multiplier outputs for the following mpc_solve_batch calls on this handle (lane and coop kernels): DEVICE
+ * buffers lambda [6*cfg.N][B] (solution.lambda, rows in the reference's constraint order MPC.cpp:116-153) and
+ * zl, zu [8*cfg.N-2][B] (solution.zl / zu, variable order MPC.cpp:189-196; zero where a variable is unbounded;
+ * the caller clears them), for the UNSCALED problem.  With them a result can be certified as a KKT point of the
+ * reference's NLP independently of the solver.  All NULL switches the outputs off.  Only with N_per == NULL. */
+int mpc_set_dual_outputs(mpc_handle *h, double *lambda, double *zl, double *zu);
+
 /* One problem, host pointers: state[6], coeffs[5] -> result[9], traj_x/traj_y[N] (or NULL).
  * What `MPC::solve` calls once per telemetry message. */
 int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs,

@@ -107,3 +107,18 @@ def start_point(cd, state):
     for k in range(6):
         xi[:, k * N] = state[:, k]
     return xi
+
+
+def lagrangian_gradient(cd, fz, state, coeffs, z, lam, zl, zu):
+    """grad_z [ f(z) + lam^T g(z) ] - zl + zu, [B, 8N-2], by complex-step differentiation of the statements
+    above (exact to rounding: f and g are analytic) -- no hand-written derivative is trusted here."""
+    B, n = z.shape
+    h = 1e-30
+    out = np.zeros((B, n))
+    zc = z.astype(np.complex128)
+    for k in range(n):
+        zk = zc.copy()
+        zk[:, k] += 1j * h
+        L = objective(cd, fz, zk) + np.sum(lam * constraints(cd, state, coeffs, zk), axis=1)
+        out[:, k] = L.imag / h
+    return out - zl + zu

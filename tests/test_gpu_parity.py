@@ -288,3 +288,71 @@ def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
     with pytest.raises(mpc.MpcError):
         S.set_handoff(-1)
     S.close()
+
+
+def test_full_size_kkt_certificate(mpc, stable_cfg, stable_cd, kernel_kind):
+    """Solver-independent proof of optimality at full batch size: with the multipliers the kernels return, every
+    successful result of the 65,536-problem batch satisfies the KKT conditions of the reference's NLP as stated
+    independently in tests/nlp_numpy.py (complex-step gradient of the Lagrangian, no hand-written derivative):
+    stationarity, primal feasibility, dual feasibility, complementarity.  Ipopt's own acceptance test is
+    max(scaled errors) <= 1e-8 with scaling s_d, s_c >= 1 and an unscaled dual-infeasibility cap of 1."""
+    import torch
+    if kernel_kind == 1:
+        pytest.skip("the first-version warp kernel has no multiplier outputs")
+    B, N = 65536, stable_cd["N"]
+    cd = stable_cd
+    b = mpc.workloads.batch_perturbed_states(B, 0, cd)
+    S = mpc.Solver(stable_cfg, 0)
+    S.set_kernel(kernel_kind)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a.T if a.ndim == 2 else a)).to(dev)
+    lam = torch.zeros(6 * N, B, dtype=torch.float64, device=dev)
+    zl = torch.zeros(8 * N - 2, B, dtype=torch.float64, device=dev)
+    zu = torch.zeros(8 * N - 2, B, dtype=torch.float64, device=dev)
+    full = torch.zeros(8 * N - 2, B, dtype=torch.float64, device=dev)
+    res = torch.zeros(9, B, dtype=torch.float64, device=dev)
+    st = torch.zeros(B, dtype=torch.int32, device=dev)
+    S.set_dual_outputs(lam, zl, zu)
+    S.solve_batch_device(B, up(b["state"]), up(b["coeffs"]), up(b["yaw_lo"]), up(b["yaw_hi"]), res, None, None, full, st, None)
+    torch.cuda.synchronize()
+    S.set_dual_outputs(None, None, None)
+    S.close()
+    ok = st.cpu().numpy() == 1
+    assert ok.mean() > 0.995
+    z, lam, zl, zu = full.cpu().numpy().T[ok], lam.cpu().numpy().T[ok], zl.cpu().numpy().T[ok], zu.cpu().numpy().T[ok]
+    state, coeffs = b["state"][ok], b["coeffs"][ok]
+    fz = {k: v[ok] if isinstance(v, np.ndarray) and v.shape[0] == B else v for k, v in nn.frozen(cd, b["state"]).items()}
+    # primal feasibility and bounds
+    assert np.abs(nn.constraints(cd, state, coeffs, z)).max() < 1e-7
+    xl, xu = nn.var_bounds(cd, b["yaw_lo"][ok], b["yaw_hi"][ok])
+    assert (z >= xl).all() and (z <= xu).all()
+    # dual feasibility; multipliers only on bounded variables
+    assert (zl >= 0).all() and (zu >= 0).all()
+    assert (zl[xl < -1e18] == 0).all() and (zu[xu > 1e18] == 0).all()
+    # stationarity of the Lagrangian (unscaled; Ipopt scales by s_d >= 1 before comparing with 1e-8)
+    g = nn.lagrangian_gradient(cd, fz, state, coeffs, z, lam, zl, zu)
+    sd = np.maximum(100.0, (np.abs(lam).sum(axis=1) + zl.sum(axis=1) + zu.sum(axis=1)) / (6 * N + 2 * (4 * N + 4 * (N - 1)) / 2)) / 100.0
+    gn = np.abs(g).max(axis=1) / sd
+    # Ipopt converges on bounds relaxed by 1e-8*max(1,|b|) and then clips the point to the original bounds
+    # (honor_original_bounds): where a steering or speed bound is active that moves the point by <= 5e-9 and the
+    # gradient by (2 w_delta + 4 w_ddelta) * 5e-9 ~ 3e-5.  Everywhere else the result is stationary to rounding.
+    nl = slice(2 * N, 7 * N - 1)      # psi, v, (cte, epsi: unbounded), delta -- the acceleration enters f and g linearly
+    at_bound = (((z - xl) < 1e-7 * np.maximum(1, np.abs(xl)))[:, nl].any(axis=1)
+                | ((xu - z) < 1e-7 * np.maximum(1, np.abs(xu)))[:, nl].any(axis=1))
+    assert 0.0 < at_bound.mean() < 0.5
+    assert gn.max() < 1e-4, gn.max()
+    assert gn[~at_bound].max() < 2e-7, gn[~at_bound].max()
+    assert np.median(gn) < 1e-10
+    # complementarity with the ORIGINAL bounds (a point clipped onto its bound has slack 0; inside, the slack to
+    # the original bound is smaller than the one the solver used).  Ipopt's tests: 1e-4 on the unscaled problem
+    # (compl_inf_tol) and 1e-8 * s_c, s_c >= 1, on the problem whose objective is scaled by
+    # sf = min(1, 100 / ||grad f(xi)||_inf) (gradient-based scaling at the start point xi).
+    bounded_l, bounded_u = xl > -1e18, xu < 1e18
+    cl = np.where(bounded_l, zl * (z - xl), 0.0).max(axis=1)
+    cu = np.where(bounded_u, zu * (xu - z), 0.0).max(axis=1)
+    assert max(cl.max(), cu.max()) < 1e-4
+    xi = nn.start_point(cd, state)
+    g0 = nn.lagrangian_gradient(cd, fz, state, coeffs, xi, np.zeros_like(lam), np.zeros_like(zl), np.zeros_like(zu))
+    sf = np.minimum(1.0, 100.0 / np.abs(g0).max(axis=1))
+    sc = np.maximum(100.0, sf * (zl.sum(axis=1) + zu.sum(axis=1)) / (4 * N + 4 * (N - 1))) / 100.0
+    assert (sf * np.maximum(cl, cu) / sc).max() < 2e-8, (sf * np.maximum(cl, cu) / sc).max()
