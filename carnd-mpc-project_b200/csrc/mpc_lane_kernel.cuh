@@ -1459,10 +1459,10 @@ struct Lane {
 };
 
 // Persistent grid, one CTA per SM; every lane pulls problems from the global counter until the batch is
-// exhausted.  The warps of a CTA walk through the slots of a trip together (__syncthreads between
-// slots): the loop body is ~100 KB of code, and warps at different places in it thrash the instruction
-// cache (profiles/r01_v3_*: 3.3 issue slots lost per instruction to "no instruction"); in step, the
-// CTA's instruction footprint is one sweep at a time.
+// exhausted.  The warps of a CTA start every trip together (the exit vote is a __syncthreads): the loop
+// body is ~100 KB of code, and warps at unrelated places in it thrash the instruction cache
+// (profiles/r01_v3_*: 3.3 issue slots lost per instruction to "no instruction" with independent one-warp
+// CTAs).  Further barriers between the slots of a trip were measured to make no difference (+-2 %).
 template <int NS, int MINB>
 __global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
   Lane<NS, false> Z;
@@ -1488,11 +1488,8 @@ __global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
     }
     if (__syncthreads_and(Z.mode == LM_DONE)) break;
     Z.trip_eval();
-    __syncthreads();
     Z.trip_accept(P);
-    __syncthreads();
     Z.trip_factor();
-    __syncthreads();
     Z.trip_solve();
   }
 }
