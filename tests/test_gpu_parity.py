@@ -356,3 +356,37 @@ def test_full_size_kkt_certificate(mpc, stable_cfg, stable_cd, kernel_kind):
     sf = np.minimum(1.0, 100.0 / np.abs(g0).max(axis=1))
     sc = np.maximum(100.0, sf * (zl.sum(axis=1) + zu.sum(axis=1)) / (4 * N + 4 * (N - 1))) / 100.0
     assert (sf * np.maximum(cl, cu) / sc).max() < 2e-8, (sf * np.maximum(cl, cu) / sc).max()
+
+
+@pytest.mark.parametrize("N,dt", [(20, 0.05), (32, 0.05)])
+def test_migration_longer_horizons(mpc, refdata, po, N, dt):
+    """Horizons above 10 use the 20- and 32-stage instantiations (groups of 32 lanes in the coop kernel); the
+    lane -> coop migration must stay invisible there too, also with per-problem weights."""
+    js = dict(refdata["configs"]["stable"], N=N, dt=dt)
+    cfg = mpc.config_from_json_text(json.dumps(js))
+    cd = po.load_config_dict(js)
+    B = mpc.LANE_MIN_BATCH
+    b = mpc.workloads.batch_perturbed_states(B, 17, cd)
+    rng = np.random.default_rng(3)
+    W = np.tile(np.array(cd["weights"]), (B, 1))
+    W[:, 3] = np.exp(rng.uniform(np.log(10), np.log(3000), B))
+    S = mpc.Solver(cfg, 0)
+    args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.set_kernel(mpc.KERNEL_COOP)
+    coop = S.solve_batch_host(*args, weights=W)
+    S.set_kernel(mpc.KERNEL_LANE)
+    S.set_handoff(0)
+    lane = S.solve_batch_host(*args, weights=W)
+    S.set_handoff(8)
+    mig = S.solve_batch_host(*args, weights=W)
+    S.close()
+    for k in ("result", "traj_x", "status", "iters"):
+        assert np.array_equal(lane[k], mig[k]), k
+        assert np.array_equal(lane[k], coop[k]), k
+    assert (lane["status"] == 1).mean() > 0.95
+    # a few of them against the oracle with their own weights
+    for i in range(0, B, B // 12):
+        r = po.solve(po.make_config(dict(cd, weights=list(W[i]))), po.make_problem(b["state"][i], b["coeffs"][i], b["yaw_lo"][i], b["yaw_hi"][i]))
+        if r["status"] == 1 and lane["status"][i] == 1:
+            assert np.abs(lane["result"][i, :8] - r["result"][:8]).max() < ABS_TOL
+            assert lane["result"][i, 8] == pytest.approx(r["result"][8], rel=REL_TOL)
