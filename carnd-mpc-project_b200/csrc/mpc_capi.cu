@@ -42,6 +42,7 @@ struct mpc_handle {
   int kernel_kind;      // MPC_KERNEL_AUTO / WARP / LANE
   int lane_threads;     // threads per CTA of the lane kernel
   int lane_ctas_per_sm; // CTAs per SM of the lane kernel (0 = occupancy maximum)
+  bool one_shot;        // set by mpc_solve_one around its launch
   int handoff_iter;     // lane kernel parks problems still running after this many iterations for the coop kernel (0 = never)
   double *d_ckpt;       // migration records
   size_t cap_ckpt;      // records
@@ -404,7 +405,7 @@ static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = 0; kp.ckpt_count = h->d_counter + 1; kp.ckpt_next = h->d_counter + 2;
-  CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
+  if (kp.counter) CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
   mpc_coop_kernel<NS><<<(unsigned)grid, threads, smem, st>>>(kp);
   CK(cudaGetLastError());
   h->launches++;
@@ -465,6 +466,7 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
     return launch<32>(h, kp, (cudaStream_t)cuda_stream);
   }
   if (kind == MPC_KERNEL_COOP) {
+    if (h->one_shot) kp.counter = nullptr;   // mpc_solve_one: one group, no work queue
     if (c.N > 32) { snprintf(g_err, sizeof(g_err), "coop kernel handles N <= 32"); return MPC_EINVAL; }
     if (c.N <= 10) return launch_coop<10>(h, kp, (cudaStream_t)cuda_stream);
     if (c.N <= 20) return launch_coop<20>(h, kp, (cudaStream_t)cuda_stream);
@@ -530,8 +532,7 @@ extern "C" int mpc_solve_batch_host(mpc_handle *h, int B, const double *state, c
   return MPC_OK;
 }
 
-// One problem: the inputs travel in ONE host-to-device copy from a pinned staging block and the outputs
-// come back in two (doubles, ints) -- a single solve is latency-bound, every API call counts.
+// One problem, host pointers.
 extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs, double yaw_lo,
                              double yaw_hi, double *result, double *traj_x, double *traj_y, int *status,
                              int *iters) {
@@ -545,15 +546,16 @@ extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *c
   for (int k = 0; k < 6; k++) hp[k] = state[k];
   for (int k = 0; k < MPC_NCOEF; k++) hp[6 + k] = coeffs[k];
   hp[11] = yaw_lo; hp[12] = yaw_hi;
-  double *d_in = h->d_in, *d_out = h->d_out;   // with B = 1 the [k][B] arrays are contiguous
-  CK(cudaMemcpyAsync(d_in, hp, 13 * sizeof(double), cudaMemcpyHostToDevice, st));
-  rc = mpc_solve_batch(h, 1, d_in, d_in + 6, d_in + 11, d_in + 12, nullptr, nullptr, nullptr, d_out, d_out + 9,
-                       d_out + 9 + N, nullptr, h->d_iout, h->d_iout + 1, st);
-  if (rc) return rc;
+  // The kernel reads the inputs from and writes the outputs to the pinned staging block directly (unified
+  // virtual addressing makes cudaMallocHost memory device-accessible under the same pointer): one launch and
+  // one synchronisation, no copy calls -- a single solve is latency-bound and every API call counts.
   double *ho = hp + 16;
   int *hi = reinterpret_cast<int *>(hp + 16 + 9 + 2 * (size_t)N);
-  CK(cudaMemcpyAsync(ho, d_out, (9 + 2 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(hi, h->d_iout, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  h->one_shot = true;
+  rc = mpc_solve_batch(h, 1, hp, hp + 6, hp + 11, hp + 12, nullptr, nullptr, nullptr, ho, ho + 9, ho + 9 + N, nullptr, hi,
+                       hi + 1, st);
+  h->one_shot = false;
+  if (rc) return rc;
   CK(cudaStreamSynchronize(st));
   for (int k = 0; k < 9; k++) result[k] = ho[k];
   if (traj_x) for (int k = 0; k < N; k++) traj_x[k] = ho[9 + k];

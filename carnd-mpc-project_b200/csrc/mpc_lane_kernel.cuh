@@ -1511,10 +1511,15 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
   Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
   Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
   Z.lh_stale = false; Z.no_handoff = false;
+  int pass = 0;
   for (;;) {
     int nb = 0;
-    if (Z.g0 == 0) nb = atomicAdd(P.counter, 1);
-    nb = __shfl_sync(Z.gm, nb, 0, G);
+    if (P.counter) {
+      if (Z.g0 == 0) nb = atomicAdd(P.counter, 1);
+      nb = __shfl_sync(Z.gm, nb, 0, G);
+    } else {   // no work queue (single solves: saves the host a memset): one problem per group, one pass
+      nb = pass++ ? P.B : (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
+    }
     if (nb >= P.B) break;
     Z.init(P, nb);
     while (Z.mode != LM_FINISH) {
