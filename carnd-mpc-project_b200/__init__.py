@@ -33,7 +33,7 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
-           "mpc_rollout", "mpc_set_handoff", "mpc_set_dual_outputs"]
+           "mpc_rollout", "mpc_set_handoff", "mpc_set_dual_outputs", "mpc_config_from_cli"]
 
 
 class MpcError(RuntimeError):
@@ -104,6 +104,7 @@ def lib():
     L.mpc_config_defaults.argtypes = [cfgp]
     L.mpc_config_load_json.argtypes = [C.c_char_p, cfgp]
     L.mpc_config_parse_json.argtypes = [C.c_char_p, cfgp]
+    L.mpc_config_from_cli.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p, cfgp, C.c_char_p, C.c_int]
     L.mpc_create.argtypes = [cfgp, C.c_int, C.POINTER(vp)]
     L.mpc_destroy.argtypes = [vp]
     L.mpc_destroy.restype = None
@@ -156,6 +157,15 @@ def config_from_json_text(text):
     cfg = MpcConfig()
     _check(lib().mpc_config_parse_json(text.encode(), C.byref(cfg)), "mpc_config_parse_json")
     return cfg
+
+
+def config_from_cli(argv, config_dir):
+    """mpc_main.cpp's command line (without the program name) -> (MpcConfig, chosen config file)."""
+    cfg = MpcConfig()
+    arr = (C.c_char_p * max(len(argv), 1))(*[a.encode() for a in argv])
+    buf = C.create_string_buffer(1024)
+    _check(lib().mpc_config_from_cli(len(argv), arr, config_dir.encode(), C.byref(cfg), buf, 1024), "mpc_config_from_cli")
+    return cfg, buf.value.decode()
 
 
 def measure_fp64_peak(device=0):

@@ -229,6 +229,41 @@ extern "C" int mpc_config_load_json(const char *path, mpc_config *c) {
   return mpc_config_parse_json(text.c_str(), c);
 }
 
+// The command line of the reference's controller (src/mpc_main.cpp:55-79) and what it does to the loaded
+// configuration on connection (mpc_main.cpp:238-246).
+extern "C" int mpc_config_from_cli(int argc, const char *const *argv, const char *config_dir, mpc_config *cfg,
+                                   char *config_file_out, int config_file_cap) {
+  if (!cfg || argc < 0 || (argc > 0 && !argv)) return MPC_EINVAL;
+  std::string dir = config_dir ? config_dir : "..";
+  std::string file = dir + "/config-stable.json";          // mpc_main.cpp:47
+  double max_speed = -1;
+  int latency = -1;
+  for (int i = 0; i < argc; i++) {
+    const std::string a = argv[i] ? argv[i] : "";
+    if (a == "-config") {
+      if (++i >= argc) return MPC_EINVAL;
+      file = argv[i];
+    } else if (a == "-speed") {
+      if (++i >= argc || sscanf(argv[i], "%lf", &max_speed) != 1) return MPC_EINVAL;
+    } else if (a == "-latency") {
+      if (++i >= argc || sscanf(argv[i], "%d", &latency) != 1) return MPC_EINVAL;
+      if (!latency) file = dir + "/config-no-latency.json";
+    } else if (a == "-fast") {
+      file = dir + "/config-fast.json";
+    } else if (a == "-stable") {
+      file = dir + "/config-stable.json";
+    } else {
+      return MPC_EINVAL;                                   // "Unknown option", exit(-1) in the reference
+    }
+  }
+  if (config_file_out && config_file_cap > 0) snprintf(config_file_out, (size_t)config_file_cap, "%s", file.c_str());
+  int rc = mpc_config_load_json(file.c_str(), cfg);
+  if (rc) return rc;
+  if (latency >= 0) cfg->latency_ms = latency;             // Config::lookahead keeps the file's value, as in the reference
+  if (max_speed > 0) cfg->max_speed = mph2mps(max_speed);  // the speed tables are NOT rescaled (mpc_main.cpp:244-246)
+  return MPC_OK;
+}
+
 static int check_config(const mpc_config *c) {
   if (!c) return MPC_EINVAL;
   if (c->N < 2 || c->N > MPC_NMAX) return MPC_EINVAL;

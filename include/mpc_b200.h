@@ -91,6 +91,15 @@ int mpc_config_load_json(const char *path, mpc_config *cfg);
 /* same, from an in-memory JSON text */
 int mpc_config_parse_json(const char *text, mpc_config *cfg);
 
+/* The controller's command line (src/mpc_main.cpp:55-79: -config <file>, -speed <mph>, -latency <ms>, -fast,
+ * -stable; argv WITHOUT the program name) and its effect on the configuration at connection time
+ * (mpc_main.cpp:238-246): picks the config file (config_dir stands for the reference's "..", NULL = ".."),
+ * loads it, then overrides latency and max speed -- without rescaling the speed tables and without touching
+ * lookahead, exactly like the reference.  Unknown options and malformed numbers return MPC_EINVAL (the
+ * reference prints and exits).  config_file_out (or NULL) receives the chosen path. */
+int mpc_config_from_cli(int argc, const char *const *argv, const char *config_dir, mpc_config *cfg,
+                        char *config_file_out, int config_file_cap);
+
 /* Create a solver bound to CUDA device `device` (workspace, stream-ordered work queue counter).
  * Replaces `MPC::MPC()` (MPC.cpp:160-179): the Ipopt option string becomes max_iter / tol. */
 int mpc_create(const mpc_config *cfg, int device, mpc_handle **out);

@@ -105,3 +105,30 @@ def test_workload_generator_matches_scalar_preprocessing(mpc, po, stable_cd, ref
     big = mpc.workloads.batch_perturbed_states(4096, 0, stable_cd)
     assert 0.2 < (np.abs(big["state"][:, 4]) > 0.8).mean() < 0.5
     assert 0.3 < (np.abs(big["state"][:, 5]) > 0.1).mean() < 0.55
+
+
+def test_command_line_like_mpc_main(mpc, refdata, tmp_path):
+    """src/mpc_main.cpp:55-79, 238-246: option parsing, config-file choice, post-load overrides."""
+    for name in refdata["configs"]:
+        (tmp_path / ("config-%s.json" % name)).write_text(json.dumps(refdata["configs"][name]))
+    d = str(tmp_path)
+    cfg, f = mpc.config_from_cli([], d)
+    assert f.endswith("config-stable.json") and cfg.max_speed == pytest.approx(120 * 1609.34 / 3600)
+    cfg, f = mpc.config_from_cli(["-fast"], d)
+    assert f.endswith("config-fast.json") and cfg.max_speed == pytest.approx(145 * 1609.34 / 3600)
+    cfg, f = mpc.config_from_cli(["-latency", "0"], d)
+    assert f.endswith("config-no-latency.json") and cfg.latency_ms == 0
+    cfg, f = mpc.config_from_cli(["-latency", "0", "-fast"], d)           # a later option overrides the file choice
+    assert f.endswith("config-fast.json") and cfg.latency_ms == 0
+    assert cfg.lookahead == pytest.approx(0.1)                             # lookahead keeps the file's value (reference quirk)
+    base = mpc.config_from_json_text(json.dumps(refdata["configs"]["stable"]))
+    cfg, f = mpc.config_from_cli(["-speed", "60", "-latency", "50"], d)
+    assert cfg.latency_ms == 50 and cfg.max_speed == pytest.approx(60 * 1609.34 / 3600)
+    assert list(cfg.steer_speeds) == list(base.steer_speeds)               # tables are not rescaled
+    cfg, f = mpc.config_from_cli(["-config", str(tmp_path / "config-fast.json")], d)
+    assert f.endswith("config-fast.json")
+    for bad in (["-bogus"], ["-speed", "fast"], ["-latency"], ["-config"]):
+        with pytest.raises(mpc.MpcError, match="MPC_EINVAL"):
+            mpc.config_from_cli(bad, d)
+    with pytest.raises(mpc.MpcError, match="MPC_EIO"):
+        mpc.config_from_cli(["-config", str(tmp_path / "missing.json")], d)
