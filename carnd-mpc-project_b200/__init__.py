@@ -33,7 +33,8 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
-           "mpc_rollout", "mpc_set_handoff", "mpc_set_dual_outputs", "mpc_config_from_cli"]
+           "mpc_rollout", "mpc_set_handoff", "mpc_set_dual_outputs", "mpc_config_from_cli",
+           "mpc_telemetry_parse", "mpc_telemetry_step"]
 
 
 class MpcError(RuntimeError):
@@ -68,6 +69,12 @@ class MpcConfig(C.Structure):
             "yaw_changes": list(self.yaw_changes[: self.n_yaw_changes]),
             "yaw_change_speeds": list(self.yaw_change_speeds[: self.n_yaw_change_speeds]),
         }
+
+
+class MpcTelemetry(C.Structure):
+    """``mpc_telemetry`` of include/mpc_b200.h."""
+    _fields_ = [("kind", C.c_int), ("npts", C.c_int), ("x", C.c_double), ("y", C.c_double), ("psi", C.c_double),
+                ("speed_mph", C.c_double), ("steering_angle", C.c_double), ("ptsx", C.c_double * 16), ("ptsy", C.c_double * 16)]
 
 
 class MpcRunAux(C.Structure):
@@ -112,6 +119,8 @@ def lib():
     L.mpc_set_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_set_handoff.argtypes = [vp, C.c_int]
     L.mpc_set_dual_outputs.argtypes = [vp, vp, vp, vp]
+    L.mpc_telemetry_parse.argtypes = [C.c_char_p, C.POINTER(MpcTelemetry)]
+    L.mpc_telemetry_step.argtypes = [vp, C.c_char_p, dp, C.c_double, C.c_int, C.c_char_p, C.c_int]
     L.mpc_solve_batch.argtypes = [vp, C.c_int] + [vp] * 13 + [vp]
     L.mpc_solve_batch_host.argtypes = [vp, C.c_int] + [vp] * 13
     L.mpc_solve_one.argtypes = [vp, dp, dp, C.c_double, C.c_double, dp, dp, dp, ip, ip]
@@ -166,6 +175,13 @@ def config_from_cli(argv, config_dir):
     buf = C.create_string_buffer(1024)
     _check(lib().mpc_config_from_cli(len(argv), arr, config_dir.encode(), C.byref(cfg), buf, 1024), "mpc_config_from_cli")
     return cfg, buf.value.decode()
+
+
+def telemetry_parse(msg):
+    """hasData + parse of one SocketIO text (mpc_main.cpp:26-36, 92-124) -> MpcTelemetry."""
+    t = MpcTelemetry()
+    _check(lib().mpc_telemetry_parse(msg.encode(), C.byref(t)), "mpc_telemetry_parse")
+    return t
 
 
 def measure_fp64_peak(device=0):
@@ -325,6 +341,14 @@ class Solver:
         _check(lib().mpc_rollout(self._h, V, T, _ptr(track_x), _ptr(track_y), int(track_x.numel()), _ptr(veh),
                                  _ptr(seg), _ptr(pending), float(dt_ctrl), float(tau_solve), _ptr(rec), stream),
                "mpc_rollout")
+
+    def telemetry_step(self, msg, throttle_prev, tau_solve=0.0, with_trajectory=False):
+        """One simulator message through the controller -> (reply text, new throttle_prev)."""
+        thr = C.c_double(throttle_prev)
+        buf = C.create_string_buffer(8192)
+        _check(lib().mpc_telemetry_step(self._h, msg.encode(), C.byref(thr), float(tau_solve), int(with_trajectory), buf, 8192),
+               "mpc_telemetry_step")
+        return buf.value.decode(), thr.value
 
     def solve_one(self, state, coeffs, yaw_lo, yaw_hi):
         N = self.cfg.N

@@ -18,6 +18,7 @@
 #include "mpc_kernel.cuh"
 #include "mpc_lane_kernel.cuh"
 #include "mpc_rollout.cuh"
+#include "mpc_run_logic.h"
 
 using namespace mpcb200;
 
@@ -597,6 +598,81 @@ extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *c
   if (traj_y) for (int k = 0; k < N; k++) traj_y[k] = ho[9 + N + k];
   if (status) *status = hi[0];
   if (iters) *iters = hi[1];
+  return MPC_OK;
+}
+
+// ---- the simulator protocol without the socket: src/mpc_main.cpp:26-36 (hasData), 81-222 (onMessage) ----------
+extern "C" int mpc_telemetry_parse(const char *msg, mpc_telemetry *out) {
+  if (!msg || !out) return MPC_EINVAL;
+  memset(out, 0, sizeof(*out));
+  const std::string sdata(msg);
+  if (!(sdata.size() > 2 && sdata[0] == '4' && sdata[1] == '2')) { out->kind = MPC_MSG_IGNORED; return MPC_OK; }
+  // hasData(): "null" anywhere means no data; otherwise from the first '[' to the last "}]"
+  std::string s;
+  const size_t b1 = sdata.find_first_of("["), b2 = sdata.rfind("}]");
+  if (sdata.find("null") == std::string::npos && b1 != std::string::npos && b2 != std::string::npos) s = sdata.substr(b1, b2 - b1 + 2);
+  if (s.empty()) { out->kind = MPC_MSG_MANUAL; return MPC_OK; }
+  JParser jp(s.c_str());
+  JVal j = jp.val();
+  if (!jp.ok || j.t != JVal::ARR || j.arr.size() < 2 || j.arr[0].t != JVal::STR) return MPC_EPARSE;
+  if (j.arr[0].str != "telemetry") { out->kind = MPC_MSG_IGNORED; return MPC_OK; }
+  JVal &d = j.arr[1];
+  if (d.t != JVal::OBJ) return MPC_EPARSE;
+  auto num = [&](const char *k, double &v) { if (!d.obj.count(k) || d.obj[k].t != JVal::NUM) return false; v = d.obj[k].num; return true; };
+  if (!num("x", out->x) || !num("y", out->y) || !num("psi", out->psi) || !num("speed", out->speed_mph) ||
+      !num("steering_angle", out->steering_angle)) return MPC_EPARSE;
+  if (!d.obj.count("ptsx") || !d.obj.count("ptsy") || d.obj["ptsx"].t != JVal::ARR || d.obj["ptsy"].t != JVal::ARR) return MPC_EPARSE;
+  const size_t n = d.obj["ptsx"].arr.size();
+  if (n != d.obj["ptsy"].arr.size() || n < 3 || n > MPC_MAX_WAYPOINTS) return MPC_EPARSE;
+  for (size_t i = 0; i < n; i++) { out->ptsx[i] = d.obj["ptsx"].arr[i].num; out->ptsy[i] = d.obj["ptsy"].arr[i].num; }
+  out->npts = (int)n;
+  out->kind = MPC_MSG_TELEMETRY;
+  return MPC_OK;
+}
+
+extern "C" int mpc_telemetry_step(mpc_handle *h, const char *msg, double *throttle_prev, double tau_solve,
+                                  int with_trajectory, char *reply, int reply_cap) {
+  if (!h || !msg || !throttle_prev || !reply || reply_cap < 32) return MPC_EINVAL;
+  reply[0] = 0;
+  mpc_telemetry t;
+  int rc = mpc_telemetry_parse(msg, &t);
+  if (rc) return rc;
+  if (t.kind == MPC_MSG_IGNORED) return MPC_OK;
+  if (t.kind == MPC_MSG_MANUAL) { snprintf(reply, (size_t)reply_cap, "42[\"manual\",{}]"); return MPC_OK; }
+  const mpc_config &c = h->cfg;
+  double x = t.x, y = t.y;
+  double psi = mpcrun::normalize_angle(t.psi);                  // mpc_main.cpp:127
+  double v = mph2mps(t.speed_mph);                              // :129
+  const double steer = -t.steering_angle;                       // :131
+  const double accel_est = (*throttle_prev - v / 50.0) * 6;     // :156
+  if (c.latency_ms) mpcrun::vehicle_move(&x, &y, &psi, &v, steer, accel_est, c.Lf, c.lookahead + tau_solve);   // :157-159
+  const double pose[4] = {x, y, psi, v};
+  double state[6], coeffs[MPC_NCOEF], ylo, yhi, res[9], out8[8], tx[MPC_NMAX], ty[MPC_NMAX];
+  mpc_run_aux aux;
+  rc = mpc_run_prepare(&c, pose, steer, t.ptsx, t.ptsy, t.npts, state, coeffs, &ylo, &yhi, &aux);
+  if (rc) return rc;
+  int status = 0, iters = 0;
+  rc = mpc_solve_one(h, state, coeffs, ylo, yhi, res, tx, ty, &status, &iters);
+  if (rc) return rc;
+  if (status != MPC_STATUS_SUCCESS) printf("Ipopt failed with %d\n", status);   // MPC.cpp:301
+  mpc_run_finish(&c, &aux, v, res, out8);
+  const double steer_value = -out8[4];                          // :172
+  const double throttle = mpcrun::compute_throttle(out8[5], out8[3], c.max_accel, c.max_decel, c.max_speed);   // :174
+  *throttle_prev = throttle;
+  // the reply object, keys in nlohmann's (sorted) order; without PLOT_TRAJECTORY the reference assigns NULL,
+  // which nlohmann stores as the integer 0 (mpc_main.cpp:189-199)
+  std::string js = "{";
+  auto arr = [](const double *a, int n) { std::string s = "["; char b[40]; for (int i = 0; i < n; i++) { snprintf(b, sizeof(b), "%s%.15g", i ? "," : "", a[i]); s += b; } return s + "]"; };
+  char b[64];
+  js += "\"mpc_x\":" + (with_trajectory ? arr(tx, c.N) : std::string("0"));
+  js += ",\"mpc_y\":" + (with_trajectory ? arr(ty, c.N) : std::string("0"));
+  js += ",\"next_x\":" + (with_trajectory ? arr(t.ptsx, t.npts) : std::string("0"));
+  js += ",\"next_y\":" + (with_trajectory ? arr(t.ptsy, t.npts) : std::string("0"));
+  snprintf(b, sizeof(b), ",\"steering_angle\":%.15g", steer_value); js += b;
+  snprintf(b, sizeof(b), ",\"throttle\":%.15g}", throttle); js += b;
+  const std::string out = "42[\"steer\"," + js + "]";
+  if ((int)out.size() + 1 > reply_cap) return MPC_EINVAL;
+  memcpy(reply, out.c_str(), out.size() + 1);
   return MPC_OK;
 }
 

@@ -197,6 +197,28 @@ int mpc_run_finish(const mpc_config *cfg, const mpc_run_aux *aux, double v, cons
 double mpc_compute_throttle(const mpc_config *cfg, double accel, double target);
 void mpc_vehicle_move(double *pose4, double steering, double accel, double length, double dt);
 
+/* ---- the simulator protocol without the socket (src/mpc_main.cpp:26-36, 81-222; fields: DATA.md) ----
+ * uWebSockets and the Unity simulator are not part of this library; these two calls are the message handler's
+ * logic, so that recorded SocketIO text can be replayed through the controller. */
+#define MPC_MSG_IGNORED 0     /* not a "42" event, or an event other than "telemetry": nothing is sent */
+#define MPC_MSG_MANUAL 1      /* "42" event without data: the reply is 42["manual",{}] */
+#define MPC_MSG_TELEMETRY 2
+typedef struct mpc_telemetry {
+  int kind, npts;
+  double x, y, psi, speed_mph, steering_angle;     /* as sent: psi unnormalised, speed in mph, simulator steering sign */
+  double ptsx[MPC_MAX_WAYPOINTS], ptsy[MPC_MAX_WAYPOINTS];
+} mpc_telemetry;
+/* hasData() + json::parse + field extraction (mpc_main.cpp:26-36, 92-124). Pure; no device needed. */
+int mpc_telemetry_parse(const char *msg, mpc_telemetry *out);
+/* One message through the controller (mpc_main.cpp:99-214): unit/sign conversion, latency compensation with the
+ * fixed solve-time estimate tau_solve (the reference averages its last five measured solve times), MPC::run,
+ * throttle map; writes the text the reference would send into reply ("" when nothing is sent).  *throttle_prev is
+ * the reference's static throttle_value: the previous reply's throttle, updated here.  with_trajectory = the
+ * PLOT_TRAJECTORY build (mpc_x/mpc_y/next_x/next_y arrays); otherwise they are 0, as the reference's NULL
+ * assignments serialise. */
+int mpc_telemetry_step(mpc_handle *h, const char *msg, double *throttle_prev, double tau_solve,
+                       int with_trajectory, char *reply, int reply_cap);
+
 /* MPC::run for a batch, entirely on the device (DEVICE pointers, async on cuda_stream): one kernel does the
  * pre-processing of mpc_run_prepare for every vehicle, the solve follows, one kernel does mpc_run_finish.
  *   pose [4][B] x, y, psi, v;  steering [B] or NULL;  ptsx, ptsy [npts][B] global waypoints (3..16)

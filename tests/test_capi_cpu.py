@@ -132,3 +132,18 @@ def test_command_line_like_mpc_main(mpc, refdata, tmp_path):
             mpc.config_from_cli(bad, d)
     with pytest.raises(mpc.MpcError, match="MPC_EIO"):
         mpc.config_from_cli(["-config", str(tmp_path / "missing.json")], d)
+
+
+def test_telemetry_message_framing(mpc):
+    """hasData() and event dispatch of src/mpc_main.cpp:26-36, 81-97, 215-219."""
+    body = {"ptsx": [1.0, 2.0, 3.5, 5.0, 7.0, 9.0], "ptsy": [0.5, 0.25, 0.0, -0.5, -1.0, -2.0], "psi_unity": 4.1, "psi": 3.7,
+            "x": -40.62, "y": 108.73, "steering_angle": -0.04, "throttle": 0.3, "speed": 42.5}
+    t = mpc.telemetry_parse('42["telemetry",' + json.dumps(body) + ']')
+    assert t.kind == 2 and t.npts == 6
+    assert (t.x, t.y, t.psi, t.speed_mph, t.steering_angle) == (-40.62, 108.73, 3.7, 42.5, -0.04)
+    assert list(t.ptsx[:6]) == body["ptsx"] and list(t.ptsy[:6]) == body["ptsy"]
+    assert mpc.telemetry_parse('42["telemetry",null]').kind == 1          # "null" anywhere -> manual driving
+    assert mpc.telemetry_parse('42').kind == 0 and mpc.telemetry_parse('2probe').kind == 0
+    assert mpc.telemetry_parse('42["steer",{"a":1}]').kind == 0           # other events are ignored
+    with pytest.raises(mpc.MpcError, match="MPC_EPARSE"):
+        mpc.telemetry_parse('42["telemetry",{"x":1}]')

@@ -88,3 +88,58 @@ def test_rollout_matches_cpu_restatement(mpc, po, refdata, name, tau):
         assert seg[i] == s_ref
     # the vehicles actually drive: they moved ~ v * T * dt along the track and stayed near the centre line
     assert (np.hypot(veh[0] - veh0[0], veh[1] - veh0[1]) > 10).all()
+
+
+def test_telemetry_replay_matches_restated_handler(mpc, po, refdata):
+    """Recorded-style SocketIO text through mpc_telemetry_step == the message handler of mpc_main.cpp:99-214
+    restated on the CPU (unit/sign conversions, latency move, MPC::run, throttle), several messages in a row so
+    that the previous throttle feeds the next latency compensation."""
+    import math
+    js = refdata["configs"]["fast"]
+    cfg = mpc.config_from_json_text(json.dumps(js))
+    cd = po.load_config_dict(js)
+    ocfg = po.make_config(cd)
+    wx, wy = np.array(refdata["waypoints"]["x"]), np.array(refdata["waypoints"]["y"])
+    b = mpc.workloads.batch_perturbed_states(4, 9, cd)
+    S = mpc.Solver(cfg, 0)
+    assert S.telemetry_step('42["telemetry",null]', 0.0)[0] == '42["manual",{}]'
+    assert S.telemetry_step("3", 0.0)[0] == ""
+    tau = 0.02
+    for i in range(4):
+        thr_prev = 0.0
+        px, py, psi, v = b["px"][i], b["py"][i], b["psi"][i] + 2 * math.pi, float(np.clip(b["v"][i], 8, 30))
+        seg = int(b["segment"][i])
+        steer_sim = 0.0
+        for step in range(3):
+            win = [(seg + k) % len(wx) for k in range(6)]
+            body = {"ptsx": wx[win].tolist(), "ptsy": wy[win].tolist(), "x": px, "y": py, "psi": psi, "psi_unity": 0.0,
+                    "speed": v * 3600.0 / 1609.34, "steering_angle": steer_sim, "throttle": thr_prev}
+            reply, thr_new = S.telemetry_step('42["telemetry",' + json.dumps(body) + ']', thr_prev, tau, with_trajectory=True)
+            assert reply.startswith('42["steer",{') and reply.endswith("}]")
+            got = json.loads(reply[len('42["steer",'):-1])
+            # restated handler
+            vv = (v * 3600.0 / 1609.34) * 1609.34 / 3600.0
+            p = clr.normalize_angle(psi)
+            st = -steer_sim
+            x2, y2, p2, v2 = clr.vehicle_move(px, py, p, vv, st, (thr_prev - vv / 50.0) * 6, cd["Lf"], cd["lookahead"] + tau)
+            state, coeffs, ylo, yhi, ex = po.preprocess(cd, (x2, y2, p2, v2), wx[win], wy[win])
+            r = po.solve(ocfg, po.make_problem(state, coeffs, ylo, yhi))
+            assert r["status"] == 1
+            myc = ex["myc"]
+            target = clr.table_limit(cd["steers"], cd["steer_speeds"], st, clr.table_limit(cd["yaw_changes"], cd["yaw_change_speeds"], myc, cd["max_speed"]))
+            sa = r["result"][6] + (cd["steer_adjust_ratio"] * myc if abs(myc) > cd["steer_adjust_thresh"] else 0.0)
+            sv = min(max(sa / cd["max_steering"], -1.0), 1.0)
+            accel = min(r["result"][7], target - v2)
+            thr = clr.compute_throttle(cd, accel, r["result"][3])
+            assert got["steering_angle"] == pytest.approx(-sv, abs=1e-6)
+            assert got["throttle"] == pytest.approx(thr, abs=1e-6) and thr_new == pytest.approx(thr, abs=1e-6)
+            assert np.abs(np.array(got["mpc_x"]) - r["z"][:cd["N"]]).max() < ABS_TOL
+            assert np.allclose(got["next_x"], ex["tx"], atol=1e-9)
+            # and without trajectories the reference's NULLs serialise as 0
+            reply0, _ = S.telemetry_step('42["telemetry",' + json.dumps(body) + ']', thr_prev, tau)
+            assert '"mpc_x":0,"mpc_y":0,"next_x":0,"next_y":0' in reply0
+            # advance the "simulator" a little for the next message
+            px, py, psi, v = clr.vehicle_move(px, py, psi, v, -got["steering_angle"] * cd["max_steering"], (thr - v / 50.0) * 6, cd["Lf"], 0.1)
+            steer_sim = got["steering_angle"] * cd["max_steering"]
+            thr_prev = thr_new
+    S.close()
