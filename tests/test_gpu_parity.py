@@ -390,3 +390,21 @@ def test_migration_longer_horizons(mpc, refdata, po, N, dt):
         if r["status"] == 1 and lane["status"][i] == 1:
             assert np.abs(lane["result"][i, :8] - r["result"][:8]).max() < ABS_TOL
             assert lane["result"][i, 8] == pytest.approx(r["result"][8], rel=REL_TOL)
+
+
+def test_pathological_inputs_terminate(solver):
+    """NaN / infinite inputs, an empty yaw interval and a huge cross-track error must end with a non-success
+    status (the reference prints "Ipopt failed with <int>" and carries on, MPC.cpp:295-303) -- never hang, and
+    never disturb the healthy problems solved in the same launch."""
+    good = [0, 0, 0.0, 20.0, 0.3, 0.02]
+    st = np.array([good, [0, 0, 0.0, np.nan, 0.1, 0.0], [0, 0, 0.0, 20.0, np.inf, 0.0], good, good, [0, 0, 0, 20.0, 1e6, 0.0], good])
+    co = np.tile(np.array([0.3, -0.02, 0.001, 0.0, 0.0]), (7, 1))
+    co[4, 2] = np.nan
+    ylo = np.array([-0.1, -0.1, -0.1, 0.2, -0.1, -0.1, -0.1])
+    yhi = np.array([0.4, 0.4, 0.4, -0.2, 0.4, 0.4, 0.4])          # problem 3: empty interval
+    r = solver.solve_batch_host(st, co, ylo, yhi)
+    assert r["status"][0] == 1 and r["status"][6] == 1
+    assert np.array_equal(r["result"][0], r["result"][6])
+    for i in (1, 2, 3, 4):
+        assert r["status"][i] != 1, (i, r["status"][i])
+    assert r["iters"].max() <= 3000
