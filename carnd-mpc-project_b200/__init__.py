@@ -17,11 +17,11 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+LIB_PATH = os.environ.get("MPC_B200_LIB") or os.path.join(_HERE, "libmpc_b200.so")   # override: A/B builds of the kernels
 CSRC = os.path.join(_HERE, "csrc")
 
 NCOEF, NTAB, NWEIGHTS, NMAX = 5, 16, 12, 64
-KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE, KERNEL_COOP = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE, KERNEL_COOP, KERNEL_SOLO = 0, 1, 2, 3, 4
 LANE_MIN_BATCH = 12288
 
 STATUS_SUCCESS = 1
@@ -33,7 +33,7 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
-           "mpc_rollout", "mpc_set_handoff", "mpc_set_dual_outputs", "mpc_config_from_cli",
+           "mpc_rollout", "mpc_set_handoff", "mpc_set_tail", "mpc_set_dual_outputs", "mpc_config_from_cli",
            "mpc_telemetry_parse", "mpc_telemetry_step"]
 
 
@@ -118,6 +118,7 @@ def lib():
     L.mpc_set_config.argtypes = [vp, cfgp]
     L.mpc_set_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_set_handoff.argtypes = [vp, C.c_int]
+    L.mpc_set_tail.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_set_dual_outputs.argtypes = [vp, vp, vp, vp]
     L.mpc_telemetry_parse.argtypes = [C.c_char_p, C.POINTER(MpcTelemetry)]
     L.mpc_telemetry_step.argtypes = [vp, C.c_char_p, dp, C.c_double, C.c_int, C.c_char_p, C.c_int]
@@ -266,6 +267,10 @@ class Solver:
     def set_kernel(self, kind=KERNEL_AUTO, lane_threads=0, lane_ctas_per_sm=0):
         """Pick the kernel (auto / one problem per warp / one problem per lane) and the lane grid."""
         _check(lib().mpc_set_kernel(self._h, kind, lane_threads, lane_ctas_per_sm), "mpc_set_kernel")
+
+    def set_tail(self, park_lanes, resume_launches, sort_ragged=True):
+        """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches, ragged sort."""
+        _check(lib().mpc_set_tail(self._h, int(park_lanes), int(resume_launches), int(bool(sort_ragged))), "mpc_set_tail")
 
     def set_handoff(self, iterations):
         """Iteration count after which the lane kernel hands a problem to the coop kernel (0 = never)."""

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,10 @@ static int cuda_fail(cudaError_t e, const char *what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// device counters of a handle: [0] work queue, [1 + 2k] records parked by launch k of a lane-kernel chain,
+// [2 + 2k] cursor of the coop kernel over them, [MPC_HIST0 ..] horizon histogram of a ragged batch
+enum { MPC_MAX_PHASES = 6, MPC_HIST0 = 20, MPC_NCOUNTER = MPC_HIST0 + MPC_NMAX + 1 };
+
 struct mpc_handle {
   mpc_config cfg;
   int device;
@@ -44,10 +49,15 @@ struct mpc_handle {
   int lane_threads;     // threads per CTA of the lane kernel
   int lane_ctas_per_sm; // CTAs per SM of the lane kernel (0 = occupancy maximum)
   bool one_shot;        // set by mpc_solve_one around its launch
-  int handoff_iter;     // lane kernel parks problems still running after this many iterations for the coop kernel (0 = never)
-  double *d_ckpt;       // migration records
-  size_t cap_ckpt;      // records
+  int handoff_iter;     // rule 1: lane kernel parks problems still running after this many iterations (0 = never, the default)
+  int park_lanes;       // tail packing: a warp with at most this many problems left parks them once the queue is empty (0 = off)
+  int resume_phases;    // lane-kernel resume launches between the main launch and the final one
+  double *d_ckpt;       // migration records, two buffers of cap_ckpt records (each launch of a chain reads one, writes the other)
+  size_t cap_ckpt;      // records per buffer
   int ckpt_ns;
+  bool sort_ragged;     // ragged batches (N_per given): hand the problems out longest horizon first
+  int *d_perm;          // ragged batches: problem order of the work queue (longest horizon first)
+  size_t cap_perm;
   double *dual_lam, *dual_zl, *dual_zu;   // caller's device buffers for the multipliers (or NULL)
   // staging buffers for the host-pointer entry points (grown on demand)
   double *d_in, *d_out;
@@ -295,12 +305,15 @@ extern "C" int mpc_create(const mpc_config *cfg, int device, mpc_handle **out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
-  CK(cudaMalloc(&h->d_counter, 4 * sizeof(int)));   // work-queue counter, records written, records taken
+  CK(cudaMalloc(&h->d_counter, MPC_NCOUNTER * sizeof(int)));   // work-queue counter, per launch of a chain: records written / taken; horizon histogram
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->kernel_kind = MPC_KERNEL_AUTO;
   h->lane_threads = 0;
   h->lane_ctas_per_sm = 0;
-  h->handoff_iter = 13;
+  h->handoff_iter = 0;
+  h->sort_ragged = true;
+  h->park_lanes = MPC_PARK_LANES_DEFAULT;
+  h->resume_phases = MPC_RESUME_PHASES_DEFAULT;
   *out = h;
   return MPC_OK;
 }
@@ -310,6 +323,7 @@ extern "C" void mpc_destroy(mpc_handle *h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_counter);
   cudaFree(h->d_ckpt);
+  cudaFree(h->d_perm);
   cudaFree(h->d_in);
   cudaFree(h->d_out);
   cudaFree(h->d_iout);
@@ -360,11 +374,69 @@ static int launch(mpc_handle *h, KParams &kp, cudaStream_t st) {
 // trip in step), sized so that every lane gets the same number of problems: with
 // r = ceil(B / (SMs * 256)) problems per lane, ceil(B / (SMs * r)) lanes per SM -- otherwise the lanes
 // without a last problem idle through the final round while their warps still issue every instruction.
+// ---- ragged batches: hand the problems out longest horizon first.  Lanes of a warp fetch neighbouring queue
+// entries, so they hold horizons of similar length (every sweep of a warp runs to the longest N among its lanes),
+// and the longest problems start first.  Counting sort by N: histogram, descending exclusive scan, scatter.
+__global__ void mpc_horizon_hist_kernel(const int *N_pp, int B, int *hist) {
+  __shared__ int sh[MPC_NMAX + 1];
+  for (int k = threadIdx.x; k <= MPC_NMAX; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    int n = N_pp[b];
+    n = n < 0 ? 0 : (n > MPC_NMAX ? MPC_NMAX : n);
+    atomicAdd(&sh[n], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= MPC_NMAX; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+__global__ void mpc_horizon_scan_kernel(int *hist) {
+  int acc = 0;
+  for (int k = MPC_NMAX; k >= 0; k--) { const int c = hist[k]; hist[k] = acc; acc += c; }
+}
+__global__ void mpc_horizon_scatter_kernel(const int *N_pp, int B, int *cursor, int *perm) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    int n = N_pp[b];
+    n = n < 0 ? 0 : (n > MPC_NMAX ? MPC_NMAX : n);
+    perm[atomicAdd(&cursor[n], 1)] = b;
+  }
+}
+
+// The solo kernel: one problem per lane, rows in shared memory, one-warp CTAs (mpc_lane_kernel.cuh).
+template <int NS, bool RESUME>
+static int launch_solo(mpc_handle *h, KParams &kp, cudaStream_t st, long long nmax) {
+  const size_t per = (size_t)NS * ST_ROW * sizeof(double);
+  int L = (int)((45 * 1024) / per);
+  if (L < 1) L = 1;
+  if (L > 32) L = 32;
+  const size_t smem = per * L;
+  static thread_local int cached_dev = -1;
+  if (cached_dev != h->device) {
+    CK(cudaFuncSetAttribute(mpc_solo_kernel<NS, RESUME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cached_dev = h->device;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_solo_kernel<NS, RESUME>, 32, smem));
+  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "solo kernel does not fit on an SM (smem %zu)", smem); return MPC_ECUDA; }
+  long long grid = (long long)h->sm_count * per_sm, want = (nmax + L - 1) / L;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  mpc_solo_kernel<NS, RESUME><<<(unsigned)grid, 32, smem, st>>>(kp, L);
+  CK(cudaGetLastError());
+  h->launches++;
+  return MPC_OK;
+}
+
+// The lane kernel and the launches that finish its tail, all on one stream with no host round trip:
+//   main launch            fresh problems from the work queue; parks by rule 1 (iterations) and rule 2 (sparse warp)
+//   resume launches        the parked problems, 32 to a warp; park by rule 2 into the other buffer
+//   final launch           N <= 32: the coop kernel (one problem per lane group, rows in shared memory);
+//                          longer horizons: the solo kernel (one problem per lane, rows in shared memory)
 template <int NS, int MINB>
 static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   static thread_local int cached_dev = -1;
   if (cached_dev != h->device) {
-    CK(cudaFuncSetAttribute(mpc_lane_kernel<NS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    CK(cudaFuncSetAttribute(mpc_lane_kernel<NS, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    CK(cudaFuncSetAttribute(mpc_lane_kernel<NS, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     cached_dev = h->device;
   }
   int threads = h->lane_threads;           // 0 = automatic
@@ -380,28 +452,61 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   long long grid = (long long)h->sm_count * (h->lane_ctas_per_sm > 0 ? h->lane_ctas_per_sm : 1);
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  // migration of the long runners to the coop kernel (same NS => same record layout); N <= 32 only
-  // (measured, profiles/r01_handoff_sweep.txt: 13% on the 64K batch; beyond a few rounds per lane the tail no
-  // longer matters and the coop kernel's lower throughput costs more than it saves)
-  const bool handoff = h->handoff_iter > 0 && NS <= 32 && kp.B >= MPC_LANE_MIN_BATCH && kp.B <= MPC_HANDOFF_MAX_BATCH;
-  kp.ckpt = nullptr; kp.ckpt_count = h->d_counter + 1; kp.ckpt_next = h->d_counter + 2; kp.ckpt_cap = 0;
-  kp.handoff_iter = h->handoff_iter;
-  if (handoff) {
-    size_t cap = (size_t)kp.B / 8;
-    if (cap > 32768) cap = 32768;
-    if (!h->d_ckpt || h->cap_ckpt < cap || h->ckpt_ns != NS) {
-      cudaFree(h->d_ckpt);
-      h->d_ckpt = nullptr;
-      CK(cudaMalloc(&h->d_ckpt, cap * Lane<NS, false>::CK_SIZE * sizeof(double)));
-      h->cap_ckpt = cap; h->ckpt_ns = NS;
-    }
-    kp.ckpt = h->d_ckpt; kp.ckpt_cap = (int)cap;
+  // rule 1 (off by default; profiles/r01_handoff_sweep.txt and r01_tail_packing_sweep.txt: 13% on the 64K batch of
+  // config-stable at 13 iterations, but a loss on workloads with a wider spread of iteration counts, and nothing on
+  // top of rule 2): needs the coop kernel
+  const bool rule1 = h->handoff_iter > 0 && NS <= 32 && kp.B >= MPC_LANE_MIN_BATCH && kp.B <= MPC_HANDOFF_MAX_BATCH;
+  const int park = kp.B >= MPC_TAIL_MIN_BATCH ? h->park_lanes : 0;
+  const int phases = park > 0 ? h->resume_phases : 0;
+  int *cnt = h->d_counter + 1;   // [2k] records written by launch k of the chain, [2k + 1] cursor of the coop kernel
+  kp.ckpt = nullptr; kp.ckpt_in = nullptr; kp.ckpt_cap = 0; kp.park_lanes = 0; kp.handoff_iter = INT_MAX;
+  kp.ckpt_count = cnt; kp.ckpt_next = cnt + 1; kp.ckpt_in_count = cnt;
+  CK(cudaMemsetAsync(kp.counter, 0, MPC_HIST0 * sizeof(int), st));
+  if (!rule1 && park <= 0) {
+    mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
+    CK(cudaGetLastError());
+    h->launches++;
+    return MPC_OK;
   }
-  CK(cudaMemsetAsync(kp.counter, 0, 3 * sizeof(int), st));
-  mpc_lane_kernel<NS, MINB><<<(unsigned)grid, threads, 0, st>>>(kp);
+  const size_t rec = Lane<NS, false>::CK_SIZE;
+  size_t cap = (size_t)kp.B / 8;
+  const size_t sparse = (size_t)grid * threads * (park > 0 ? park : 0) / 32 + 1024;
+  if (cap < sparse) cap = sparse;
+  if (cap > 32768) cap = 32768;
+  if (cap > (size_t)kp.B) cap = kp.B;
+  if (!h->d_ckpt || h->cap_ckpt < cap || h->ckpt_ns != NS) {
+    cudaFree(h->d_ckpt);
+    h->d_ckpt = nullptr;
+    CK(cudaMalloc(&h->d_ckpt, 2 * cap * rec * sizeof(double)));
+    h->cap_ckpt = cap; h->ckpt_ns = NS;
+  }
+  double *buf[2] = {h->d_ckpt, h->d_ckpt + h->cap_ckpt * rec};
+  kp.ckpt_cap = (int)cap;
+  kp.ckpt = buf[0]; kp.ckpt_count = cnt;
+  kp.park_lanes = park; kp.handoff_iter = rule1 ? h->handoff_iter : INT_MAX;
+  mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
   CK(cudaGetLastError());
   h->launches++;
-  if (handoff) {
+  // resume launches: enough lanes for a full buffer in one pass, dealt over all SMs
+  int rthreads = (int)(((cap + h->sm_count - 1) / h->sm_count + 31) / 32) * 32;
+  if (rthreads > 256) rthreads = 256;
+  long long rgrid = ((long long)cap + rthreads - 1) / rthreads;
+  if (rgrid > h->sm_count) rgrid = h->sm_count;
+  kp.handoff_iter = INT_MAX;
+  kp.perm = nullptr;
+  for (int k = 1; k <= phases; k++) {
+    kp.ckpt_in = buf[(k - 1) & 1]; kp.ckpt_in_count = cnt + 2 * (k - 1);
+    kp.ckpt = buf[k & 1]; kp.ckpt_count = cnt + 2 * k;
+    kp.park_lanes = park;
+    mpc_lane_kernel<NS, MINB, true><<<(unsigned)rgrid, rthreads, 0, st>>>(kp);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
+  kp.ckpt = buf[phases & 1]; kp.ckpt_count = cnt + 2 * phases; kp.ckpt_next = cnt + 2 * phases + 1;
+  kp.ckpt_in = nullptr; kp.park_lanes = 0;
+  if constexpr (NS > 32) {
+    return launch_solo<NS, true>(h, kp, st, (long long)kp.ckpt_cap);
+  } else {
     const int ct = 128, G = NS <= 16 ? 16 : 32, groups = ct / G;
     const size_t smem = (size_t)groups * NS * ST_ROW_SH * sizeof(double);
     static thread_local int cached_dev2 = -1;
@@ -440,7 +545,7 @@ static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
   long long grid = (long long)h->sm_count * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = 0; kp.ckpt_count = h->d_counter + 1; kp.ckpt_next = h->d_counter + 2;
+  kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = INT_MAX; kp.ckpt_count = h->d_counter + 1; kp.ckpt_next = h->d_counter + 2;
   if (kp.counter) CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
   mpc_coop_kernel<NS><<<(unsigned)grid, threads, smem, st>>>(kp);
   CK(cudaGetLastError());
@@ -460,8 +565,16 @@ extern "C" int mpc_set_handoff(mpc_handle *h, int iterations) {
   return MPC_OK;
 }
 
+extern "C" int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int sort_ragged) {
+  if (!h || park_lanes < 0 || park_lanes > 31 || resume_launches < 0 || resume_launches > MPC_MAX_PHASES) return MPC_EINVAL;
+  h->park_lanes = park_lanes;
+  h->resume_phases = resume_launches;
+  h->sort_ragged = sort_ragged != 0;
+  return MPC_OK;
+}
+
 extern "C" int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm) {
-  if (!h || kind < MPC_KERNEL_AUTO || kind > MPC_KERNEL_COOP) return MPC_EINVAL;
+  if (!h || kind < MPC_KERNEL_AUTO || kind > MPC_KERNEL_SOLO) return MPC_EINVAL;
   if (lane_threads != 0 && (lane_threads < 32 || lane_threads > 256 || lane_threads % 32)) return MPC_EINVAL;
   h->kernel_kind = kind;
   h->lane_threads = lane_threads;
@@ -496,7 +609,18 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   // coop kernel (one problem per group of 16/32 lanes) wins; above it the lane kernel (one problem per lane)
   // has the throughput.  The warp kernel is the first version, kept selectable as a cross-check.
   int kind = h->kernel_kind;
-  if (kind == MPC_KERNEL_AUTO) kind = (B >= MPC_LANE_MIN_BATCH || c.N > 32) ? MPC_KERNEL_LANE : MPC_KERNEL_COOP;
+  if (kind == MPC_KERNEL_AUTO) {
+    if (c.N > 32) kind = B <= MPC_SOLO_MAX_BATCH ? MPC_KERNEL_SOLO : MPC_KERNEL_LANE;
+    else kind = B >= MPC_LANE_MIN_BATCH ? MPC_KERNEL_LANE : MPC_KERNEL_COOP;
+  }
+  if (kind == MPC_KERNEL_SOLO) {
+    CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), (cudaStream_t)cuda_stream));
+    kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = INT_MAX;
+    if (c.N <= 10) return launch_solo<10, false>(h, kp, (cudaStream_t)cuda_stream, B);
+    if (c.N <= 20) return launch_solo<20, false>(h, kp, (cudaStream_t)cuda_stream, B);
+    if (c.N <= 32) return launch_solo<32, false>(h, kp, (cudaStream_t)cuda_stream, B);
+    return launch_solo<MPC_NMAX, false>(h, kp, (cudaStream_t)cuda_stream, B);
+  }
   if (kind == MPC_KERNEL_WARP) {
     if (c.N > 32) { snprintf(g_err, sizeof(g_err), "warp kernel handles N <= 32"); return MPC_EINVAL; }
     return launch<32>(h, kp, (cudaStream_t)cuda_stream);
@@ -507,6 +631,24 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
     if (c.N <= 10) return launch_coop<10>(h, kp, (cudaStream_t)cuda_stream);
     if (c.N <= 20) return launch_coop<20>(h, kp, (cudaStream_t)cuda_stream);
     return launch_coop<32>(h, kp, (cudaStream_t)cuda_stream);
+  }
+  if (N_per && B >= MPC_TAIL_MIN_BATCH && h->sort_ragged) {
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (!h->d_perm || h->cap_perm < (size_t)B) {
+      cudaFree(h->d_perm);
+      h->d_perm = nullptr;
+      CK(cudaMalloc(&h->d_perm, (size_t)B * sizeof(int)));
+      h->cap_perm = B;
+    }
+    int *hist = h->d_counter + MPC_HIST0;
+    CK(cudaMemsetAsync(hist, 0, (MPC_NMAX + 1) * sizeof(int), st));
+    const int sg = (B + 255) / 256 < 4 * h->sm_count ? (B + 255) / 256 : 4 * h->sm_count;
+    mpc_horizon_hist_kernel<<<sg, 256, 0, st>>>(N_per, B, hist);
+    mpc_horizon_scan_kernel<<<1, 1, 0, st>>>(hist);
+    mpc_horizon_scatter_kernel<<<sg, 256, 0, st>>>(N_per, B, hist, h->d_perm);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    kp.perm = h->d_perm;
   }
   if (c.N <= 10) return launch_lane<10, 1>(h, kp, (cudaStream_t)cuda_stream);
   if (c.N <= 20) return launch_lane<20, 1>(h, kp, (cudaStream_t)cuda_stream);

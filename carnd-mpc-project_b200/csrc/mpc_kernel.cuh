@@ -88,6 +88,13 @@ struct KParams {
   int *ckpt_count;   // records written (may run past ckpt_cap: the surplus problems simply stay where they are)
   int *ckpt_next;    // next record the coop kernel takes
   int ckpt_cap, handoff_iter;
+  // tail packing (mpc_lane_kernel.cuh): once the queue is empty, a warp with at most park_lanes problems left parks
+  // them too; a resume launch reads the records of the previous launch (ckpt_in, *ckpt_in_count of them) packed 32 to
+  // a warp and parks into the other buffer
+  int park_lanes;
+  const double *ckpt_in;
+  const int *ckpt_in_count;
+  const int *perm;   // order in which the work queue hands out the problems (ragged batches: longest horizon first), or NULL
   // optional multiplier outputs (solution.lambda / zl / zu of CppAD::ipopt::solve_result), unscaled
   double *dual_lam, *dual_zl, *dual_zu;
 };

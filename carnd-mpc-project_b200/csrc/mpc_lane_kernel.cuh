@@ -82,20 +82,23 @@ enum { ST_S = 0,      // iterate: x, y, psi, v, cte, epsi
        ST_ROW = 78,   // thread-private rows (76 used, padded to a multiple of 16 bytes that is not one of 64)
        ST_LH = 76,    // coop kernel only: StageLin (10) + StageHess (18) of the stage, built one stage per lane
        ST_ROW_SH = 106 };   // shared-memory rows: 104 used; 106 keeps neighbouring lanes' rows 2-way bank-conflict free
-template <int NS, bool SH> struct LaneRows { typedef double type[NS][ST_ROW]; enum { ROW = ST_ROW }; };
-template <int NS> struct LaneRows<NS, true> { typedef double (*type)[ST_ROW_SH]; enum { ROW = ST_ROW_SH }; };
+template <int NS, bool SH, bool PAR> struct LaneRows { typedef double type[NS][ST_ROW]; enum { ROW = ST_ROW }; };
+template <int NS> struct LaneRows<NS, true, true> { typedef double (*type)[ST_ROW_SH]; enum { ROW = ST_ROW_SH }; };
+template <int NS> struct LaneRows<NS, true, false> { typedef double (*type)[ST_ROW]; enum { ROW = ST_ROW }; };
 
 struct StageLin { double a13, a14, a23, a24, a34, b3, a51, a54, a56, a61; };
 struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa, gp, gv, gc, ge, gdp, gd, ga; };
 
-template <int NS, bool SH>
+template <int NS, bool SH, bool PAR = SH>
 struct Lane {
   // ---- per-stage data (thread-private memory): 70 doubles per stage are touched on the common path
   // Per-stage data: one row of ST_ROW doubles per horizon stage (offsets ST_*).  SH = false: thread-private
   // memory (one problem per lane; rows 16-byte aligned, so neighbouring doubles pair into 128-bit local
-  // accesses).  SH = true: a pointer into shared memory (one problem per lane GROUP, mpc_coop_kernel).
-  enum { NS_GROUP = SH ? (NS <= 16 ? 16 : 32) : 1 };
-  typedef typename LaneRows<NS, SH>::type Rows;
+  // accesses).  SH = true: a pointer into shared memory.  PAR = true (needs SH): one problem per lane GROUP, the
+  // sweeps that are parallel over the horizon run one stage per lane (mpc_coop_kernel); PAR = false with SH: one
+  // problem per lane as in the lane kernel, only the rows live in shared memory (mpc_solo_kernel).
+  enum { NS_GROUP = PAR ? (NS <= 16 ? 16 : 32) : 1 };
+  typedef typename LaneRows<NS, SH, PAR>::type Rows;
   alignas(16) Rows ST;
   alignas(16) double PC[LC_SIZE];
   alignas(16) double FLT[2 * K_NFILT];
@@ -104,7 +107,7 @@ struct Lane {
   // the one-problem-per-lane kernel
   int g0, gstep;
   unsigned gm;
-  __device__ __forceinline__ void gsync() const { if (SH) __syncwarp(gm); }
+  __device__ __forceinline__ void gsync() const { if (PAR) __syncwarp(gm); }
   // ---- scalars ----
   int m1, m3;
   bool solve_ok, lh_stale, no_handoff;
@@ -218,20 +221,20 @@ struct Lane {
     sincos(s[2], &sp, &cp);
     sincos(s[5], &se, &ce);
     const double x = s[0];
-    const double f = (((c4_ * x + c3_) * x + c2_) * x + c1_) * x + c0_;
-    const double f1 = ((4.0 * c4_ * x + 3.0 * c3_) * x + 2.0 * c2_) * x + c1_;
-    const double f2 = (12.0 * c4_ * x + 6.0 * c3_) * x + 2.0 * c2_;
-    const double f3 = 24.0 * c4_ * x + 6.0 * c3_;
+    const double f = fma(fma(fma(fma(c4_, x, c3_), x, c2_), x, c1_), x, c0_);
+    const double f1 = fma(fma(fma(4.0 * c4_, x, 3.0 * c3_), x, 2.0 * c2_), x, c1_);
+    const double f2 = fma(fma(12.0 * c4_, x, 6.0 * c3_), x, 2.0 * c2_);
+    const double f3 = fma(24.0 * c4_, x, 6.0 * c3_);
     const double q = fma(f1, f1, 1.0), iq = rcp(q);
     tg[0] = sp; tg[1] = cp; tg[2] = se; tg[3] = ce; tg[4] = f1; tg[5] = f2;
     tg[6] = -f2 * iq;                                    // d/dx of -atan(f')
-    tg[7] = (f3 * q - 2.0 * f1 * f2 * f2) * iq * iq;      // and its derivative
+    tg[7] = fma(f3, q, -(2.0 * f1 * f2 * f2)) * iq * iq;      // and its derivative
     const double vdt = s[3] * dt;
-    F[0] = s[0] + cp * vdt;
-    F[1] = s[1] + sp * vdt;
-    F[2] = s[2] + u0 * s[3] * dtLf;
-    F[3] = s[3] + u1 * dt;
-    F[4] = (f - s[1]) + se * vdt;
+    F[0] = fma(cp, vdt, s[0]);
+    F[1] = fma(sp, vdt, s[1]);
+    F[2] = fma(u0 * s[3], dtLf, s[2]);
+    F[3] = fma(u1, dt, s[3]);
+    F[4] = fma(se, vdt, f - s[1]);
     F[5] = F[2] - atan(f1);
   }
   __device__ __forceinline__ void lin_at(const double *tg, double v, double d0, StageLin &L) const {
@@ -263,18 +266,18 @@ struct Lane {
     double sig[4], gb[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      sig[k] = zl[k] * il[k] + zu[k] * iu[k];
+      sig[k] = fma(zl[k], il[k], zu[k] * iu[k]);
       gb[k] = ls ? (zu[k] - zl[k]) : mu * (iu[k] - il[k]);
     }
     H.gp = gb[0];
-    H.gv = wv2 * (v - vref(i)) + nv2(i) * v + gb[1];
+    H.gv = fma(nv2(i), v, wv2 * (v - vref(i))) + gb[1];
     H.gc = wc2(i) * c;
     H.ge = we2(i) * e;
     H.gdp = 0.0; H.gd = 0.0; H.ga = 0.0;
     if (hasu) {
       const double dd = cpl ? d0 - dprev : 0.0;
       H.gdp = -cw * dd;
-      H.gd = wd2 * d0 + cw * dd + gb[2];
+      H.gd = fma(cw, dd, wd2 * d0) + gb[2];
       H.ga = gb[3];
     }
     if (ls) {
@@ -287,11 +290,11 @@ struct Lane {
     H.qcc = wc2(i) + dwv;
     if (hasu) {
       const double vdt = v * dt;
-      H.qxx = -ln[4] * tg[5] + ln[5] * tg[7] + dwv;
-      H.qpp = (ln[0] * tg[1] + ln[1] * tg[0]) * vdt + sig[0] + dwv;
-      H.qpv = (ln[0] * tg[0] - ln[1] * tg[1]) * dt;
+      H.qxx = fma(ln[5], tg[7], -(ln[4] * tg[5])) + dwv;
+      H.qpp = fma(fma(ln[0], tg[1], ln[1] * tg[0]), vdt, sig[0]) + dwv;
+      H.qpv = fma(ln[0], tg[0], -(ln[1] * tg[1])) * dt;
       H.qve = -ln[4] * tg[3] * dt;
-      H.qee = ln[4] * tg[2] * vdt + we2(i) + dwv;
+      H.qee = fma(ln[4] * tg[2], vdt, we2(i)) + dwv;
       H.svd = -(ln[2] + ln[5]) * dtLf;
       H.rdd = wd2 + (cpl ? cw : 0.0) + sig[2] + dwv;
       H.raa = sig[3] + dwv;
@@ -306,7 +309,7 @@ struct Lane {
   // trig/polynomial values of the trial point are kept (TT, CT) and become the iterate's on acceptance
   // ------------------------------------------------------------------------------------------
   __device__ void eval_sweep(double a) {
-    if (SH) { eval_par(a); return; }
+    if (PAR) { eval_par(a); return; }
     const double lo_p = PC[LC_LO], hi_p = PC[LC_HI], lo_v = PC[LC_LO + 1], hi_v = PC[LC_HI + 1];
     const double lo_d = PC[LC_LO + 2], hi_d = PC[LC_HI + 2], lo_a = PC[LC_LO + 3], hi_a = PC[LC_HI + 3];
     double F[6] = {0, 0, 0, 0, 0, 0};
@@ -324,7 +327,7 @@ struct Lane {
         for (int k = 0; k < 6; k++) { const double c = s[k] - F[k]; ST[i - 1][ST_CT + k] = c; th += fabs(c); }
       }
       const double dv = s[3] - vref(i);
-      fl += 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + PC[LC_WV2] * dv * dv + nv2(i) * s[3] * s[3]);
+      fl = fma(0.5, fma(nv2(i) * s[3], s[3], fma(PC[LC_WV2] * dv, dv, fma(we2(i) * s[5], s[5], wc2(i) * s[4] * s[4]))), fl);
       double prod = (s[2] - lo_p) * (hi_p - s[2]) * (s[3] - lo_v) * (hi_v - s[3]);
       if (i < N - 1) {
         const double u0 = fma(a, ST[i][ST_DU + 0], ST[i][ST_U + 0]), u1 = fma(a, ST[i][ST_DU + 1], ST[i][ST_U + 1]);
@@ -332,8 +335,8 @@ struct Lane {
         point_eval(s, u0, u1, tg, F);
 #pragma unroll
         for (int k = 0; k < 8; k++) ST[i][ST_TT + k] = tg[k];
-        fl += 0.5 * PC[LC_WD2] * u0 * u0;
-        if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * PC[LC_CW] * dd * dd; }
+        fl = fma(0.5 * PC[LC_WD2] * u0, u0, fl);
+        if (i >= 1) { const double dd = u0 - dprev; fl = fma(0.5 * PC[LC_CW] * dd, dd, fl); }
         dprev = u0;
         prod *= (u0 - lo_d) * (hi_d - u0) * (u1 - lo_a) * (hi_a - u1);
       }
@@ -344,7 +347,7 @@ struct Lane {
   // the same evaluation with one stage per lane of the group: the residual of the constraint that defines
   // s_i needs F(s_{i-1}, u_{i-1}) from the lane below; the three sums are butterfly reductions
   __device__ void eval_par(double a) {
-    const int G = SH ? NS_GROUP : 1;
+    const int G = PAR ? NS_GROUP : 1;
     const int i = g0;
     const bool act = i < N, hasu = i < N - 1;
     const int ii = act ? i : 0;
@@ -370,11 +373,11 @@ struct Lane {
     }
     if (act) {
       const double dv = s[3] - vref(i);
-      fl = 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + PC[LC_WV2] * dv * dv + nv2(i) * s[3] * s[3]);
+      fl = 0.5 * fma(nv2(i) * s[3], s[3], fma(PC[LC_WV2] * dv, dv, fma(we2(i) * s[5], s[5], wc2(i) * s[4] * s[4])));
       double prod = (s[2] - PC[LC_LO]) * (PC[LC_HI] - s[2]) * (s[3] - PC[LC_LO + 1]) * (PC[LC_HI + 1] - s[3]);
       if (hasu) {
-        fl += 0.5 * PC[LC_WD2] * u0 * u0;
-        if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * PC[LC_CW] * dd * dd; }
+        fl = fma(0.5 * PC[LC_WD2] * u0, u0, fl);
+        if (i >= 1) { const double dd = u0 - dprev; fl = fma(0.5 * PC[LC_CW] * dd, dd, fl); }
         prod *= (u0 - PC[LC_LO + 2]) * (PC[LC_HI + 2] - u0) * (u1 - PC[LC_LO + 3]) * (PC[LC_HI + 3] - u1);
       }
       ll = log(prod);
@@ -403,7 +406,7 @@ struct Lane {
   //  (3) Ipopt's optimality error terms at the resulting iterate.
   // ------------------------------------------------------------------------------------------
   __device__ void advance(bool do_update, bool ls, bool zero_lam) {
-    if (SH) { advance_par(do_update, ls, zero_lam); return; }
+    if (PAR) { advance_par(do_update, ls, zero_lam); return; }
     const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     const double a = alpha, az = alpha_z;
     const double dwv = ls ? 0.0 : dw_used;
@@ -446,18 +449,18 @@ struct Lane {
         double h[6];
         h[0] = H.qxx * ds[0];
         h[1] = H.qyy * ds[1];
-        h[2] = H.qpp * ds[2] + H.qpv * ds[3] + H.gp;
-        h[3] = H.qpv * ds[2] + H.qvv * ds[3] + H.qve * ds[5] + H.gv + H.svd * du0;
-        h[4] = H.qcc * ds[4] + H.gc;
-        h[5] = H.qve * ds[3] + H.qee * ds[5] + H.ge;
+        h[2] = fma(H.qpv, ds[3], H.qpp * ds[2]) + H.gp;
+        h[3] = fma(H.svd, du0, fma(H.qve, ds[5], fma(H.qvv, ds[3], H.qpv * ds[2])) + H.gv);
+        h[4] = fma(H.qcc, ds[4], H.gc);
+        h[5] = fma(H.qee, ds[5], H.qve * ds[3]) + H.ge;
         if (hasu) {
           const double l25 = lp_n[2] + lp_n[5];
-          lp[0] = lp_n[0] + L.a51 * lp_n[4] + L.a61 * lp_n[5] - h[0];
+          lp[0] = fma(L.a61, lp_n[5], fma(L.a51, lp_n[4], lp_n[0])) - h[0];
           lp[1] = lp_n[1] - lp_n[4] - h[1];
-          lp[2] = L.a13 * lp_n[0] + L.a23 * lp_n[1] + l25 - h[2];
-          lp[3] = L.a14 * lp_n[0] + L.a24 * lp_n[1] + L.a34 * l25 + lp_n[3] + L.a54 * lp_n[4] - h[3];
+          lp[2] = fma(L.a23, lp_n[1], L.a13 * lp_n[0]) + l25 - h[2];
+          lp[3] = fma(L.a54, lp_n[4], fma(L.a34, l25, fma(L.a24, lp_n[1], L.a14 * lp_n[0])) + lp_n[3]) - h[3];
           lp[4] = -h[4];
-          lp[5] = L.a56 * lp_n[4] - h[5];
+          lp[5] = fma(L.a56, lp_n[4], -h[5]);
         } else {
 #pragma unroll
           for (int k = 0; k < 6; k++) lp[k] = -h[k];
@@ -469,7 +472,7 @@ struct Lane {
         if (do_update) {
           const double dx[4] = {ds[2], ds[3], du0, du1};
 #pragma unroll
-          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] += a * (lp[k] - lam[k]); ST[i][ST_S + k] = s[k]; }
+          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] = fma(a, lp[k] - lam[k], lam[k]); ST[i][ST_S + k] = s[k]; }
           if (hasu) {
             u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
             ST[i][ST_U + 0] = u0; ST[i][ST_U + 1] = u1;
@@ -480,10 +483,10 @@ struct Lane {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             if (k < 2 || hasu) {
-              const double dzl = (mu - zl[k] * dx[k]) * il[k] - zl[k];
-              const double dzu = (mu + zu[k] * dx[k]) * iu[k] - zu[k];
-              zl[k] = dmax(dmin(zl[k] + az * dzl, zcap * iln[k]), zfloor * iln[k]);
-              zu[k] = dmax(dmin(zu[k] + az * dzu, zcap * iun[k]), zfloor * iun[k]);
+              const double dzl = fma(fma(-zl[k], dx[k], mu), il[k], -zl[k]);
+              const double dzu = fma(fma(zu[k], dx[k], mu), iu[k], -zu[k]);
+              zl[k] = dmax(dmin(fma(az, dzl, zl[k]), zcap * iln[k]), zfloor * iln[k]);
+              zu[k] = dmax(dmin(fma(az, dzu, zu[k]), zcap * iun[k]), zfloor * iun[k]);
               ST[i][ST_ZL + k] = zl[k]; ST[i][ST_ZU + k] = zu[k];
             }
           }
@@ -520,10 +523,10 @@ struct Lane {
       const double v = s[3];
       if (hasu) {
         const double l25 = ln_n[2] + ln_n[5];
-        os[0] = ln_n[0] + L.a51 * ln_n[4] + L.a61 * ln_n[5];
+        os[0] = fma(L.a61, ln_n[5], fma(L.a51, ln_n[4], ln_n[0]));
         os[1] = ln_n[1] - ln_n[4];
-        os[2] = L.a13 * ln_n[0] + L.a23 * ln_n[1] + l25;
-        os[3] = L.a14 * ln_n[0] + L.a24 * ln_n[1] + L.a34 * l25 + ln_n[3] + L.a54 * ln_n[4];
+        os[2] = fma(L.a23, ln_n[1], L.a13 * ln_n[0]) + l25;
+        os[3] = fma(L.a54, ln_n[4], fma(L.a34, l25, fma(L.a24, ln_n[1], L.a14 * ln_n[0])) + ln_n[3]);
         os[5] = L.a56 * ln_n[4];
         ou0 = L.b3 * l25;
         ou1 = dt * ln_n[3];
@@ -531,7 +534,7 @@ struct Lane {
       double gs[6];
       gs[0] = 0.0; gs[1] = 0.0;
       gs[2] = -zl[0] + zu[0];
-      gs[3] = wv2 * (v - vref(i)) + nv2(i) * v - zl[1] + zu[1];
+      gs[3] = fma(nv2(i), v, wv2 * (v - vref(i))) - zl[1] + zu[1];
       gs[4] = wc2(i) * s[4];
       gs[5] = we2(i) * s[5];
 #pragma unroll
@@ -549,8 +552,8 @@ struct Lane {
       }
       if (hasu) {
         double gd = wd2 * u0;
-        if (i >= 1) gd += cw * (u0 - dprev);
-        if (i <= N - 3) gd -= cw * (dnext - u0);
+        if (i >= 1) gd = fma(cw, u0 - dprev, gd);
+        if (i <= N - 3) gd = fma(-cw, dnext - u0, gd);
         r = nanmax(r, fabs(gd - ou0 - zl[2] + zu[2]));
         r = nanmax(r, fabs(-ou1 - zl[3] + zu[3]));
         zz += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
@@ -571,7 +574,7 @@ struct Lane {
   // part: N steps of a 6-vector handed down the lanes by shuffle; neighbours' new values (lambda_{i+1},
   // delta_{i+-1}) travel by shuffle too, the six error terms are butterfly reductions.
   __device__ void advance_par(bool do_update, bool ls, bool zero_lam) {
-    const int G = SH ? NS_GROUP : 1;
+    const int G = PAR ? NS_GROUP : 1;
     const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     const double a = alpha, az = alpha_z;
     const double dwv = ls ? 0.0 : dw_used;
@@ -607,10 +610,10 @@ struct Lane {
         hess_at(i, ls, dwv, tg, s[3], s[4], s[5], u0, (hasu && i >= 1) ? dprev_old : 0.0, lo_n, zl, zu, il, iu, H);
         h[0] = H.qxx * ds[0];
         h[1] = H.qyy * ds[1];
-        h[2] = H.qpp * ds[2] + H.qpv * ds[3] + H.gp;
-        h[3] = H.qpv * ds[2] + H.qvv * ds[3] + H.qve * ds[5] + H.gv + H.svd * du0;
-        h[4] = H.qcc * ds[4] + H.gc;
-        h[5] = H.qve * ds[3] + H.qee * ds[5] + H.ge;
+        h[2] = fma(H.qpv, ds[3], H.qpp * ds[2]) + H.gp;
+        h[3] = fma(H.svd, du0, fma(H.qve, ds[5], fma(H.qvv, ds[3], H.qpv * ds[2])) + H.gv);
+        h[4] = fma(H.qcc, ds[4], H.gc);
+        h[5] = fma(H.qee, ds[5], H.qve * ds[3]) + H.ge;
       }
       // lambda+_i = A_i^T lambda+_{i+1} - h_i, from the last stage down
 #pragma unroll 1
@@ -621,12 +624,12 @@ struct Lane {
         if (i == j) {
           if (hasu) {
             const double l25 = n[2] + n[5];
-            lp[0] = n[0] + L.a51 * n[4] + L.a61 * n[5] - h[0];
+            lp[0] = fma(L.a61, n[5], fma(L.a51, n[4], n[0])) - h[0];
             lp[1] = n[1] - n[4] - h[1];
-            lp[2] = L.a13 * n[0] + L.a23 * n[1] + l25 - h[2];
-            lp[3] = L.a14 * n[0] + L.a24 * n[1] + L.a34 * l25 + n[3] + L.a54 * n[4] - h[3];
+            lp[2] = fma(L.a23, n[1], L.a13 * n[0]) + l25 - h[2];
+            lp[3] = fma(L.a54, n[4], fma(L.a34, l25, fma(L.a24, n[1], L.a14 * n[0])) + n[3]) - h[3];
             lp[4] = -h[4];
-            lp[5] = L.a56 * n[4] - h[5];
+            lp[5] = fma(L.a56, n[4], -h[5]);
           } else {
 #pragma unroll
             for (int k = 0; k < 6; k++) lp[k] = -h[k];
@@ -641,7 +644,7 @@ struct Lane {
         if (act) {
           const double dx[4] = {ds[2], ds[3], du0, du1};
 #pragma unroll
-          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] += a * (lp[k] - lam[k]); ST[i][ST_S + k] = s[k]; }
+          for (int k = 0; k < 6; k++) { s[k] = fma(a, ds[k], s[k]); lam[k] = fma(a, lp[k] - lam[k], lam[k]); ST[i][ST_S + k] = s[k]; }
           if (hasu) {
             u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
             ST[i][ST_U + 0] = u0; ST[i][ST_U + 1] = u1;
@@ -651,10 +654,10 @@ struct Lane {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             if (k < 2 || hasu) {
-              const double dzl = (mu - zl[k] * dx[k]) * il[k] - zl[k];
-              const double dzu = (mu + zu[k] * dx[k]) * iu[k] - zu[k];
-              zl[k] = dmax(dmin(zl[k] + az * dzl, zcap * iln[k]), zfloor * iln[k]);
-              zu[k] = dmax(dmin(zu[k] + az * dzu, zcap * iun[k]), zfloor * iun[k]);
+              const double dzl = fma(fma(-zl[k], dx[k], mu), il[k], -zl[k]);
+              const double dzu = fma(fma(zu[k], dx[k], mu), iu[k], -zu[k]);
+              zl[k] = dmax(dmin(fma(az, dzl, zl[k]), zcap * iln[k]), zfloor * iln[k]);
+              zu[k] = dmax(dmin(fma(az, dzu, zu[k]), zcap * iun[k]), zfloor * iun[k]);
               ST[i][ST_ZL + k] = zl[k]; ST[i][ST_ZU + k] = zu[k];
             }
           }
@@ -700,10 +703,10 @@ struct Lane {
       const double v = s[3];
       if (hasu) {
         const double l25 = ln_n[2] + ln_n[5];
-        os[0] = ln_n[0] + L.a51 * ln_n[4] + L.a61 * ln_n[5];
+        os[0] = fma(L.a61, ln_n[5], fma(L.a51, ln_n[4], ln_n[0]));
         os[1] = ln_n[1] - ln_n[4];
-        os[2] = L.a13 * ln_n[0] + L.a23 * ln_n[1] + l25;
-        os[3] = L.a14 * ln_n[0] + L.a24 * ln_n[1] + L.a34 * l25 + ln_n[3] + L.a54 * ln_n[4];
+        os[2] = fma(L.a23, ln_n[1], L.a13 * ln_n[0]) + l25;
+        os[3] = fma(L.a54, ln_n[4], fma(L.a34, l25, fma(L.a24, ln_n[1], L.a14 * ln_n[0])) + ln_n[3]);
         os[5] = L.a56 * ln_n[4];
         ou0 = L.b3 * l25;
         ou1 = dt * ln_n[3];
@@ -711,7 +714,7 @@ struct Lane {
       double gs[6];
       gs[0] = 0.0; gs[1] = 0.0;
       gs[2] = -zl[0] + zu[0];
-      gs[3] = wv2 * (v - vref(i)) + nv2(i) * v - zl[1] + zu[1];
+      gs[3] = fma(nv2(i), v, wv2 * (v - vref(i))) - zl[1] + zu[1];
       gs[4] = wc2(i) * s[4];
       gs[5] = we2(i) * s[5];
 #pragma unroll
@@ -730,8 +733,8 @@ struct Lane {
       }
       if (hasu) {
         double gd = wd2 * u0;
-        if (i >= 1) gd += cw * (u0 - dprev);
-        if (i <= N - 3) gd -= cw * (dnext - u0);
+        if (i >= 1) gd = fma(cw, u0 - dprev, gd);
+        if (i <= N - 3) gd = fma(-cw, dnext - u0, gd);
         r = nanmax(r, fabs(gd - ou0 - zl[2] + zu[2]));
         r = nanmax(r, fabs(-ou1 - zl[3] + zu[3]));
         zz += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
@@ -779,13 +782,13 @@ struct Lane {
     gsync();
   }
   __device__ __forceinline__ void load_lin(int i, StageLin &L) const {
-    const double *q = &ST[i][SH ? ST_LH : 0];
+    const double *q = &ST[i][PAR ? ST_LH : 0];
     L.a13 = q[0]; L.a14 = q[1]; L.a23 = q[2]; L.a24 = q[3]; L.a34 = q[4]; L.b3 = q[5]; L.a51 = q[6]; L.a54 = q[7];
     L.a56 = q[8]; L.a61 = q[9];
   }
   // ls: H = I has no dw (the least-squares system is not regularised)
   __device__ __forceinline__ void load_hess(int i, double dwv, StageHess &H) const {
-    const double *q = &ST[i][SH ? ST_LH : 0];
+    const double *q = &ST[i][PAR ? ST_LH : 0];
     H.qxx = q[10] + dwv; H.qyy = q[11] + dwv; H.qpp = q[12] + dwv; H.qpv = q[13]; H.qvv = q[14] + dwv; H.qve = q[15];
     H.qcc = q[16] + dwv; H.qee = q[17] + dwv; H.svd = q[18]; H.rdd = q[19] + dwv; H.raa = q[20] + dwv;
     H.gp = q[21]; H.gv = q[22]; H.gc = q[23]; H.ge = q[24]; H.gdp = q[25]; H.gd = q[26]; H.ga = q[27];
@@ -805,7 +808,7 @@ struct Lane {
     {
       const int t = N - 1;
       StageHess H;
-      if (SH) {
+      if (PAR) {
         load_hess(t, dwv, H);
       } else {
         double zl[4] = {ST[t][ST_ZL + 0], ST[t][ST_ZL + 1], 0.0, 0.0}, zu[4] = {ST[t][ST_ZU + 0], ST[t][ST_ZU + 1], 0.0, 0.0}, il[4], iu[4];
@@ -829,7 +832,7 @@ struct Lane {
       StageLin L;
       StageHess H;
       double d[6];
-      if (SH) {
+      if (PAR) {
         load_lin(i, L);
         load_hess(i, ls ? 0.0 : dwv, H);
       } else {
@@ -862,18 +865,18 @@ struct Lane {
       double vv[6];
 #pragma unroll
       for (int r = 0; r < 6; r++)
-        vv[r] = pv[r] + Pm[r][0] * d[0] + Pm[r][1] * d[1] + Pm[r][2] * d[2] + Pm[r][3] * d[3] + Pm[r][4] * d[5];
-      const double v4 = p4 + P44 * d[4];
+        vv[r] = fma(Pm[r][4], d[5], fma(Pm[r][3], d[3], fma(Pm[r][2], d[2], fma(Pm[r][1], d[1], fma(Pm[r][0], d[0], pv[r])))));
+      const double v4 = fma(P44, d[4], p4);
       // T = P+ G, columns x, y, psi, v, delta, a
       double T[6][6];
 #pragma unroll
       for (int r = 0; r < 6; r++) {
         const double pe = Pm[r][2] + Pm[r][4];
-        T[r][0] = Pm[r][0] + L.a61 * Pm[r][4];
+        T[r][0] = fma(L.a61, Pm[r][4], Pm[r][0]);
         T[r][1] = Pm[r][1];
-        T[r][2] = L.a13 * Pm[r][0] + L.a23 * Pm[r][1] + pe;
-        T[r][3] = L.a14 * Pm[r][0] + L.a24 * Pm[r][1] + L.a34 * pe + Pm[r][3];
-        T[r][4] = L.b3 * pe + Pm[r][5];
+        T[r][2] = fma(L.a23, Pm[r][1], L.a13 * Pm[r][0]) + pe;
+        T[r][3] = fma(L.a34, pe, fma(L.a24, Pm[r][1], L.a14 * Pm[r][0])) + Pm[r][3];
+        T[r][4] = fma(L.b3, pe, Pm[r][5]);
         T[r][5] = dt * Pm[r][3];
       }
       // M = G^T T (upper triangle over x, y, psi, v, delta, a), then + cte rank-1 + stage Hessian
@@ -881,19 +884,19 @@ struct Lane {
 #pragma unroll
       for (int c = 0; c < 6; c++) {
         const double te = T[2][c] + T[4][c];
-        M[0][c] = T[0][c] + L.a61 * T[4][c];
+        M[0][c] = fma(L.a61, T[4][c], T[0][c]);
         if (c >= 1) M[1][c] = T[1][c];
-        if (c >= 2) M[2][c] = L.a13 * T[0][c] + L.a23 * T[1][c] + te;
-        if (c >= 3) M[3][c] = L.a14 * T[0][c] + L.a24 * T[1][c] + L.a34 * te + T[3][c];
-        if (c >= 4) M[4][c] = L.b3 * te + T[5][c];
+        if (c >= 2) M[2][c] = fma(L.a23, T[1][c], L.a13 * T[0][c]) + te;
+        if (c >= 3) M[3][c] = fma(L.a34, te, fma(L.a24, T[1][c], L.a14 * T[0][c])) + T[3][c];
+        if (c >= 4) M[4][c] = fma(L.b3, te, T[5][c]);
         if (c >= 5) M[5][c] = dt * T[3][c];
       }
       // cte row of G: (a51 [x], -1 [y], a54 [v], a56 [epsi])
       const double g4x = P44 * L.a51, g4v = P44 * L.a54, g4e = P44 * L.a56;
-      const double Mxx = M[0][0] + g4x * L.a51 + H.qxx;
+      const double Mxx = fma(g4x, L.a51, M[0][0]) + H.qxx;
       const double Mxy = M[0][1] - g4x;
       const double Mxp = M[0][2];
-      const double Mxv = M[0][3] + g4x * L.a54;
+      const double Mxv = fma(g4x, L.a54, M[0][3]);
       const double Mxe = g4x * L.a56;
       const double Mxd = M[0][4], Mxa = M[0][5];
       const double Myy = M[1][1] + P44 + H.qyy;
@@ -904,24 +907,24 @@ struct Lane {
       const double Mpp = M[2][2] + H.qpp;
       const double Mpv = M[2][3] + H.qpv;
       const double Mpd = M[2][4], Mpa = M[2][5];
-      const double Mvv = M[3][3] + g4v * L.a54 + H.qvv;
-      const double Mve = g4v * L.a56 + H.qve;
+      const double Mvv = fma(g4v, L.a54, M[3][3]) + H.qvv;
+      const double Mve = fma(g4v, L.a56, H.qve);
       const double Mvd = M[3][4] + H.svd, Mva = M[3][5];
-      const double Mee = g4e * L.a56 + H.qee;
+      const double Mee = fma(g4e, L.a56, H.qee);
       const double Mdd = M[4][4] + H.rdd, Mda = M[4][5], Maa = M[5][5] + H.raa;
       // delta_prev row: only the rate coupling:  M[dp][dp] = cwe, M[dp][delta] = -cwe
       // m = G^T v + g
       const double ve = vv[2] + vv[4];
-      const double mx = vv[0] + L.a61 * vv[4] + L.a51 * v4;
+      const double mx = fma(L.a51, v4, fma(L.a61, vv[4], vv[0]));
       const double my = vv[1] - v4;
-      const double mp = L.a13 * vv[0] + L.a23 * vv[1] + ve + H.gp;
-      const double mv = L.a14 * vv[0] + L.a24 * vv[1] + L.a34 * ve + vv[3] + L.a54 * v4 + H.gv;
-      const double me = L.a56 * v4 + H.ge;
+      const double mp = fma(L.a23, vv[1], L.a13 * vv[0]) + ve + H.gp;
+      const double mv = fma(L.a54, v4, fma(L.a34, ve, fma(L.a24, vv[1], L.a14 * vv[0])) + vv[3]) + H.gv;
+      const double me = fma(L.a56, v4, H.ge);
       const double mdp = H.gdp;
-      const double md = L.b3 * ve + vv[5] + H.gd;
-      const double ma = dt * vv[3] + H.ga;
+      const double md = fma(L.b3, ve, vv[5]) + H.gd;
+      const double ma = fma(dt, vv[3], H.ga);
       // 2x2 control pivot
-      const double det = Mdd * Maa - Mda * Mda;
+      const double det = fma(Mdd, Maa, -(Mda * Mda));
       ok = ok && (Mdd > 0.0) && (det > 0.0);
       const double idet = rcp(det);
       const double i11 = Maa * idet, i12 = -Mda * idet, i22 = Mdd * idet;
@@ -931,46 +934,46 @@ struct Lane {
       double K0[5], K1[5];
 #pragma unroll
       for (int c = 0; c < 5; c++) {
-        K0[c] = -(i11 * cd[c] + i12 * ca[c]);
-        K1[c] = -(i12 * cd[c] + i22 * ca[c]);
+        K0[c] = -fma(i11, cd[c], i12 * ca[c]);
+        K1[c] = -fma(i12, cd[c], i22 * ca[c]);
         ST[i][ST_KG + c] = K0[c];
         ST[i][ST_KG + 5 + c] = K1[c];
       }
-      const double k0 = -(i11 * md + i12 * ma), k1 = -(i12 * md + i22 * ma);
+      const double k0 = -fma(i11, md, i12 * ma), k1 = -fma(i12, md, i22 * ma);
       ST[i][ST_KG + 10] = k0; ST[i][ST_KG + 11] = k1;
       // Schur complement -> new cost-to-go (index order X, Y, PSI, V, E, DP)
-      Pm[0][0] = Mxx + Mxd * K0[0] + Mxa * K1[0];
-      Pm[0][1] = Mxy + Mxd * K0[1] + Mxa * K1[1];
-      Pm[0][2] = Mxp + Mxd * K0[2] + Mxa * K1[2];
-      Pm[0][3] = Mxv + Mxd * K0[3] + Mxa * K1[3];
+      Pm[0][0] = fma(Mxa, K1[0], fma(Mxd, K0[0], Mxx));
+      Pm[0][1] = fma(Mxa, K1[1], fma(Mxd, K0[1], Mxy));
+      Pm[0][2] = fma(Mxa, K1[2], fma(Mxd, K0[2], Mxp));
+      Pm[0][3] = fma(Mxa, K1[3], fma(Mxd, K0[3], Mxv));
       Pm[0][4] = Mxe;
-      Pm[0][5] = Mxd * K0[4] + Mxa * K1[4];
-      Pm[1][1] = Myy + Myd * K0[1] + Mya * K1[1];
-      Pm[1][2] = Myp + Myd * K0[2] + Mya * K1[2];
-      Pm[1][3] = Myv + Myd * K0[3] + Mya * K1[3];
+      Pm[0][5] = fma(Mxa, K1[4], Mxd * K0[4]);
+      Pm[1][1] = fma(Mya, K1[1], fma(Myd, K0[1], Myy));
+      Pm[1][2] = fma(Mya, K1[2], fma(Myd, K0[2], Myp));
+      Pm[1][3] = fma(Mya, K1[3], fma(Myd, K0[3], Myv));
       Pm[1][4] = Mye;
-      Pm[1][5] = Myd * K0[4] + Mya * K1[4];
-      Pm[2][2] = Mpp + Mpd * K0[2] + Mpa * K1[2];
-      Pm[2][3] = Mpv + Mpd * K0[3] + Mpa * K1[3];
+      Pm[1][5] = fma(Mya, K1[4], Myd * K0[4]);
+      Pm[2][2] = fma(Mpa, K1[2], fma(Mpd, K0[2], Mpp));
+      Pm[2][3] = fma(Mpa, K1[3], fma(Mpd, K0[3], Mpv));
       Pm[2][4] = 0.0;
-      Pm[2][5] = Mpd * K0[4] + Mpa * K1[4];
-      Pm[3][3] = Mvv + Mvd * K0[3] + Mva * K1[3];
+      Pm[2][5] = fma(Mpa, K1[4], Mpd * K0[4]);
+      Pm[3][3] = fma(Mva, K1[3], fma(Mvd, K0[3], Mvv));
       Pm[3][4] = Mve;
-      Pm[3][5] = Mvd * K0[4] + Mva * K1[4];
+      Pm[3][5] = fma(Mva, K1[4], Mvd * K0[4]);
       Pm[4][4] = Mee;
       Pm[4][5] = 0.0;
-      Pm[5][5] = cwe - cwe * K0[4];
+      Pm[5][5] = fma(-cwe, K0[4], cwe);
 #pragma unroll
       for (int r = 1; r < 6; r++) {
 #pragma unroll
         for (int c = 0; c < r; c++) Pm[r][c] = Pm[c][r];
       }
-      pv[0] = mx + Mxd * k0 + Mxa * k1;
-      pv[1] = my + Myd * k0 + Mya * k1;
-      pv[2] = mp + Mpd * k0 + Mpa * k1;
-      pv[3] = mv + Mvd * k0 + Mva * k1;
+      pv[0] = fma(Mxa, k1, fma(Mxd, k0, mx));
+      pv[1] = fma(Mya, k1, fma(Myd, k0, my));
+      pv[2] = fma(Mpa, k1, fma(Mpd, k0, mp));
+      pv[3] = fma(Mva, k1, fma(Mvd, k0, mv));
       pv[4] = me;
-      pv[5] = mdp - cwe * k0;
+      pv[5] = fma(-cwe, k0, mdp);
       P44 = H.qcc;
       p4 = H.gc;
     }
@@ -983,7 +986,7 @@ struct Lane {
   // to the boundary for x and for z) and grad(phi_mu)^T dx of the line search
   // ------------------------------------------------------------------------------------------
   __device__ void forward_and_ratios(bool ls, bool soc) {
-    if (SH) { forward_par(ls, soc); return; }
+    if (PAR) { forward_par(ls, soc); return; }
     const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     double t[6], dp = 0.0;
 #pragma unroll
@@ -1006,8 +1009,8 @@ struct Lane {
 #pragma unroll
         for (int k = 0; k < 8; k++) tg[k] = ST[i][ST_TG + k];
         u0 = ST[i][ST_U + 0]; u1 = ST[i][ST_U + 1];
-        du0 = kg[10] + kg[0] * t[0] + kg[1] * t[1] + kg[2] * t[2] + kg[3] * t[3] + kg[4] * dp;
-        du1 = kg[11] + kg[5] * t[0] + kg[6] * t[1] + kg[7] * t[2] + kg[8] * t[3] + kg[9] * dp;
+        du0 = fma(kg[4], dp, fma(kg[3], t[3], fma(kg[2], t[2], fma(kg[1], t[1], fma(kg[0], t[0], kg[10])))));
+        du1 = fma(kg[9], dp, fma(kg[8], t[3], fma(kg[7], t[2], fma(kg[6], t[1], fma(kg[5], t[0], kg[11])))));
         ST[i][ST_DU + 0] = du0; ST[i][ST_DU + 1] = du1;
         if (ls) {
 #pragma unroll
@@ -1021,20 +1024,20 @@ struct Lane {
         }
         StageLin L;
         lin_at(tg, v, u0, L);
-        tn[0] = t[0] + L.a13 * t[2] + L.a14 * t[3] + d[0];
-        tn[1] = t[1] + L.a23 * t[2] + L.a24 * t[3] + d[1];
-        tn[2] = t[2] + L.a34 * t[3] + L.b3 * du0 + d[2];
-        tn[3] = t[3] + dt * du1 + d[3];
-        tn[4] = L.a51 * t[0] - t[1] + L.a54 * t[3] + L.a56 * t[5] + d[4];
-        tn[5] = L.a61 * t[0] + t[2] + L.a34 * t[3] + L.b3 * du0 + d[5];
+        tn[0] = fma(L.a14, t[3], fma(L.a13, t[2], t[0])) + d[0];
+        tn[1] = fma(L.a24, t[3], fma(L.a23, t[2], t[1])) + d[1];
+        tn[2] = fma(L.b3, du0, fma(L.a34, t[3], t[2])) + d[2];
+        tn[3] = fma(dt, du1, t[3]) + d[3];
+        tn[4] = fma(L.a56, t[5], fma(L.a54, t[3], fma(L.a51, t[0], -t[1]))) + d[4];
+        tn[5] = fma(L.b3, du0, fma(L.a34, t[3], fma(L.a61, t[0], t[2]))) + d[5];
       }
       if (!ls) {
-        acc += (wv2 * (v - vref(i)) + nv2(i) * v) * t[3] + wc2(i) * ST[i][ST_S + 4] * t[4] + we2(i) * ST[i][ST_S + 5] * t[5];
+        acc += fma(we2(i) * ST[i][ST_S + 5], t[5], fma(wc2(i) * ST[i][ST_S + 4], t[4], fma(nv2(i), v, wv2 * (v - vref(i))) * t[3]));
         if (hasu) {
           double gd = wd2 * u0;
-          if (i >= 1) gd += cw * (u0 - dprev);
-          if (i <= N - 3) gd -= cw * (ST[i + 1][ST_U + 0] - u0);
-          acc += gd * du0;
+          if (i >= 1) gd = fma(cw, u0 - dprev, gd);
+          if (i <= N - 3) gd = fma(-cw, ST[i + 1][ST_U + 0] - u0, gd);
+          acc = fma(gd, du0, acc);
           dprev = u0;
         }
         double il[4], iu[4];
@@ -1044,10 +1047,10 @@ struct Lane {
         for (int k = 0; k < 4; k++) {
           if (k < 2 || hasu) {
             const double zl = ST[i][ST_ZL + k], zu = ST[i][ST_ZU + k];
-            acc += mu * (iu[k] - il[k]) * dx[k];
+            acc = fma(mu * (iu[k] - il[k]), dx[k], acc);
             rmax = dmax(rmax, dmax(-dx[k] * il[k], dx[k] * iu[k]));
-            const double dzl = (mu - zl * dx[k]) * il[k] - zl;
-            const double dzu = (mu + zu * dx[k]) * iu[k] - zu;
+            const double dzl = fma(fma(-zl, dx[k], mu), il[k], -zl);
+            const double dzu = fma(fma(zu, dx[k], mu), iu[k], -zu);
             // z/(-dz) < zn/zd  <=>  z*zd < zn*(-dz)   (all denominators positive)
             if (dzl < 0.0 && (zd == 0.0 || zl * zd < zn * (-dzl))) { zn = zl; zd = -dzl; }
             if (dzu < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu))) { zn = zu; zd = -dzu; }
@@ -1069,7 +1072,7 @@ struct Lane {
   // coop kernel: the recursion runs identically in every lane of the group (on the derivative pieces of
   // build_lh); each lane keeps the step of its own stage and computes that stage's step-length ratios
   __device__ void forward_par(bool ls, bool soc) {
-    const int G = SH ? NS_GROUP : 1;
+    const int G = PAR ? NS_GROUP : 1;
     const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     double t[6], dp = 0.0;
 #pragma unroll
@@ -1083,8 +1086,8 @@ struct Lane {
         double kg[12], d[6];
 #pragma unroll
         for (int k = 0; k < 12; k++) kg[k] = ST[i][ST_KG + k];
-        du0 = kg[10] + kg[0] * t[0] + kg[1] * t[1] + kg[2] * t[2] + kg[3] * t[3] + kg[4] * dp;
-        du1 = kg[11] + kg[5] * t[0] + kg[6] * t[1] + kg[7] * t[2] + kg[8] * t[3] + kg[9] * dp;
+        du0 = fma(kg[4], dp, fma(kg[3], t[3], fma(kg[2], t[2], fma(kg[1], t[1], fma(kg[0], t[0], kg[10])))));
+        du1 = fma(kg[9], dp, fma(kg[8], t[3], fma(kg[7], t[2], fma(kg[6], t[1], fma(kg[5], t[0], kg[11])))));
         if (ls) {
 #pragma unroll
           for (int k = 0; k < 6; k++) d[k] = 0.0;
@@ -1097,12 +1100,12 @@ struct Lane {
         }
         StageLin L;
         load_lin(i, L);
-        tn[0] = t[0] + L.a13 * t[2] + L.a14 * t[3] + d[0];
-        tn[1] = t[1] + L.a23 * t[2] + L.a24 * t[3] + d[1];
-        tn[2] = t[2] + L.a34 * t[3] + L.b3 * du0 + d[2];
-        tn[3] = t[3] + dt * du1 + d[3];
-        tn[4] = L.a51 * t[0] - t[1] + L.a54 * t[3] + L.a56 * t[5] + d[4];
-        tn[5] = L.a61 * t[0] + t[2] + L.a34 * t[3] + L.b3 * du0 + d[5];
+        tn[0] = fma(L.a14, t[3], fma(L.a13, t[2], t[0])) + d[0];
+        tn[1] = fma(L.a24, t[3], fma(L.a23, t[2], t[1])) + d[1];
+        tn[2] = fma(L.b3, du0, fma(L.a34, t[3], t[2])) + d[2];
+        tn[3] = fma(dt, du1, t[3]) + d[3];
+        tn[4] = fma(L.a56, t[5], fma(L.a54, t[3], fma(L.a51, t[0], -t[1]))) + d[4];
+        tn[5] = fma(L.b3, du0, fma(L.a34, t[3], fma(L.a61, t[0], t[2]))) + d[5];
       }
       if (i == g0) {
 #pragma unroll
@@ -1120,12 +1123,12 @@ struct Lane {
       const bool hasu = i < N - 1;
       const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3];
       const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
-      acc = (wv2 * (v - vref(i)) + nv2(i) * v) * mt[3] + wc2(i) * ST[i][ST_S + 4] * mt[4] + we2(i) * ST[i][ST_S + 5] * mt[5];
+      acc = fma(we2(i) * ST[i][ST_S + 5], mt[5], fma(wc2(i) * ST[i][ST_S + 4], mt[4], fma(nv2(i), v, wv2 * (v - vref(i))) * mt[3]));
       if (hasu) {
         double gd = wd2 * u0;
-        if (i >= 1) gd += cw * (u0 - ST[i - 1][ST_U + 0]);
-        if (i <= N - 3) gd -= cw * (ST[i + 1][ST_U + 0] - u0);
-        acc += gd * mdu0;
+        if (i >= 1) gd = fma(cw, u0 - ST[i - 1][ST_U + 0], gd);
+        if (i <= N - 3) gd = fma(-cw, ST[i + 1][ST_U + 0] - u0, gd);
+        acc = fma(gd, mdu0, acc);
       }
       double il[4], iu[4];
       slack_rcp(psi, v, u0, u1, hasu, il, iu);
@@ -1134,10 +1137,10 @@ struct Lane {
       for (int k = 0; k < 4; k++) {
         if (k < 2 || hasu) {
           const double zl = ST[i][ST_ZL + k], zu = ST[i][ST_ZU + k];
-          acc += mu * (iu[k] - il[k]) * dx[k];
+          acc = fma(mu * (iu[k] - il[k]), dx[k], acc);
           rmax = dmax(rmax, dmax(-dx[k] * il[k], dx[k] * iu[k]));
-          const double dzl = (mu - zl * dx[k]) * il[k] - zl;
-          const double dzu = (mu + zu * dx[k]) * iu[k] - zu;
+          const double dzl = fma(fma(-zl, dx[k], mu), il[k], -zl);
+          const double dzu = fma(fma(zu, dx[k], mu), iu[k], -zu);
           if (dzl < 0.0 && (zd == 0.0 || zl * zd < zn * (-dzl))) { zn = zl; zd = -dzl; }
           if (dzu < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu))) { zn = zu; zd = -dzu; }
         }
@@ -1245,13 +1248,13 @@ struct Lane {
       s[2] = fmin(fmax(s[2], PC[LC_LO0]), PC[LC_HI0]);
       s[3] = fmin(fmax(s[3], PC[LC_LO0 + 1]), PC[LC_HI0 + 1]);
       const double dv = s[3] - vref(i);
-      fl += 0.5 * (wc2(i) * s[4] * s[4] + we2(i) * s[5] * s[5] + wv2 * dv * dv + nv2(i) * s[3] * s[3]);
+      fl = fma(0.5, fma(nv2(i) * s[3], s[3], fma(wv2 * dv, dv, fma(we2(i) * s[5], s[5], wc2(i) * s[4] * s[4]))), fl);
       double u0 = 0.0, u1 = 0.0;
       if (hasu) {
         u0 = fmin(fmax(ST[i][ST_U + 0], PC[LC_LO0 + 2]), PC[LC_HI0 + 2]);
         u1 = fmin(fmax(ST[i][ST_U + 1], PC[LC_LO0 + 3]), PC[LC_HI0 + 3]);
-        fl += 0.5 * wd2 * u0 * u0;
-        if (i >= 1) { const double dd = u0 - dprev; fl += 0.5 * cw * dd * dd; }
+        fl = fma(0.5 * wd2 * u0, u0, fl);
+        if (i >= 1) { const double dd = u0 - dprev; fl = fma(0.5 * cw * dd, dd, fl); }
         dprev = u0;
       }
       if (i == 1) {
@@ -1352,7 +1355,7 @@ struct Lane {
     } else if (m1 == LM_LSQ_ZERO) {
       zero = true; err = true;
     } else if (m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
-      const double phi_t = ft - mu * lt;
+      const double phi_t = fma(-mu, lt, ft);
       if (m1 == LM_TRIAL) alpha_test = alpha;
       if (ls_accept(alpha_test, tht, phi_t)) {
         if (m1 == LM_SOC_TRIAL) alpha = alpha_soc;
@@ -1408,7 +1411,7 @@ struct Lane {
     if (solve) {
       const bool ls = m3 == LM_LSQ;
       const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? dw : dw_used);
-      if (SH && (lh_stale || ls || (m3 == LM_NEWTON && dw == 0.0))) { build_lh(ls); lh_stale = false; }
+      if (PAR && (lh_stale || ls || (m3 == LM_NEWTON && dw == 0.0))) { build_lh(ls); lh_stale = false; }
       solve_ok = riccati(ls, m3 == LM_SOC, dwv);
     } else {
       m3 = LM_IDLE;
@@ -1436,7 +1439,7 @@ struct Lane {
       alpha = alpha_soc;   // alpha_max
       ls_gbd = gbd_new;
       ls_theta = theta;
-      ls_phi = fx - mu * lsum;
+      ls_phi = fma(-mu, lsum, fx);
       pow_gbd = ls_gbd < 0.0 ? pow(-ls_gbd, K_S_PHI) : 0.0;
       pow_theta = pow(ls_theta, K_S_THETA);
       double amin_ = K_GAMMA_THETA;
@@ -1463,28 +1466,55 @@ struct Lane {
 // body is ~100 KB of code, and warps at unrelated places in it thrash the instruction cache
 // (profiles/r01_v3_*: 3.3 issue slots lost per instruction to "no instruction" with independent one-warp
 // CTAs).  Further barriers between the slots of a trip were measured to make no difference (+-2 %).
-template <int NS, int MINB>
+//
+// A warp costs the same per trip whether 32 of its lanes hold a problem or one.  Two rules move problems out
+// of warps that would run nearly empty (both at a trip boundary, as flat records, see Lane::save):
+//   1. a problem still running after handoff_iter iterations is parked;
+//   2. once the queue is empty (a lane of the warp found nothing to fetch), a warp with at most park_lanes
+//      problems left parks them all.
+// RESUME = true is the same kernel started from the records of the previous launch instead of fresh problems,
+// 32 consecutive records to a warp, warps dealt round-robin to the CTAs -- so the survivors of many sparse
+// warps run in a few full ones.  The last launch of a chain parks nothing (P.ckpt == NULL).
+template <int NS, int MINB, bool RESUME>
 __global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
   Lane<NS, false> Z;
   Z.mode = LM_IDLE;
   Z.b = 0;
   Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;
   Z.lh_stale = false; Z.no_handoff = false;
+  int n_in = 0, next_in = 0;
+  if (RESUME) {
+    n_in = *P.ckpt_in_count;
+    if (n_in > P.ckpt_cap) n_in = P.ckpt_cap;
+    next_in = (int)(((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31));
+  }
   for (;;) {
     // ---- slot 0: retire / migrate / fetch
     if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
-    // A problem that is still running after handoff_iter iterations is one of the few that set the length of
-    // the batch's tail; a lone lane needs ~47 us per trip for it.  Park it for the coop kernel, which runs
-    // after this one and takes ~19 us per trip, and pull the next problem.
-    if (P.ckpt && Z.mode != LM_IDLE && Z.mode != LM_DONE && Z.iter >= P.handoff_iter && !Z.no_handoff) {
-      const int slot = atomicAdd(P.ckpt_count, 1);
-      if (slot < P.ckpt_cap) { Z.save(P.ckpt + (size_t)slot * Lane<NS, false>::CK_SIZE); Z.mode = LM_IDLE; }
-      else Z.no_handoff = true;
-    }
-    if (Z.mode == LM_IDLE) Z.no_handoff = false;
-    if (Z.mode == LM_IDLE) {
-      const int nb = atomicAdd(P.counter, 1);
-      if (nb < P.B) Z.init(P, nb); else Z.mode = LM_DONE;
+    // two passes over one copy of the park / fetch code: rule 1 then fetch, rule 2 after the fetch
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      unsigned live = 0xffffffffu;
+      if (pass == 1) live = __ballot_sync(0xffffffffu, Z.mode != LM_DONE);
+      const bool can = P.ckpt && Z.mode != LM_IDLE && Z.mode != LM_DONE && !Z.no_handoff;
+      // rule 2: a lane is only ever DONE when the queue had nothing left for it
+      const bool park = can && (pass == 0 ? Z.iter >= P.handoff_iter
+                                          : (live != 0xffffffffu && __popc(live) <= P.park_lanes));
+      if (park) {
+        const int slot = atomicAdd(P.ckpt_count, 1);
+        if (slot < P.ckpt_cap) { Z.save(P.ckpt + (size_t)slot * Lane<NS, false>::CK_SIZE); Z.mode = pass == 0 ? LM_IDLE : LM_DONE; }
+        else Z.no_handoff = true;
+      }
+      if (pass == 0 && Z.mode == LM_IDLE) {
+        Z.no_handoff = false;
+        if (RESUME) {
+          if (next_in < n_in) { Z.load(P.ckpt_in + (size_t)next_in * Lane<NS, false>::CK_SIZE); next_in += (int)(gridDim.x * blockDim.x); }
+          else Z.mode = LM_DONE;
+        } else {
+          const int nb = atomicAdd(P.counter, 1);
+          if (nb < P.B) Z.init(P, P.perm ? P.perm[nb] : nb); else Z.mode = LM_DONE;
+        }
+      }
     }
     if (__syncthreads_and(Z.mode == LM_DONE)) break;
     Z.trip_eval();
@@ -1563,6 +1593,43 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_resume_kernel(const KParams P
     }
     if (Z.g0 == 0) Z.write_outputs(P);
     Z.gsync();
+  }
+}
+
+// One problem per WARP-lane with the rows in shared memory (the lane kernel's sequential sweeps, Lane<NS, true, false>):
+// the finisher for horizons the coop kernel does not take (N > 32), and the kernel for a handful of such problems.
+// A lane that is alone in its warp still touches one 128-byte line of thread-private memory per word (the lanes of
+// a warp are interleaved word by word), N * 20 KB per sweep: beyond N ~ 12 that no longer fits the L1 and every
+// access of the last long-running problems goes to L2.  Here the rows of a problem are N * 624 contiguous bytes of
+// shared memory.  lanes_per_warp lanes of every one-warp CTA hold a problem (1 for NS = 64: five CTAs per SM).
+template <int NS, bool RESUME>
+__global__ void __launch_bounds__(32, 1) mpc_solo_kernel(const KParams P, int lanes_per_warp) {
+  extern __shared__ double solo_smem[];
+  Lane<NS, true, false> Z;
+  Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;
+  Z.lh_stale = false; Z.no_handoff = true;
+  Z.b = 0;
+  const bool has = (int)threadIdx.x < lanes_per_warp;
+  Z.ST = reinterpret_cast<double (*)[ST_ROW]>(solo_smem + (size_t)(has ? threadIdx.x : 0) * NS * ST_ROW);
+  Z.mode = has ? LM_IDLE : LM_DONE;
+  int n = P.B;
+  if (RESUME) {
+    n = *P.ckpt_count;
+    if (n > P.ckpt_cap) n = P.ckpt_cap;
+  }
+  for (;;) {
+    if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
+    if (Z.mode == LM_IDLE) {
+      const int k = atomicAdd(RESUME ? P.ckpt_next : P.counter, 1);
+      if (k >= n) Z.mode = LM_DONE;
+      else if (RESUME) Z.load(P.ckpt + (size_t)k * Lane<NS, true, false>::CK_SIZE);
+      else Z.init(P, P.perm ? P.perm[k] : k);
+    }
+    if (__all_sync(0xffffffffu, Z.mode == LM_DONE)) break;
+    Z.trip_eval();
+    Z.trip_accept(P);
+    Z.trip_factor();
+    Z.trip_solve();
   }
 }
 

@@ -277,6 +277,7 @@ def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
     args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
     S.set_kernel(mpc.KERNEL_LANE)
     S.set_handoff(0)
+    S.set_tail(0, 0)
     ref = S.solve_batch_host(*args, want_full=True)
     for it in (1, 5, 10, 13, 25):
         S.set_handoff(it)
@@ -287,6 +288,73 @@ def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
             assert np.array_equal(got[k], ref[k]), (it, k)
     with pytest.raises(mpc.MpcError):
         S.set_handoff(-1)
+    # tail packing: sparse warps park their problems, resume launches pick them up 32 to a warp, the coop kernel
+    # finishes -- any combination, same bits
+    for hand, park, resume in ((0, 8, 0), (0, 8, 1), (13, 16, 2), (0, 31, 3), (5, 4, 6)):
+        S.set_handoff(hand)
+        S.set_tail(park, resume)
+        n0 = S.launches
+        got = S.solve_batch_host(*args, want_full=True)
+        assert S.launches - n0 == 2 + resume
+        for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
+            assert np.array_equal(got[k], ref[k]), (hand, park, resume, k)
+    with pytest.raises(mpc.MpcError):
+        S.set_tail(32, 0)
+    with pytest.raises(mpc.MpcError):
+        S.set_tail(8, 7)
+    S.close()
+
+
+def test_long_horizon_kernels_agree_bit_for_bit(mpc, stable_cd, refdata):
+    """N > 32 has no coop kernel: a few problems run the solo kernel (one problem per lane, rows in shared memory),
+    big batches the lane kernel with lane-kernel resume launches and the solo kernel as the finisher.  All of them
+    are the same arithmetic (the library is built without implicit multiply-add contraction), so: same bits."""
+    import json
+    cfg = mpc.config_from_json_text(json.dumps(dict(refdata["configs"]["stable"], N=40, dt=0.05)))
+    S = mpc.Solver(cfg, 0)
+    b = mpc.workloads.batch_perturbed_states(3000, 17, cfg.as_dict())
+    args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.set_kernel(mpc.KERNEL_LANE)
+    S.set_tail(0, 0)
+    ref = S.solve_batch_host(*args, want_full=True)
+    assert (ref["status"] == 1).mean() > 0.9 and ref["iters"].max() > 40
+    for kind, park, resume in ((mpc.KERNEL_SOLO, 0, 0), (mpc.KERNEL_LANE, 8, 0), (mpc.KERNEL_LANE, 16, 2), (mpc.KERNEL_AUTO, 31, 1)):
+        S.set_kernel(kind)
+        S.set_tail(park, resume)
+        got = S.solve_batch_host(*args, want_full=True)
+        for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
+            assert np.array_equal(got[k], ref[k]), (kind, park, resume, k)
+    # AUTO on a handful of long-horizon problems is the solo kernel: one launch
+    S.set_kernel(mpc.KERNEL_AUTO)
+    n0 = S.launches
+    few = S.solve_batch_host(*(a[:100] for a in args), want_full=True)
+    assert S.launches - n0 == 1
+    for k in ("result", "full", "status", "iters"):
+        assert np.array_equal(few[k], ref[k][:100]), k
+    S.close()
+
+
+def test_ragged_batch_order_is_invisible(mpc, stable_cd, refdata):
+    """Batches with per-problem horizons are handed out longest horizon first (a counting sort on the device); the
+    order in which lanes pick problems up does not change any result."""
+    import json
+    cfg = mpc.config_from_json_text(json.dumps(dict(refdata["configs"]["stable"], N=50)))
+    S = mpc.Solver(cfg, 0)
+    B = 6000
+    b = mpc.workloads.batch_perturbed_states(B, 23, cfg.as_dict())
+    rng = np.random.default_rng(5)
+    Np = rng.choice([10, 17, 25, 33, 50], B).astype(np.int32)
+    dtp = rng.choice([0.1, 0.05, 0.02], B)
+    dtp[Np >= 33] = 0.02
+    args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.set_kernel(mpc.KERNEL_LANE)
+    S.set_tail(0, 0, False)
+    ref = S.solve_batch_host(*args, N_per=Np, dt_per=dtp)
+    for park, resume, srt in ((0, 0, True), (8, 1, True), (16, 2, False)):
+        S.set_tail(park, resume, srt)
+        got = S.solve_batch_host(*args, N_per=Np, dt_per=dtp)
+        for k in ("result", "traj_x", "traj_y", "status", "iters"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (park, resume, srt, k)
     S.close()
 
 
