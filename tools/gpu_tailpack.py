@@ -4,6 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mpc_b200 as mpc
 which = sys.argv[1] if len(sys.argv) > 1 else "134"
+only = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]]   # optional: just these (handoff, park, resume, sort) settings
 rd = mpc.workloads.reference_data()
 js = rd['configs']['stable']
 dev = torch.device('cuda:0')
@@ -19,7 +20,7 @@ def sweep(name, S, B, call, settings, reps):
     res = torch.zeros(9, B, dtype=torch.float64, device=dev)
     st = torch.zeros(B, dtype=torch.int32, device=dev); it = torch.zeros(B, dtype=torch.int32, device=dev)
     ref = None
-    for hand, park, ph, srt in settings:
+    for hand, park, ph, srt in (only or settings):
         S.set_handoff(hand); S.set_tail(park, ph, srt)
         res.zero_(); st.zero_(); it.zero_()
         l0 = S.launches
