@@ -268,9 +268,9 @@ class Solver:
         """Pick the kernel (auto / one problem per warp / one problem per lane) and the lane grid."""
         _check(lib().mpc_set_kernel(self._h, kind, lane_threads, lane_ctas_per_sm), "mpc_set_kernel")
 
-    def set_tail(self, park_lanes, resume_launches, sort_ragged=True):
-        """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches, ragged sort."""
-        _check(lib().mpc_set_tail(self._h, int(park_lanes), int(resume_launches), int(bool(sort_ragged))), "mpc_set_tail")
+    def set_tail(self, park_lanes, resume_launches, sort_ragged=True, solo_finisher=False):
+        """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches, ragged sort, finisher."""
+        _check(lib().mpc_set_tail(self._h, int(park_lanes), int(resume_launches), (1 if sort_ragged else 0) | (2 if solo_finisher else 0)), "mpc_set_tail")
 
     def set_handoff(self, iterations):
         """Iteration count after which the lane kernel hands a problem to the coop kernel (0 = never)."""

@@ -56,6 +56,7 @@ struct mpc_handle {
   size_t cap_ckpt;      // records per buffer
   int ckpt_ns;
   bool sort_ragged;     // ragged batches (N_per given): hand the problems out longest horizon first
+  bool solo_finisher;   // finish the tail with the solo kernel instead of the coop kernel (experiments)
   int *d_perm;          // ragged batches: problem order of the work queue (longest horizon first)
   size_t cap_perm;
   double *dual_lam, *dual_zl, *dual_zu;   // caller's device buffers for the multipliers (or NULL)
@@ -455,7 +456,7 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   // rule 1 (off by default; profiles/r01_handoff_sweep.txt and r01_tail_packing_sweep.txt: 13% on the 64K batch of
   // config-stable at 13 iterations, but a loss on workloads with a wider spread of iteration counts, and nothing on
   // top of rule 2): needs the coop kernel
-  const bool rule1 = h->handoff_iter > 0 && NS <= 32 && kp.B >= MPC_LANE_MIN_BATCH && kp.B <= MPC_HANDOFF_MAX_BATCH;
+  const bool rule1 = h->handoff_iter > 0 && kp.B >= MPC_LANE_MIN_BATCH && kp.B <= MPC_HANDOFF_MAX_BATCH;
   const int park = kp.B >= MPC_TAIL_MIN_BATCH ? h->park_lanes : 0;
   const int phases = park > 0 ? h->resume_phases : 0;
   int *cnt = h->d_counter + 1;   // [2k] records written by launch k of the chain, [2k + 1] cursor of the coop kernel
@@ -504,7 +505,7 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   }
   kp.ckpt = buf[phases & 1]; kp.ckpt_count = cnt + 2 * phases; kp.ckpt_next = cnt + 2 * phases + 1;
   kp.ckpt_in = nullptr; kp.park_lanes = 0;
-  if constexpr (NS > 32) {
+  if (h->solo_finisher) {
     return launch_solo<NS, true>(h, kp, st, (long long)kp.ckpt_cap);
   } else {
     const int ct = 128, G = NS <= 16 ? 16 : 32, groups = ct / G;
@@ -565,11 +566,12 @@ extern "C" int mpc_set_handoff(mpc_handle *h, int iterations) {
   return MPC_OK;
 }
 
-extern "C" int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int sort_ragged) {
+extern "C" int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int flags) {
   if (!h || park_lanes < 0 || park_lanes > 31 || resume_launches < 0 || resume_launches > MPC_MAX_PHASES) return MPC_EINVAL;
   h->park_lanes = park_lanes;
   h->resume_phases = resume_launches;
-  h->sort_ragged = sort_ragged != 0;
+  h->sort_ragged = (flags & MPC_TAIL_SORT_RAGGED) != 0;
+  h->solo_finisher = (flags & MPC_TAIL_SOLO_FINISHER) != 0;
   return MPC_OK;
 }
 
@@ -610,7 +612,7 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   // has the throughput.  The warp kernel is the first version, kept selectable as a cross-check.
   int kind = h->kernel_kind;
   if (kind == MPC_KERNEL_AUTO) {
-    if (c.N > 32) kind = B <= MPC_SOLO_MAX_BATCH ? MPC_KERNEL_SOLO : MPC_KERNEL_LANE;
+    if (c.N > 32) kind = B <= MPC_COOP_MAX_BATCH_LONG ? MPC_KERNEL_COOP : MPC_KERNEL_LANE;
     else kind = B >= MPC_LANE_MIN_BATCH ? MPC_KERNEL_LANE : MPC_KERNEL_COOP;
   }
   if (kind == MPC_KERNEL_SOLO) {
@@ -627,10 +629,10 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   }
   if (kind == MPC_KERNEL_COOP) {
     if (h->one_shot) kp.counter = nullptr;   // mpc_solve_one: one group, no work queue
-    if (c.N > 32) { snprintf(g_err, sizeof(g_err), "coop kernel handles N <= 32"); return MPC_EINVAL; }
     if (c.N <= 10) return launch_coop<10>(h, kp, (cudaStream_t)cuda_stream);
     if (c.N <= 20) return launch_coop<20>(h, kp, (cudaStream_t)cuda_stream);
-    return launch_coop<32>(h, kp, (cudaStream_t)cuda_stream);
+    if (c.N <= 32) return launch_coop<32>(h, kp, (cudaStream_t)cuda_stream);
+    return launch_coop<MPC_NMAX>(h, kp, (cudaStream_t)cuda_stream);
   }
   if (N_per && B >= MPC_TAIL_MIN_BATCH && h->sort_ragged) {
     cudaStream_t st = (cudaStream_t)cuda_stream;

@@ -97,7 +97,7 @@ struct Lane {
   // accesses).  SH = true: a pointer into shared memory.  PAR = true (needs SH): one problem per lane GROUP, the
   // sweeps that are parallel over the horizon run one stage per lane (mpc_coop_kernel); PAR = false with SH: one
   // problem per lane as in the lane kernel, only the rows live in shared memory (mpc_solo_kernel).
-  enum { NS_GROUP = PAR ? (NS <= 16 ? 16 : 32) : 1 };
+  enum { NS_GROUP = PAR ? (NS <= 16 ? 16 : 32) : 1, NPASS = (NS + NS_GROUP - 1) / NS_GROUP };   // stages per lane of a group
   typedef typename LaneRows<NS, SH, PAR>::type Rows;
   alignas(16) Rows ST;
   alignas(16) double PC[LC_SIZE];
@@ -347,6 +347,7 @@ struct Lane {
   // the same evaluation with one stage per lane of the group: the residual of the constraint that defines
   // s_i needs F(s_{i-1}, u_{i-1}) from the lane below; the three sums are butterfly reductions
   __device__ void eval_par(double a) {
+    if (NPASS > 1) { eval_parN(a); return; }
     const int G = PAR ? NS_GROUP : 1;
     const int i = g0;
     const bool act = i < N, hasu = i < N - 1;
@@ -381,6 +382,67 @@ struct Lane {
         prod *= (u0 - PC[LC_LO + 2]) * (PC[LC_HI + 2] - u0) * (u1 - PC[LC_LO + 3]) * (PC[LC_HI + 3] - u1);
       }
       ll = log(prod);
+    }
+    ft = gsum<NS_GROUP>(fl, gm); lt = gsum<NS_GROUP>(ll, gm); tht = gsum<NS_GROUP>(th, gm);
+    gsync();
+  }
+  // More stages than lanes in the group (N > 32): lane g holds stages g, g + G, ...  F(s_i, u_i) travels to the owner
+  // of stage i + 1 through the CT slot of row i (which that owner then overwrites with the residual), the neighbour's
+  // trial delta is recomputed from its row.  Same operations per stage as eval_par / eval_sweep.
+  __device__ void eval_parN(double a) {
+    const int G = PAR ? NS_GROUP : 1;
+    double s[NPASS][6], u0[NPASS];
+    double fl = 0.0, ll = 0.0, th = 0.0;
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+      const int i = g0 + p * G;
+      const bool act = i < N, hasu = i < N - 1;
+      const int ii = act ? i : 0;
+      u0[p] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s[p][k] = fma(a, ST[ii][ST_DS + k], ST[ii][ST_S + k]);
+      if (hasu) {
+        double tg[8], F[6];
+        u0[p] = fma(a, ST[i][ST_DU + 0], ST[i][ST_U + 0]);
+        const double u1 = fma(a, ST[i][ST_DU + 1], ST[i][ST_U + 1]);
+        point_eval(s[p], u0[p], u1, tg, F);
+#pragma unroll
+        for (int k = 0; k < 8; k++) ST[i][ST_TT + k] = tg[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) ST[i][ST_CT + k] = F[k];
+        double prod = (s[p][2] - PC[LC_LO]) * (PC[LC_HI] - s[p][2]) * (s[p][3] - PC[LC_LO + 1]) * (PC[LC_HI + 1] - s[p][3]);
+        prod *= (u0[p] - PC[LC_LO + 2]) * (PC[LC_HI + 2] - u0[p]) * (u1 - PC[LC_LO + 3]) * (PC[LC_HI + 3] - u1);
+        ll += log(prod);
+      } else if (act) {
+        ll += log((s[p][2] - PC[LC_LO]) * (PC[LC_HI] - s[p][2]) * (s[p][3] - PC[LC_LO + 1]) * (PC[LC_HI + 1] - s[p][3]));
+      }
+    }
+    gsync();
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      c0t[k] = fma(a, ST[0][ST_DS + k], ST[0][ST_S + k]) - PC[LC_S0 + k];
+      if (g0 == 0) th += fabs(c0t[k]);
+    }
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+      const int i = g0 + p * G;
+      const bool act = i < N, hasu = i < N - 1;
+      if (act && i >= 1) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { const double c = s[p][k] - ST[i - 1][ST_CT + k]; ST[i - 1][ST_CT + k] = c; th += fabs(c); }
+      }
+      if (act) {
+        const double dv = s[p][3] - vref(i);
+        double f = 0.5 * fma(nv2(i) * s[p][3], s[p][3], fma(PC[LC_WV2] * dv, dv, fma(we2(i) * s[p][5], s[p][5], wc2(i) * s[p][4] * s[p][4])));
+        if (hasu) {
+          f = fma(0.5 * PC[LC_WD2] * u0[p], u0[p], f);
+          if (i >= 1) {
+            const double dd = u0[p] - fma(a, ST[i - 1][ST_DU + 0], ST[i - 1][ST_U + 0]);
+            f = fma(0.5 * PC[LC_CW] * dd, dd, f);
+          }
+        }
+        fl += f;
+      }
     }
     ft = gsum<NS_GROUP>(fl, gm); lt = gsum<NS_GROUP>(ll, gm); tht = gsum<NS_GROUP>(th, gm);
     gsync();
@@ -574,6 +636,7 @@ struct Lane {
   // part: N steps of a 6-vector handed down the lanes by shuffle; neighbours' new values (lambda_{i+1},
   // delta_{i+-1}) travel by shuffle too, the six error terms are butterfly reductions.
   __device__ void advance_par(bool do_update, bool ls, bool zero_lam) {
+    if (NPASS > 1) { advance_parN(do_update, ls, zero_lam); return; }
     const int G = PAR ? NS_GROUP : 1;
     const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     const double a = alpha, az = alpha_z;
@@ -748,14 +811,221 @@ struct Lane {
     amin = gmin<NS_GROUP>(am, gm); amax = gmax<NS_GROUP>(aM, gm); lsq_lmax = gmax<NS_GROUP>(lmax, gm);
     gsync();
   }
+  // More stages than lanes in the group: the neighbours' old values are read from their rows before anything is
+  // written, the costate vector is handed from the owner of stage j + 1 to the owner of stage j by an indexed
+  // shuffle, the neighbours' new values are read back after the update.  Same operations per stage as advance_par.
+  __device__ void advance_parN(bool do_update, bool ls, bool zero_lam) {
+    const int G = PAR ? NS_GROUP : 1;
+    const double dt = PC[LC_DT], cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
+    const double a = alpha, az = alpha_z;
+    const double dwv = ls ? 0.0 : dw_used;
+    const double zcap = K_KAPPA_SIGMA * mu, zfloor = mu / K_KAPPA_SIGMA;
+    const bool costate = do_update || ls;
+    double lp[NPASS][6], h[NPASS][6], lmax = 0.0;
+    StageLin L[NPASS];
+    // ---- phase 1: h_i = (W + Sigma) d_i + grad terms at the OLD iterate (reads only)
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+      const int i = g0 + p * G;
+      const bool act = i < N, hasu = i < N - 1;
+      const int ii = act ? i : 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { lp[p][k] = 0.0; h[p][k] = 0.0; }
+      double tg[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) tg[k] = hasu ? ST[ii][ST_TG + k] : 0.0;
+      const double v = ST[ii][ST_S + 3], u0 = hasu ? ST[ii][ST_U + 0] : 0.0, u1 = hasu ? ST[ii][ST_U + 1] : 0.0;
+      lin_at(tg, v, u0, L[p]);
+      if (costate && act) {
+        double zl[4], zu[4], lo_n[6], il[4], iu[4], ds[6], du0 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { zl[k] = ST[i][ST_ZL + k]; zu[k] = ST[i][ST_ZU + k]; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) { lo_n[k] = hasu ? ST[i + 1][ST_LAM + k] : 0.0; ds[k] = ST[i][ST_DS + k]; }
+        if (hasu) du0 = ST[i][ST_DU + 0];
+        const double dprev_old = (hasu && i >= 1) ? ST[i - 1][ST_U + 0] : 0.0;
+        slack_rcp(ST[i][ST_S + 2], v, u0, u1, hasu, il, iu);
+        StageHess H;
+        hess_at(i, ls, dwv, tg, v, ST[i][ST_S + 4], ST[i][ST_S + 5], u0, dprev_old, lo_n, zl, zu, il, iu, H);
+        h[p][0] = H.qxx * ds[0];
+        h[p][1] = H.qyy * ds[1];
+        h[p][2] = fma(H.qpv, ds[3], H.qpp * ds[2]) + H.gp;
+        h[p][3] = fma(H.svd, du0, fma(H.qve, ds[5], fma(H.qvv, ds[3], H.qpv * ds[2])) + H.gv);
+        h[p][4] = fma(H.qcc, ds[4], H.gc);
+        h[p][5] = fma(H.qee, ds[5], H.qve * ds[3]) + H.ge;
+      }
+    }
+    // ---- phase 2: lambda+_j = A_j^T lambda+_{j+1} - h_j, from the last stage down
+    if (costate) {
+#pragma unroll 1
+      for (int j = N - 1; j >= 0; j--) {
+        const int src = (j + 1) % G, sp = (j + 1) / G;
+        double n[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          double v = lp[0][k];
+#pragma unroll
+          for (int p = 1; p < NPASS; p++) v = (sp == p) ? lp[p][k] : v;
+          n[k] = __shfl_sync(gm, v, src, G);
+        }
+        if (j % G == g0) {
+          const int pj = j / G;
+#pragma unroll
+          for (int p = 0; p < NPASS; p++) {
+            if (p == pj) {
+              if (j < N - 1) {
+                const double l25 = n[2] + n[5];
+                lp[p][0] = fma(L[p].a61, n[5], fma(L[p].a51, n[4], n[0])) - h[p][0];
+                lp[p][1] = n[1] - n[4] - h[p][1];
+                lp[p][2] = fma(L[p].a23, n[1], L[p].a13 * n[0]) + l25 - h[p][2];
+                lp[p][3] = fma(L[p].a54, n[4], fma(L[p].a34, l25, fma(L[p].a24, n[1], L[p].a14 * n[0])) + n[3]) - h[p][3];
+                lp[p][4] = -h[p][4];
+                lp[p][5] = fma(L[p].a56, n[4], -h[p][5]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) lp[p][k] = -h[p][k];
+              }
+            }
+          }
+        }
+      }
+    }
+    gsync();   // every lane has read its neighbours' old rows
+    // ---- phase 3: accept the step
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+      const int i = g0 + p * G;
+      const bool act = i < N, hasu = i < N - 1;
+      if (!act) continue;
+      if (costate) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) lmax = nanmax(lmax, fabs(lp[p][k]));
+        double lam[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) lam[k] = ST[i][ST_LAM + k];
+        if (do_update) {
+          double sv[6], ds[6], zl[4], zu[4], il[4], iu[4], iln[4], iun[4];
+          double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+          const double du0 = hasu ? ST[i][ST_DU + 0] : 0.0, du1 = hasu ? ST[i][ST_DU + 1] : 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; k++) { sv[k] = ST[i][ST_S + k]; ds[k] = ST[i][ST_DS + k]; }
+#pragma unroll
+          for (int k = 0; k < 4; k++) { zl[k] = ST[i][ST_ZL + k]; zu[k] = ST[i][ST_ZU + k]; }
+          slack_rcp(sv[2], sv[3], u0, u1, hasu, il, iu);
+          const double dx[4] = {ds[2], ds[3], du0, du1};
+#pragma unroll
+          for (int k = 0; k < 6; k++) { sv[k] = fma(a, ds[k], sv[k]); lam[k] = fma(a, lp[p][k] - lam[k], lam[k]); ST[i][ST_S + k] = sv[k]; }
+          if (hasu) {
+            u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
+            ST[i][ST_U + 0] = u0; ST[i][ST_U + 1] = u1;
+          }
+          slack_rcp(sv[2], sv[3], u0, u1, hasu, iln, iun);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < 2 || hasu) {
+              const double dzl = fma(fma(-zl[k], dx[k], mu), il[k], -zl[k]);
+              const double dzu = fma(fma(zu[k], dx[k], mu), iu[k], -zu[k]);
+              zl[k] = dmax(dmin(fma(az, dzl, zl[k]), zcap * iln[k]), zfloor * iln[k]);
+              zu[k] = dmax(dmin(fma(az, dzu, zu[k]), zcap * iun[k]), zfloor * iun[k]);
+              ST[i][ST_ZL + k] = zl[k]; ST[i][ST_ZU + k] = zu[k];
+            }
+          }
+          if (hasu) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) ST[i][ST_CN + k] = ST[i][ST_CT + k];
+#pragma unroll
+            for (int k = 0; k < 8; k++) ST[i][ST_TG + k] = ST[i][ST_TT + k];
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) lam[k] = lp[p][k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) ST[i][ST_LAM + k] = lam[k];
+      } else if (zero_lam) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ST[i][ST_LAM + k] = 0.0;
+      }
+    }
+    if (do_update) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) c0[k] = c0t[k];
+    }
+    gsync();   // the new rows are visible
+    // ---- phase 4: optimality error terms at the (new) iterate
+    double r = 0.0, cv = 0.0, l1 = 0.0, zz = 0.0, am = 1e300, aM = 0.0;
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+      const int i = g0 + p * G;
+      const bool act = i < N, hasu = i < N - 1;
+      if (!act) continue;
+      double sv[6], lam[6], zl[4], zu[4], ln_n[6], cn[6], tg[8];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { sv[k] = ST[i][ST_S + k]; lam[k] = ST[i][ST_LAM + k]; ln_n[k] = hasu ? ST[i + 1][ST_LAM + k] : 0.0; cn[k] = hasu ? ST[i][ST_CN + k] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { zl[k] = ST[i][ST_ZL + k]; zu[k] = ST[i][ST_ZU + k]; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) tg[k] = hasu ? ST[i][ST_TG + k] : 0.0;
+      const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+      const double v = sv[3];
+      StageLin Ln;
+      lin_at(tg, v, u0, Ln);
+      double os[6] = {0, 0, 0, 0, 0, 0}, ou0 = 0.0, ou1 = 0.0;
+      if (hasu) {
+        const double l25 = ln_n[2] + ln_n[5];
+        os[0] = fma(Ln.a61, ln_n[5], fma(Ln.a51, ln_n[4], ln_n[0]));
+        os[1] = ln_n[1] - ln_n[4];
+        os[2] = fma(Ln.a23, ln_n[1], Ln.a13 * ln_n[0]) + l25;
+        os[3] = fma(Ln.a54, ln_n[4], fma(Ln.a34, l25, fma(Ln.a24, ln_n[1], Ln.a14 * ln_n[0])) + ln_n[3]);
+        os[5] = Ln.a56 * ln_n[4];
+        ou0 = Ln.b3 * l25;
+        ou1 = dt * ln_n[3];
+      }
+      double gs[6];
+      gs[0] = 0.0; gs[1] = 0.0;
+      gs[2] = -zl[0] + zu[0];
+      gs[3] = fma(nv2(i), v, wv2 * (v - vref(i))) - zl[1] + zu[1];
+      gs[4] = wc2(i) * sv[4];
+      gs[5] = we2(i) * sv[5];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        r = nanmax(r, fabs(gs[k] + lam[k] - os[k]));
+        l1 += fabs(lam[k]);
+        cv = nanmax(cv, fabs(cn[k]));
+        if (i == 0) cv = nanmax(cv, fabs(c0[k]));
+      }
+      zz += fabs(zl[0]) + fabs(zu[0]) + fabs(zl[1]) + fabs(zu[1]);
+      {
+        const double p0 = (sv[2] - PC[LC_LO]) * zl[0], p1 = (PC[LC_HI] - sv[2]) * zu[0];
+        const double p2 = (sv[3] - PC[LC_LO + 1]) * zl[1], p3 = (PC[LC_HI + 1] - sv[3]) * zu[1];
+        am = dmin(am, dmin(dmin(p0, p1), dmin(p2, p3)));
+        aM = dmax(aM, dmax(dmax(p0, p1), dmax(p2, p3)));
+      }
+      if (hasu) {
+        double gd = wd2 * u0;
+        if (i >= 1) gd = fma(cw, u0 - ST[i - 1][ST_U + 0], gd);
+        if (i <= N - 3) gd = fma(-cw, ST[i + 1][ST_U + 0] - u0, gd);
+        r = nanmax(r, fabs(gd - ou0 - zl[2] + zu[2]));
+        r = nanmax(r, fabs(-ou1 - zl[3] + zu[3]));
+        zz += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
+        const double p0 = (u0 - PC[LC_LO + 2]) * zl[2], p1 = (PC[LC_HI + 2] - u0) * zu[2];
+        const double p2 = (u1 - PC[LC_LO + 3]) * zl[3], p3 = (PC[LC_HI + 3] - u1) * zu[3];
+        am = dmin(am, dmin(dmin(p0, p1), dmin(p2, p3)));
+        aM = dmax(aM, dmax(dmax(p0, p1), dmax(p2, p3)));
+      }
+    }
+    dinf = gmax<NS_GROUP>(r, gm); cviol = gmax<NS_GROUP>(cv, gm); lam1 = gsum<NS_GROUP>(l1, gm); z1 = gsum<NS_GROUP>(zz, gm);
+    amin = gmin<NS_GROUP>(am, gm); amax = gmax<NS_GROUP>(aM, gm); lsq_lmax = gmax<NS_GROUP>(lmax, gm);
+    gsync();
+  }
   // max_i |slack_i * z_i - m|  from the extreme complementarity products
   __device__ __forceinline__ double compl_err(double m) const { return nanmax(fabs(amax - m), fabs(amin - m)); }
 
   // coop kernel: derivative pieces of every stage at the iterate, one stage per lane, into the shared row
   // (dw is added by the Riccati sweep, so an inertia-correction retry does not rebuild them)
   __device__ void build_lh(bool ls) {
-    const int i = g0;
-    if (i < N) {
+#pragma unroll 1
+    for (int i = g0; i < N; i += NS_GROUP) {
       const bool hasu = i < N - 1;
       double tg[8], ln[6], zl[4], zu[4], il[4], iu[4];
 #pragma unroll
@@ -1077,7 +1347,13 @@ struct Lane {
     double t[6], dp = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; k++) t[k] = ls ? 0.0 : (soc ? -cs0[k] : -c0[k]);
-    double mt[6] = {0, 0, 0, 0, 0, 0}, mdu0 = 0.0, mdu1 = 0.0;
+    double mts[NPASS][6], mdu0s[NPASS], mdu1s[NPASS];
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+      mdu0s[p] = 0.0; mdu1s[p] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) mts[p][k] = 0.0;
+    }
 #pragma unroll 1
     for (int i = 0; i < N; i++) {
       const bool hasu = i < N - 1;
@@ -1107,23 +1383,34 @@ struct Lane {
         tn[4] = fma(L.a56, t[5], fma(L.a54, t[3], fma(L.a51, t[0], -t[1]))) + d[4];
         tn[5] = fma(L.b3, du0, fma(L.a34, t[3], fma(L.a61, t[0], t[2]))) + d[5];
       }
-      if (i == g0) {
+      if (i % G == g0) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) { mt[k] = t[k]; ST[i][ST_DS + k] = t[k]; }
-        mdu0 = du0; mdu1 = du1;
+        for (int p = 0; p < NPASS; p++) {
+          if (p == i / G) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) mts[p][k] = t[k];
+            mdu0s[p] = du0; mdu1s[p] = du1;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) ST[i][ST_DS + k] = t[k];
         if (hasu) { ST[i][ST_DU + 0] = du0; ST[i][ST_DU + 1] = du1; }
       }
 #pragma unroll
       for (int k = 0; k < 6; k++) t[k] = tn[k];
       dp = du0;
     }
-    double rmax = 0.0, zn = 1.0, zd = 0.0, acc = 0.0;
-    const int i = g0;
+    double rmax = 0.0, zn = 1.0, zd = 0.0, gbd = 0.0;
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+    const int i = g0 + p * G;
+    const double *mt = mts[p];
+    const double mdu0 = mdu0s[p], mdu1 = mdu1s[p];
     if (!ls && i < N) {
       const bool hasu = i < N - 1;
       const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3];
       const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
-      acc = fma(we2(i) * ST[i][ST_S + 5], mt[5], fma(wc2(i) * ST[i][ST_S + 4], mt[4], fma(nv2(i), v, wv2 * (v - vref(i))) * mt[3]));
+      double acc = fma(we2(i) * ST[i][ST_S + 5], mt[5], fma(wc2(i) * ST[i][ST_S + 4], mt[4], fma(nv2(i), v, wv2 * (v - vref(i))) * mt[3]));
       if (hasu) {
         double gd = wd2 * u0;
         if (i >= 1) gd = fma(cw, u0 - ST[i - 1][ST_U + 0], gd);
@@ -1145,6 +1432,8 @@ struct Lane {
           if (dzu < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu))) { zn = zu; zd = -dzu; }
         }
       }
+      gbd = (p == 0) ? acc : gbd + acc;
+    }
     }
     gsync();
     // group minimum of zn / zd (zd == 0 stands for +infinity), maximum of rmax, sum of acc
@@ -1155,7 +1444,7 @@ struct Lane {
       if (take) { zn = on; zd = od; }
     }
     rmax = gmax<NS_GROUP>(rmax, gm);
-    gbd_new = gsum<NS_GROUP>(acc, gm);
+    gbd_new = gsum<NS_GROUP>(gbd, gm);
     if (ls) return;
     alpha_soc = (rmax > tau) ? tau / rmax : 1.0;
     alpha_z = (zd > 0.0 && tau * zn < zd) ? tau * zn / zd : 1.0;

@@ -141,23 +141,24 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
                          double *result, double *traj_x, double *traj_y, double *full,
                          int *status, int *iters);
 
-/* Kernel selection.  MPC_KERNEL_AUTO (default): batches of at least MPC_LANE_MIN_BATCH problems, or
- * horizons above 32, run the throughput kernel (one problem per lane); smaller batches -- where the time is
- * set by the longest-running problem, not by throughput -- run the coop kernel (one problem per group of
- * 16/32 lanes, rows in shared memory).  The crossover was measured on B200 (profiles/r01_kernel_crossover.txt).
+/* Kernel selection.  MPC_KERNEL_AUTO (default): batches of at least MPC_LANE_MIN_BATCH problems (N <= 32) or more
+ * than MPC_COOP_MAX_BATCH_LONG problems (N > 32) run the throughput kernel (one problem per lane, tail handled as
+ * mpc_set_tail describes); smaller batches -- where the time is set by the longest-running problem, not by
+ * throughput -- run the coop kernel (one problem per group of 16/32 lanes, rows in shared memory; a lane holds one
+ * stage, or two for N > 32).  The crossover was measured on B200 (profiles/r01_kernel_crossover.txt).
  * lane_threads (CTA size 32..256, multiple of 32; 0 = automatic, balanced over the SMs) and
  * lane_ctas_per_sm (0 = one) tune the persistent grid of the lane kernel. */
 #define MPC_KERNEL_AUTO 0
 #define MPC_KERNEL_WARP 1   /* one problem per warp, stage per lane: the first version, kept as a cross-check (N <= 32) */
 #define MPC_KERNEL_LANE 2
-#define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory (N <= 32) */
-#define MPC_KERNEL_SOLO 4   /* one problem per lane of one-warp CTAs, rows in shared memory: few problems with N > 32 */
+#define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory */
+#define MPC_KERNEL_SOLO 4   /* one problem per lane of one-warp CTAs, rows in shared memory (kept as a cross-check) */
 #define MPC_LANE_MIN_BATCH 12288
-#define MPC_SOLO_MAX_BATCH 512   /* AUTO, N > 32: up to this many problems run the solo kernel */
+#define MPC_COOP_MAX_BATCH_LONG 8192   /* AUTO, N > 32: up to this many problems run the coop kernel */
 int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm);
 #define MPC_HANDOFF_MAX_BATCH 300000
 /* Iteration rule (off by default, `iterations` = 0).  Batches of MPC_LANE_MIN_BATCH .. MPC_HANDOFF_MAX_BATCH
- * problems with N <= 32: the lane kernel parks the problems that are still running after `iterations`
+ * problems: the lane kernel parks the problems that are still running after `iterations`
  * interior-point iterations and the launches that finish the tail (see mpc_set_tail) take them over.  13 is
  * the best value for the config-stable workload on its own (~6 % of the problems); with tail packing on it adds
  * nothing there and costs time on workloads whose iteration counts spread wider (weight sweeps).  All kernels
@@ -166,15 +167,18 @@ int mpc_set_handoff(mpc_handle *h, int iterations);
 /* Tail packing.  A warp of the lane kernel costs the same per trip whether 32 of its lanes hold a problem or one.
  * Once the work queue is empty, a warp with at most `park_lanes` problems left (default MPC_PARK_LANES_DEFAULT,
  * 0 = off) parks them; `resume_launches` further launches of the lane kernel (default MPC_RESUME_PHASES_DEFAULT)
- * pick the parked problems up 32 to a warp, and a final launch finishes what is left: the coop kernel for N <= 32,
- * one more lane-kernel launch for longer horizons.  All launches are on the caller's stream, results are
- * bit-identical for every setting.  Applies to batches of at least MPC_TAIL_MIN_BATCH problems.
- * sort_ragged (default 1): batches with N_per hand the problems out longest horizon first, so that the lanes of a
- * warp hold horizons of similar length. */
+ * pick the parked problems up 32 to a warp, and a final launch of the coop kernel finishes what is left.  All
+ * launches are on the caller's stream, results are bit-identical for every setting.  Applies to batches of at
+ * least MPC_TAIL_MIN_BATCH problems.
+ * flags (default MPC_TAIL_SORT_RAGGED): MPC_TAIL_SORT_RAGGED -- batches with N_per hand the problems out longest
+ * horizon first, so that the lanes of a warp hold horizons of similar length; MPC_TAIL_SOLO_FINISHER -- finish
+ * with the solo kernel instead of the coop kernel. */
 #define MPC_TAIL_MIN_BATCH 1024
 #define MPC_PARK_LANES_DEFAULT 16
 #define MPC_RESUME_PHASES_DEFAULT 2
-int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int sort_ragged);
+#define MPC_TAIL_SORT_RAGGED 1
+#define MPC_TAIL_SOLO_FINISHER 2
+int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int flags);
 
 /* Multiplier outputs for the following mpc_solve_batch calls on this handle (lane and coop kernels): DEVICE
  * buffers lambda [6*cfg.N][B] (solution.lambda, rows in the reference's constraint order MPC.cpp:116-153) and

@@ -306,31 +306,52 @@ def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
 
 
 def test_long_horizon_kernels_agree_bit_for_bit(mpc, stable_cd, refdata):
-    """N > 32 has no coop kernel: a few problems run the solo kernel (one problem per lane, rows in shared memory),
-    big batches the lane kernel with lane-kernel resume launches and the solo kernel as the finisher.  All of them
-    are the same arithmetic (the library is built without implicit multiply-add contraction), so: same bits."""
+    """N > 32: the coop kernel gives every lane of a 32-lane group two stages (neighbour values through the shared rows
+    instead of shuffles), the solo kernel runs the lane kernel's sweeps on rows in shared memory, and a big batch is the
+    lane kernel with resume launches and either of them as the finisher.  All of them are the same arithmetic (the
+    library is built without implicit multiply-add contraction), so: same bits -- including N = 64, the maximum, N = 33,
+    one stage into the second pass, and a horizon of 25 run through the two-stages-per-lane code."""
     import json
-    cfg = mpc.config_from_json_text(json.dumps(dict(refdata["configs"]["stable"], N=40, dt=0.05)))
+    for N, dt, B in ((40, 0.05, 3000), (64, 0.02, 1500), (33, 0.05, 1500)):
+        cfg = mpc.config_from_json_text(json.dumps(dict(refdata["configs"]["stable"], N=N, dt=dt)))
+        S = mpc.Solver(cfg, 0)
+        b = mpc.workloads.batch_perturbed_states(B, 17, cfg.as_dict())
+        args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+        S.set_kernel(mpc.KERNEL_LANE)
+        S.set_tail(0, 0)
+        ref = S.solve_batch_host(*args, want_full=True)
+        assert (ref["status"] == 1).mean() > 0.9
+        if N == 40:
+            assert ref["iters"].max() > 40
+        for kind, park, resume, solo in ((mpc.KERNEL_COOP, 0, 0, False), (mpc.KERNEL_SOLO, 0, 0, False), (mpc.KERNEL_LANE, 8, 0, False),
+                                         (mpc.KERNEL_LANE, 16, 2, True), (mpc.KERNEL_AUTO, 31, 1, False)):
+            S.set_kernel(kind)
+            S.set_tail(park, resume, True, solo)
+            got = S.solve_batch_host(*args, want_full=True)
+            for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
+                assert np.array_equal(got[k], ref[k]), (N, kind, park, resume, k)
+        # AUTO on a handful of long-horizon problems is the coop kernel: one launch
+        S.set_kernel(mpc.KERNEL_AUTO)
+        n0 = S.launches
+        few = S.solve_batch_host(*(a[:100] for a in args), want_full=True)
+        assert S.launches - n0 == 1
+        for k in ("result", "full", "status", "iters"):
+            assert np.array_equal(few[k], ref[k][:100]), k
+        S.close()
+    # per-problem horizons of 10..25 in a solver configured for N = 50: the NS = 64 kernels on short problems
+    cfg = mpc.config_from_json_text(json.dumps(dict(refdata["configs"]["stable"], N=50)))
     S = mpc.Solver(cfg, 0)
-    b = mpc.workloads.batch_perturbed_states(3000, 17, cfg.as_dict())
+    B = 2000
+    b = mpc.workloads.batch_perturbed_states(B, 29, cfg.as_dict())
+    Np = np.random.default_rng(3).choice([10, 16, 25, 32, 34, 50], B).astype(np.int32)
+    dtp = np.where(Np > 25, 0.02, 0.05)
     args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
-    S.set_kernel(mpc.KERNEL_LANE)
-    S.set_tail(0, 0)
-    ref = S.solve_batch_host(*args, want_full=True)
-    assert (ref["status"] == 1).mean() > 0.9 and ref["iters"].max() > 40
-    for kind, park, resume in ((mpc.KERNEL_SOLO, 0, 0), (mpc.KERNEL_LANE, 8, 0), (mpc.KERNEL_LANE, 16, 2), (mpc.KERNEL_AUTO, 31, 1)):
-        S.set_kernel(kind)
-        S.set_tail(park, resume)
-        got = S.solve_batch_host(*args, want_full=True)
-        for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
-            assert np.array_equal(got[k], ref[k]), (kind, park, resume, k)
-    # AUTO on a handful of long-horizon problems is the solo kernel: one launch
-    S.set_kernel(mpc.KERNEL_AUTO)
-    n0 = S.launches
-    few = S.solve_batch_host(*(a[:100] for a in args), want_full=True)
-    assert S.launches - n0 == 1
-    for k in ("result", "full", "status", "iters"):
-        assert np.array_equal(few[k], ref[k][:100]), k
+    S.set_kernel(mpc.KERNEL_LANE); S.set_tail(0, 0)
+    ref = S.solve_batch_host(*args, N_per=Np, dt_per=dtp)
+    S.set_kernel(mpc.KERNEL_COOP)
+    got = S.solve_batch_host(*args, N_per=Np, dt_per=dtp)
+    for k in ("result", "traj_x", "traj_y", "status", "iters"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
     S.close()
 
 
