@@ -22,7 +22,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 NCOEF, NTAB, NWEIGHTS, NMAX = 5, 16, 12, 64
 KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE, KERNEL_COOP, KERNEL_SOLO = 0, 1, 2, 3, 4
-LANE_MIN_BATCH = 12288
+LANE_MIN_BATCH = 9216
 
 STATUS_SUCCESS = 1
 STATUS_NAMES = {0: "not_defined", 1: "success", 2: "maxiter_exceeded", 3: "stop_at_tiny_step",

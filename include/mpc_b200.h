@@ -153,7 +153,7 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
 #define MPC_KERNEL_LANE 2
 #define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory */
 #define MPC_KERNEL_SOLO 4   /* one problem per lane of one-warp CTAs, rows in shared memory (kept as a cross-check) */
-#define MPC_LANE_MIN_BATCH 12288
+#define MPC_LANE_MIN_BATCH 9216
 #define MPC_COOP_MAX_BATCH_LONG 8192   /* AUTO, N > 32: up to this many problems run the coop kernel */
 int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm);
 #define MPC_HANDOFF_MAX_BATCH 300000
