@@ -477,8 +477,19 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   if (cap > (size_t)kp.B) cap = kp.B;
   if (!h->d_ckpt || h->cap_ckpt < cap || h->ckpt_ns != NS) {
     cudaFree(h->d_ckpt);
-    h->d_ckpt = nullptr;
-    CK(cudaMalloc(&h->d_ckpt, 2 * cap * rec * sizeof(double)));
+    h->d_ckpt = nullptr; h->cap_ckpt = 0;
+    // no memory for the record buffers (2.6 GB for the largest case, NS = 64): run without tail handling
+    while (cap >= 1024 && cudaMalloc(&h->d_ckpt, 2 * cap * rec * sizeof(double)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      h->d_ckpt = nullptr;
+      cap /= 4;
+    }
+    if (!h->d_ckpt) {
+      mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
+      CK(cudaGetLastError());
+      h->launches++;
+      return MPC_OK;
+    }
     h->cap_ckpt = cap; h->ckpt_ns = NS;
   }
   double *buf[2] = {h->d_ckpt, h->d_ckpt + h->cap_ckpt * rec};
