@@ -968,4 +968,4 @@ extern "C" int mpc_measure_fp64_peak(int device, double *tflops) {
 
 extern "C" long long mpc_launch_count(const mpc_handle *h) { return h ? h->launches : 0; }
 extern "C" const char *mpc_last_error(void) { return g_err; }
-extern "C" const char *mpc_version(void) { return "mpc_b200 0.1 (sm_100a, fp64 interior point, one problem per warp)"; }
+extern "C" const char *mpc_version(void) { return "mpc_b200 0.2 (sm_100a, fp64 interior point; lane, coop and solo kernels, explicit fma)"; }

@@ -82,9 +82,9 @@ def test_other_shipped_configs(mpc, po, refdata, name, kernel_kind):
                                   (25, 0.025), (30, 0.02), (32, 0.05), (40, 0.05), (50, 0.02), (64, 0.02)])
 def test_horizon_and_timestep_grid(mpc, po, refdata, N, dt, kernel_kind):
     """N x dt cells of the reference's examples/ grid (submission-report.md:250-265).  The warp kernel
-    holds one stage per lane (N <= 32); the lane kernel goes to MPC_NMAX = 64."""
-    if kernel_kind in (1, 3) and N > 32:
-        pytest.skip("warp / coop kernels: N <= 32")
+    holds one stage per lane (N <= 32); the lane, coop and solo kernels go to MPC_NMAX = 64."""
+    if kernel_kind == 1 and N > 32:
+        pytest.skip("warp kernel: N <= 32")
     js = dict(refdata["configs"]["stable"], N=N, dt=dt)
     cfg = mpc.config_from_json_text(json.dumps(js))
     cd = po.load_config_dict(js)
