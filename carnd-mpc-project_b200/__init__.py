@@ -33,7 +33,7 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
-           "mpc_rollout", "mpc_set_handoff", "mpc_set_tail", "mpc_set_dual_outputs", "mpc_config_from_cli",
+           "mpc_rollout", "mpc_set_handoff", "mpc_set_tail", "mpc_tail_counts", "mpc_set_dual_outputs", "mpc_config_from_cli",
            "mpc_telemetry_parse", "mpc_telemetry_step"]
 
 
@@ -119,6 +119,7 @@ def lib():
     L.mpc_set_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_set_handoff.argtypes = [vp, C.c_int]
     L.mpc_set_tail.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.mpc_tail_counts.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
     L.mpc_set_dual_outputs.argtypes = [vp, vp, vp, vp]
     L.mpc_telemetry_parse.argtypes = [C.c_char_p, C.POINTER(MpcTelemetry)]
     L.mpc_telemetry_step.argtypes = [vp, C.c_char_p, dp, C.c_double, C.c_int, C.c_char_p, C.c_int]
@@ -271,6 +272,12 @@ class Solver:
     def set_tail(self, park_lanes, resume_launches, sort_ragged=True, solo_finisher=False):
         """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches, ragged sort, finisher."""
         _check(lib().mpc_set_tail(self._h, int(park_lanes), int(resume_launches), (1 if sort_ragged else 0) | (2 if solo_finisher else 0)), "mpc_set_tail")
+
+    def tail_counts(self, n=4):
+        """Problems parked by each launch of the last lane-kernel chain (mpc_tail_counts)."""
+        out = (C.c_int * n)()
+        _check(lib().mpc_tail_counts(self._h, out, n), "mpc_tail_counts")
+        return list(out)
 
     def set_handoff(self, iterations):
         """Iteration count after which the lane kernel hands a problem to the coop kernel (0 = never)."""

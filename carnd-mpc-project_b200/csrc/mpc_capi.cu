@@ -966,6 +966,17 @@ extern "C" int mpc_measure_fp64_peak(int device, double *tflops) {
   return MPC_OK;
 }
 
+// records parked by launch k = 0, 1, ... of the last lane-kernel chain (synchronises the device)
+extern "C" int mpc_tail_counts(mpc_handle *h, int *parked, int n) {
+  if (!h || !parked || n < 0) return MPC_EINVAL;
+  int host[MPC_HIST0];
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host, h->d_counter, sizeof(host), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n; k++) parked[k] = (1 + 2 * k < MPC_HIST0) ? host[1 + 2 * k] : 0;
+  return MPC_OK;
+}
+
 extern "C" long long mpc_launch_count(const mpc_handle *h) { return h ? h->launches : 0; }
 extern "C" const char *mpc_last_error(void) { return g_err; }
 extern "C" const char *mpc_version(void) { return "mpc_b200 0.2 (sm_100a, fp64 interior point; lane, coop and solo kernels, explicit fma)"; }

@@ -179,6 +179,9 @@ int mpc_set_handoff(mpc_handle *h, int iterations);
 #define MPC_TAIL_SORT_RAGGED 1
 #define MPC_TAIL_SOLO_FINISHER 2
 int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int flags);
+/* accounting: parked[k] = problems parked by launch k (0 = main, 1.. = resume launches) of the last lane-kernel
+ * chain of this handle; synchronises the device */
+int mpc_tail_counts(mpc_handle *h, int *parked, int n);
 
 /* Multiplier outputs for the following mpc_solve_batch calls on this handle (lane and coop kernels): DEVICE
  * buffers lambda [6*cfg.N][B] (solution.lambda, rows in the reference's constraint order MPC.cpp:116-153) and
