@@ -33,7 +33,7 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_destroy", "mpc_set_config", "mpc_solve_batch", "mpc_solve_batch_host", "mpc_solve_one",
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
-           "mpc_rollout", "mpc_set_handoff", "mpc_set_tail", "mpc_tail_counts", "mpc_set_dual_outputs", "mpc_config_from_cli",
+           "mpc_rollout", "mpc_set_handoff", "mpc_set_tail", "mpc_tail_counts", "mpc_measure_solve_latency", "mpc_set_dual_outputs", "mpc_config_from_cli",
            "mpc_telemetry_parse", "mpc_telemetry_step"]
 
 
@@ -120,6 +120,7 @@ def lib():
     L.mpc_set_handoff.argtypes = [vp, C.c_int]
     L.mpc_set_tail.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_tail_counts.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
+    L.mpc_measure_solve_latency.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mpc_set_dual_outputs.argtypes = [vp, vp, vp, vp]
     L.mpc_telemetry_parse.argtypes = [C.c_char_p, C.POINTER(MpcTelemetry)]
     L.mpc_telemetry_step.argtypes = [vp, C.c_char_p, dp, C.c_double, C.c_int, C.c_char_p, C.c_int]
@@ -272,6 +273,16 @@ class Solver:
     def set_tail(self, park_lanes, resume_launches, sort_ragged=True, solo_finisher=False):
         """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches, ragged sort, finisher."""
         _check(lib().mpc_set_tail(self._h, int(park_lanes), int(resume_launches), (1 if sort_ragged else 0) | (2 if solo_finisher else 0)), "mpc_set_tail")
+
+    def measure_solve_latency(self, state, coeffs, yaw_lo, yaw_hi, reps=1000, warmup=200):
+        """(p50, p99) in microseconds of mpc_solve_one called from native code on the given problems ([n,6], [n,5], [n], [n])."""
+        st = np.ascontiguousarray(state, dtype=np.float64); co = np.ascontiguousarray(coeffs, dtype=np.float64)
+        yl = np.ascontiguousarray(yaw_lo, dtype=np.float64); yh = np.ascontiguousarray(yaw_hi, dtype=np.float64)
+        assert co.shape[1] == NCOEF and st.shape[1] == 6
+        p50, p99 = C.c_double(0), C.c_double(0)
+        _check(lib().mpc_measure_solve_latency(self._h, st.shape[0], st.ctypes.data, co.ctypes.data, yl.ctypes.data, yh.ctypes.data,
+                                               reps, warmup, C.byref(p50), C.byref(p99)), "mpc_measure_solve_latency")
+        return p50.value, p99.value
 
     def tail_counts(self, n=4):
         """Problems parked by each launch of the last lane-kernel chain (mpc_tail_counts)."""

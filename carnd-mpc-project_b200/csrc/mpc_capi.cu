@@ -7,6 +7,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -767,6 +769,31 @@ extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *c
   if (traj_y) for (int k = 0; k < N; k++) traj_y[k] = ho[9 + N + k];
   if (status) *status = hi[0];
   if (iters) *iters = hi[1];
+  return MPC_OK;
+}
+
+// Native latency of mpc_solve_one: reps calls, problem k % n of the given set each, timed one by one on the host
+// clock around the call (what a C++ caller of MPC::solve sees; the Python binding adds its own argument marshalling).
+extern "C" int mpc_measure_solve_latency(mpc_handle *h, int n, const double *state, const double *coeffs,
+                                         const double *yaw_lo, const double *yaw_hi, int reps, int warmup,
+                                         double *p50_us, double *p99_us) {
+  if (!h || n < 1 || !state || !coeffs || !yaw_lo || !yaw_hi || reps < 1 || warmup < 0 || !p50_us || !p99_us) return MPC_EINVAL;
+  std::vector<double> t;
+  t.reserve(reps);
+  double res[9];
+  int status = 0, iters = 0;
+  for (int k = 0; k < warmup + reps; k++) {
+    const int i = k % n;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = mpc_solve_one(h, state + 6 * (size_t)i, coeffs + MPC_NCOEF * (size_t)i, yaw_lo[i], yaw_hi[i], res, nullptr, nullptr,
+                           &status, &iters);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc) return rc;
+    if (k >= warmup) t.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+  }
+  std::sort(t.begin(), t.end());
+  *p50_us = t[t.size() / 2];
+  *p99_us = t[(size_t)((t.size() - 1) * 0.99)];
   return MPC_OK;
 }
 

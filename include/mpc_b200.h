@@ -195,6 +195,12 @@ int mpc_set_dual_outputs(mpc_handle *h, double *lambda, double *zl, double *zu);
 int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs,
                   double yaw_lo, double yaw_hi,
                   double *result, double *traj_x, double *traj_y, int *status, int *iters);
+/* Latency of mpc_solve_one measured in native code: `reps` calls after `warmup`, problem k % n of the given set
+ * ([n][6] states, [n][MPC_NCOEF] coefficients, row-major), host clock around each call; median and 99th percentile
+ * in microseconds.  bench.py reports it beside the latency seen through the Python binding. */
+int mpc_measure_solve_latency(mpc_handle *h, int n, const double *state, const double *coeffs,
+                              const double *yaw_lo, const double *yaw_hi, int reps, int warmup,
+                              double *p50_us, double *p99_us);
 
 /* ---- one control step around the solve: MPC::run (MPC.cpp:327-382), host-side, pure functions ---- */
 #define MPC_MAX_WAYPOINTS 16
