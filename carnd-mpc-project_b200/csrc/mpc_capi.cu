@@ -547,13 +547,12 @@ static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
   const int G = NS <= 16 ? 16 : 32;
   const int groups = threads / G;
   const size_t smem = (size_t)groups * NS * ST_ROW_SH * sizeof(double);
-  static thread_local int cached_dev = -1;
+  static thread_local int cached_dev = -1, per_sm = 0;
   if (cached_dev != h->device) {
     CK(cudaFuncSetAttribute(mpc_coop_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<NS>, threads, smem));
     cached_dev = h->device;
   }
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<NS>, threads, smem));
   if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "coop kernel does not fit on an SM (smem %zu)", smem); return MPC_ECUDA; }
   long long want = ((long long)kp.B + groups - 1) / groups;
   long long grid = (long long)h->sm_count * per_sm;
