@@ -426,7 +426,7 @@ def main():
                        "sharding": "independent batch shard per rank, no collective in the solve; one all_gather of result[9][B] per step" if world > 1 else "single GPU"},
             "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "mpc_lane_kernel<10,1,false> (one problem per lane; dominant) + the launches that finish its tail: 2x mpc_lane_kernel<10,1,true> (parked problems, 32 to a warp) + mpc_coop_resume_kernel<10>; %d launches per step, kernel_ms is their sum" % (launches // args.steps) if B >= mpc.LANE_MIN_BATCH else "mpc_coop_kernel<10> (one problem per group of 16 lanes)",
+                         "kernel": "mpc_lane_kernel<10,1,false> (one problem per lane; dominant) + the launches that finish its tail: up to 3x mpc_lane_kernel<10,1,true> (parked problems, 32 to a warp; each returns at once when at most 8192 are parked) + mpc_coop_resume_kernel<10>; %d launches per step, kernel_ms is their sum" % (launches // args.steps) if B >= mpc.LANE_MIN_BATCH else "mpc_coop_kernel<10> (one problem per group of 16 lanes)",
                          "peak_source": "measured in this run by mpc_measure_fp64_peak (DFMA chains; MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_launch": flops_per_launch, "flops_model": "sum_b iters_b * F_iter(N), F_iter(10)=17505 (SURVEY.md 8d)",
                          "kernel_ms": kernel_ms},

@@ -54,6 +54,7 @@ struct mpc_handle {
   int handoff_iter;     // rule 1: lane kernel parks problems still running after this many iterations (0 = never, the default)
   int park_lanes;       // tail packing: a warp with at most this many problems left parks them once the queue is empty (0 = off)
   int resume_phases;    // lane-kernel resume launches between the main launch and the final one
+  int resume_min;       // a resume launch with no more than this many records to work on leaves them to the next launch
   double *d_ckpt;       // migration records, two buffers of cap_ckpt records (each launch of a chain reads one, writes the other)
   size_t cap_ckpt;      // records per buffer
   int ckpt_ns;
@@ -317,6 +318,7 @@ extern "C" int mpc_create(const mpc_config *cfg, int device, mpc_handle **out) {
   h->sort_ragged = true;
   h->park_lanes = MPC_PARK_LANES_DEFAULT;
   h->resume_phases = MPC_RESUME_PHASES_DEFAULT;
+  h->resume_min = MPC_RESUME_MIN_DEFAULT;
   *out = h;
   return MPC_OK;
 }
@@ -498,26 +500,28 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   kp.ckpt_cap = (int)cap;
   kp.ckpt = buf[0]; kp.ckpt_count = cnt;
   kp.park_lanes = park; kp.handoff_iter = rule1 ? h->handoff_iter : INT_MAX;
+  kp.chain_counts = cnt; kp.chain_buf0 = buf[0]; kp.chain_buf1 = buf[1];
+  kp.chain_pos = 0; kp.chain_last = phases + 1; kp.resume_min = h->resume_min;
   mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
   CK(cudaGetLastError());
   h->launches++;
-  // resume launches: enough lanes for a full buffer in one pass, dealt over all SMs
+  // resume launches: enough lanes for a full buffer in one pass, dealt over all SMs.  Each works out on the device
+  // which buffer holds the live records (chain_resolve) and returns at once if there are too few to be worth a pass.
   int rthreads = (int)(((cap + h->sm_count - 1) / h->sm_count + 31) / 32) * 32;
   if (rthreads > 256) rthreads = 256;
   long long rgrid = ((long long)cap + rthreads - 1) / rthreads;
   if (rgrid > h->sm_count) rgrid = h->sm_count;
   kp.handoff_iter = INT_MAX;
   kp.perm = nullptr;
+  kp.ckpt = nullptr; kp.ckpt_count = nullptr;
   for (int k = 1; k <= phases; k++) {
-    kp.ckpt_in = buf[(k - 1) & 1]; kp.ckpt_in_count = cnt + 2 * (k - 1);
-    kp.ckpt = buf[k & 1]; kp.ckpt_count = cnt + 2 * k;
-    kp.park_lanes = park;
+    kp.chain_pos = k;
     mpc_lane_kernel<NS, MINB, true><<<(unsigned)rgrid, rthreads, 0, st>>>(kp);
     CK(cudaGetLastError());
     h->launches++;
   }
-  kp.ckpt = buf[phases & 1]; kp.ckpt_count = cnt + 2 * phases; kp.ckpt_next = cnt + 2 * phases + 1;
-  kp.ckpt_in = nullptr; kp.park_lanes = 0;
+  kp.chain_pos = phases + 1;
+  kp.park_lanes = 0;
   if (h->solo_finisher) {
     return launch_solo<NS, true>(h, kp, st, (long long)kp.ckpt_cap);
   } else {
@@ -578,10 +582,11 @@ extern "C" int mpc_set_handoff(mpc_handle *h, int iterations) {
   return MPC_OK;
 }
 
-extern "C" int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int flags) {
-  if (!h || park_lanes < 0 || park_lanes > 31 || resume_launches < 0 || resume_launches > MPC_MAX_PHASES) return MPC_EINVAL;
+extern "C" int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int resume_min_records, int flags) {
+  if (!h || park_lanes < 0 || park_lanes > 31 || resume_launches < 0 || resume_launches > MPC_MAX_PHASES || resume_min_records < 0) return MPC_EINVAL;
   h->park_lanes = park_lanes;
   h->resume_phases = resume_launches;
+  h->resume_min = resume_min_records;
   h->sort_ragged = (flags & MPC_TAIL_SORT_RAGGED) != 0;
   h->solo_finisher = (flags & MPC_TAIL_SOLO_FINISHER) != 0;
   return MPC_OK;

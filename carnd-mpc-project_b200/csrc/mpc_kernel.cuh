@@ -94,6 +94,12 @@ struct KParams {
   int park_lanes;
   const double *ckpt_in;
   const int *ckpt_in_count;
+  // a chain of launches (main, resume..., final): counters [2j] = records parked by launch j, [2j + 1] = cursor of
+  // launch j over its input; the two record buffers; this launch's position, the final launch's, and the number of
+  // records below which a resume launch leaves them to the next launch
+  int *chain_counts;
+  double *chain_buf0, *chain_buf1;
+  int chain_pos, chain_last, resume_min;
   const int *perm;   // order in which the work queue hands out the problems (ragged batches: longest horizon first), or NULL
   // optional multiplier outputs (solution.lambda / zl / zu of CppAD::ipopt::solve_result), unscaled
   double *dual_lam, *dual_zl, *dual_zu;

@@ -1750,6 +1750,28 @@ struct Lane {
   }
 };
 
+// Which records does launch chain_pos of a chain work on, and where does it park?  A resume launch that would find
+// no more than resume_min records does nothing -- the final launch copes with that many at a lower cost than another
+// pass of the lane kernel -- so the records stay where they are; every launch replays those decisions from the
+// counters of the launches before it (all final: same stream).  No host round trip anywhere in a chain.
+struct ChainIO { const double *in; int n; double *out; int *out_count; int *cursor; bool run; };
+__device__ __forceinline__ ChainIO chain_resolve(const KParams &P) {
+  int slot = 0, buf = 0;
+  ChainIO io;
+  for (int j = 1;; j++) {
+    int n = P.chain_counts[2 * slot];
+    if (n > P.ckpt_cap) n = P.ckpt_cap;
+    const bool run = j == P.chain_last || n > P.resume_min;
+    if (j >= P.chain_pos) {
+      io.in = buf ? P.chain_buf1 : P.chain_buf0; io.n = n;
+      io.out = buf ? P.chain_buf0 : P.chain_buf1; io.out_count = P.chain_counts + 2 * j; io.cursor = P.chain_counts + 2 * j + 1;
+      io.run = run;
+      return io;
+    }
+    if (run) { slot = j; buf ^= 1; }
+  }
+}
+
 // Persistent grid, one CTA per SM; every lane pulls problems from the global counter until the batch is
 // exhausted.  The warps of a CTA start every trip together (the exit vote is a __syncthreads): the loop
 // body is ~100 KB of code, and warps at unrelated places in it thrash the instruction cache
@@ -1772,9 +1794,13 @@ __global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
   Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;
   Z.lh_stale = false; Z.no_handoff = false;
   int n_in = 0, next_in = 0;
+  double *park_buf = P.ckpt;
+  int *park_count = P.ckpt_count;
+  const double *rec_in = nullptr;
   if (RESUME) {
-    n_in = *P.ckpt_in_count;
-    if (n_in > P.ckpt_cap) n_in = P.ckpt_cap;
+    const ChainIO io = chain_resolve(P);
+    if (!io.run) return;
+    n_in = io.n; rec_in = io.in; park_buf = io.out; park_count = io.out_count;
     next_in = (int)(((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31));
   }
   for (;;) {
@@ -1785,19 +1811,19 @@ __global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
     for (int pass = 0; pass < 2; pass++) {
       unsigned live = 0xffffffffu;
       if (pass == 1) live = __ballot_sync(0xffffffffu, Z.mode != LM_DONE);
-      const bool can = P.ckpt && Z.mode != LM_IDLE && Z.mode != LM_DONE && !Z.no_handoff;
+      const bool can = park_buf && Z.mode != LM_IDLE && Z.mode != LM_DONE && !Z.no_handoff;
       // rule 2: a lane is only ever DONE when the queue had nothing left for it
       const bool park = can && (pass == 0 ? Z.iter >= P.handoff_iter
                                           : (live != 0xffffffffu && __popc(live) <= P.park_lanes));
       if (park) {
-        const int slot = atomicAdd(P.ckpt_count, 1);
-        if (slot < P.ckpt_cap) { Z.save(P.ckpt + (size_t)slot * Lane<NS, false>::CK_SIZE); Z.mode = pass == 0 ? LM_IDLE : LM_DONE; }
+        const int slot = atomicAdd(park_count, 1);
+        if (slot < P.ckpt_cap) { Z.save(park_buf + (size_t)slot * Lane<NS, false>::CK_SIZE); Z.mode = pass == 0 ? LM_IDLE : LM_DONE; }
         else Z.no_handoff = true;
       }
       if (pass == 0 && Z.mode == LM_IDLE) {
         Z.no_handoff = false;
         if (RESUME) {
-          if (next_in < n_in) { Z.load(P.ckpt_in + (size_t)next_in * Lane<NS, false>::CK_SIZE); next_in += (int)(gridDim.x * blockDim.x); }
+          if (next_in < n_in) { Z.load(rec_in + (size_t)next_in * Lane<NS, false>::CK_SIZE); next_in += (int)(gridDim.x * blockDim.x); }
           else Z.mode = LM_DONE;
         } else {
           const int nb = atomicAdd(P.counter, 1);
@@ -1865,14 +1891,14 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_resume_kernel(const KParams P
   Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
   Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
   Z.no_handoff = true;
-  int n = *P.ckpt_count;
-  if (n > P.ckpt_cap) n = P.ckpt_cap;
+  const ChainIO io = chain_resolve(P);
+  const int n = io.n;
   for (;;) {
     int k = 0;
-    if (Z.g0 == 0) k = atomicAdd(P.ckpt_next, 1);
+    if (Z.g0 == 0) k = atomicAdd(io.cursor, 1);
     k = __shfl_sync(Z.gm, k, 0, G);
     if (k >= n) break;
-    Z.load(P.ckpt + (size_t)k * Lane<NS, true>::CK_SIZE);
+    Z.load(io.in + (size_t)k * Lane<NS, true>::CK_SIZE);
     while (Z.mode != LM_FINISH) {
       Z.trip_eval();
       Z.trip_accept(P);
@@ -1902,16 +1928,18 @@ __global__ void __launch_bounds__(32, 1) mpc_solo_kernel(const KParams P, int la
   Z.ST = reinterpret_cast<double (*)[ST_ROW]>(solo_smem + (size_t)(has ? threadIdx.x : 0) * NS * ST_ROW);
   Z.mode = has ? LM_IDLE : LM_DONE;
   int n = P.B;
+  const double *rec_in = nullptr;
+  int *cursor = P.counter;
   if (RESUME) {
-    n = *P.ckpt_count;
-    if (n > P.ckpt_cap) n = P.ckpt_cap;
+    const ChainIO io = chain_resolve(P);
+    n = io.n; rec_in = io.in; cursor = io.cursor;
   }
   for (;;) {
     if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
     if (Z.mode == LM_IDLE) {
-      const int k = atomicAdd(RESUME ? P.ckpt_next : P.counter, 1);
+      const int k = atomicAdd(cursor, 1);
       if (k >= n) Z.mode = LM_DONE;
-      else if (RESUME) Z.load(P.ckpt + (size_t)k * Lane<NS, true, false>::CK_SIZE);
+      else if (RESUME) Z.load(rec_in + (size_t)k * Lane<NS, true, false>::CK_SIZE);
       else Z.init(P, P.perm ? P.perm[k] : k);
     }
     if (__all_sync(0xffffffffu, Z.mode == LM_DONE)) break;

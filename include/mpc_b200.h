@@ -166,8 +166,10 @@ int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_
 int mpc_set_handoff(mpc_handle *h, int iterations);
 /* Tail packing.  A warp of the lane kernel costs the same per trip whether 32 of its lanes hold a problem or one.
  * Once the work queue is empty, a warp with at most `park_lanes` problems left (default MPC_PARK_LANES_DEFAULT,
- * 0 = off) parks them; `resume_launches` further launches of the lane kernel (default MPC_RESUME_PHASES_DEFAULT)
- * pick the parked problems up 32 to a warp, and a final launch of the coop kernel finishes what is left.  All
+ * 0 = off) parks them; up to `resume_launches` further launches of the lane kernel (default
+ * MPC_RESUME_PHASES_DEFAULT) pick the parked problems up 32 to a warp -- each decides on the device whether there are
+ * more than `resume_min_records` of them (default MPC_RESUME_MIN_DEFAULT), and otherwise returns at once -- and a
+ * final launch of the coop kernel finishes what is left.  All
  * launches are on the caller's stream, results are bit-identical for every setting.  Applies to batches of at
  * least MPC_TAIL_MIN_BATCH problems.
  * flags (default MPC_TAIL_SORT_RAGGED): MPC_TAIL_SORT_RAGGED -- batches with N_per hand the problems out longest
@@ -175,10 +177,11 @@ int mpc_set_handoff(mpc_handle *h, int iterations);
  * with the solo kernel instead of the coop kernel. */
 #define MPC_TAIL_MIN_BATCH 1024
 #define MPC_PARK_LANES_DEFAULT 16
-#define MPC_RESUME_PHASES_DEFAULT 2
+#define MPC_RESUME_PHASES_DEFAULT 3
+#define MPC_RESUME_MIN_DEFAULT 8192
 #define MPC_TAIL_SORT_RAGGED 1
 #define MPC_TAIL_SOLO_FINISHER 2
-int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int flags);
+int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int resume_min_records, int flags);
 /* accounting: parked[k] = problems parked by launch k (0 = main, 1.. = resume launches) of the last lane-kernel
  * chain of this handle; synchronises the device */
 int mpc_tail_counts(mpc_handle *h, int *parked, int n);

@@ -298,6 +298,20 @@ def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
         assert S.launches - n0 == 2 + resume
         for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
             assert np.array_equal(got[k], ref[k]), (hand, park, resume, k)
+    # resume launches that find too few parked problems return at once and leave them to the next launch: any
+    # threshold -- none skipped, some skipped, all skipped -- same bits, and the counters show who did the work
+    for rmin in (0, 1500, 100000):
+        S.set_handoff(0)
+        S.set_tail(16, 3, True, False, rmin)
+        got = S.solve_batch_host(*args, want_full=True)
+        for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
+            assert np.array_equal(got[k], ref[k]), (rmin, k)
+        parked = S.tail_counts(4)
+        assert parked[0] > 0
+        if rmin == 0:
+            assert parked[1] > 0
+        if rmin == 100000:
+            assert parked[1:] == [0, 0, 0]
     with pytest.raises(mpc.MpcError):
         S.set_tail(32, 0)
     with pytest.raises(mpc.MpcError):
@@ -542,7 +556,7 @@ def test_repeated_runs_give_the_same_bits(mpc, stable_cfg, stable_cd):
         torch.cuda.synchronize()
         if rep == 0:
             ref = (res, tx, st, it)
-            assert S.launches == 4 and sum(S.tail_counts(3)) > 0       # the chain ran and parked problems
+            assert S.launches == 5 and sum(S.tail_counts(4)) > 0       # main + 3 resume + final launches; problems were parked
         else:
             assert all(torch.equal(a, b_) for a, b_ in zip(ref, (res, tx, st, it))), rep
     S.close()

@@ -20,8 +20,9 @@ def sweep(name, S, B, call, settings, reps):
     res = torch.zeros(9, B, dtype=torch.float64, device=dev)
     st = torch.zeros(B, dtype=torch.int32, device=dev); it = torch.zeros(B, dtype=torch.int32, device=dev)
     ref = None
-    for hand, park, ph, srt in (only or settings):
-        S.set_handoff(hand); S.set_tail(park, ph, srt)
+    for tup in (only or settings):
+        hand, park, ph, srt = tup[:4]; rmin = tup[4] if len(tup) > 4 else 0
+        S.set_handoff(hand); S.set_tail(park, ph, srt, False, rmin)
         res.zero_(); st.zero_(); it.zero_()
         l0 = S.launches
         ms = timed(lambda: call(S, res, st, it), reps)
@@ -29,8 +30,8 @@ def sweep(name, S, B, call, settings, reps):
         cur = (res.clone(), st.clone(), it.clone())
         if ref is None: ref = cur
         same = all(torch.equal(a, b) for a, b in zip(ref, cur))
-        print('%s B=%d handoff=%2d park=%2d resume=%d sort=%d  %8.3f ms  %10.0f solves/s  launches %d  ok=%.4f iters max %d  identical=%s' % (
-            name, B, hand, park, ph, srt, ms, B / ms * 1e3, nl, (st == 1).float().mean().item(), it.max().item(), same), flush=True)
+        print('%s B=%d handoff=%2d park=%2d resume=%d sort=%d rmin=%5d  %8.3f ms  %10.0f solves/s  launches %d  ok=%.4f iters max %d  identical=%s' % (
+            name, B, hand, park, ph, srt, rmin, ms, B / ms * 1e3, nl, (st == 1).float().mean().item(), it.max().item(), same), flush=True)
 cfg = mpc.config_from_json_text(json.dumps(js))
 cd = cfg.as_dict()
 if "1" in which:
