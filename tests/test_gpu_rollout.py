@@ -90,6 +90,36 @@ def test_rollout_matches_cpu_restatement(mpc, po, refdata, name, tau):
     assert (np.hypot(veh[0] - veh0[0], veh[1] - veh0[1]) > 10).all()
 
 
+def test_big_fleet_rollout_uses_the_lane_chain_and_agrees_with_the_coop_kernel(mpc, refdata):
+    """More vehicles than the coop/lane crossover: every control step of mpc_rollout is then the lane kernel with its
+    resume launches and finisher (several launches per step on one stream, counters reset each step); the
+    closed-loop record must be the one the coop kernel produces, bit for bit."""
+    import torch
+    cfg = mpc.config_from_json_text(json.dumps(refdata["configs"]["fast"]))
+    cd = cfg.as_dict()
+    wx, wy = np.array(refdata["waypoints"]["x"]), np.array(refdata["waypoints"]["y"])
+    V, T = mpc.LANE_MIN_BATCH + 1000, 6
+    b = mpc.workloads.batch_perturbed_states(V, 3, cd)
+    recs = {}
+    for kind in (mpc.KERNEL_COOP, mpc.KERNEL_AUTO):
+        S = mpc.Solver(cfg, 0)
+        S.set_kernel(kind)
+        veh = _dev(np.stack([b["px"], b["py"], b["psi"], np.clip(b["v"], 8, 30), np.zeros(V), np.zeros(V)]))
+        seg = _dev(b["segment"].astype(np.int32))
+        pending = torch.zeros(2, V, dtype=torch.float64, device="cuda")
+        rec = torch.zeros(T, 8, V, dtype=torch.float64, device="cuda")
+        n0 = S.launches
+        S.rollout_device(V, T, _dev(wx), _dev(wy), veh, seg, pending, 0.1, 0.02, rec)
+        torch.cuda.synchronize()
+        per_step = (S.launches - n0) // T
+        assert per_step == (3 if kind == mpc.KERNEL_COOP else 7)      # pre, solve (1 or 5 launches), post
+        recs[kind] = (rec.clone(), veh.clone(), seg.clone())
+        S.close()
+    for a, c in zip(recs[mpc.KERNEL_COOP], recs[mpc.KERNEL_AUTO]):
+        assert torch.equal(a, c)
+    assert (recs[mpc.KERNEL_AUTO][0][:, 6] == 1).float().mean().item() > 0.99
+
+
 def test_telemetry_replay_matches_restated_handler(mpc, po, refdata):
     """Recorded-style SocketIO text through mpc_telemetry_step == the message handler of mpc_main.cpp:99-214
     restated on the CPU (unit/sign conversions, latency move, MPC::run, throttle), several messages in a row so
