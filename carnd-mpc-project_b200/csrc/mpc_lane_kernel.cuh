@@ -75,11 +75,12 @@ enum { ST_S = 0,      // iterate: x, y, psi, v, cte, epsi
        ST_CN = 30,    // c_{i+1} at the iterate
        ST_DS = 36,    // primal search direction
        ST_DU = 42,
-       ST_TT = 44,    // TG / CN at the trial point (copied on acceptance)
-       ST_CT = 52,
-       ST_KG = 58,    // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
-       ST_CS = 70,    // second-order-correction right-hand side (rare path only)
-       ST_ROW = 78,   // thread-private rows (76 used, padded to a multiple of 16 bytes that is not one of 64)
+       ST_KG = 44,    // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
+       ST_CS = 56,    // second-order-correction right-hand side (rare path only)
+       ST_KEEP = 62,  // what is live at a trip boundary: the rows of the one-problem-per-lane kernels, and of a record
+       ST_ROW = 62,   // thread-private / solo rows (a multiple of 16 bytes that is not one of 64)
+       ST_TT = 62,    // coop kernel only: TG / CN at the trial point, handed from the evaluation to the acceptance sweep
+       ST_CT = 70,    //   (the one-problem-per-lane kernels recompute them there instead: 14 doubles less per stage to stream)
        ST_LH = 76,    // coop kernel only: StageLin (10) + StageHess (18) of the stage, built one stage per lane
        ST_ROW_SH = 106 };   // shared-memory rows: 104 used; 106 keeps neighbouring lanes' rows 2-way bank-conflict free
 template <int NS, bool SH, bool PAR> struct LaneRows { typedef double type[NS][ST_ROW]; enum { ROW = ST_ROW }; };
@@ -324,7 +325,7 @@ struct Lane {
         for (int k = 0; k < 6; k++) { const double c = s[k] - PC[LC_S0 + k]; c0t[k] = c; th += fabs(c); }
       } else {
 #pragma unroll
-        for (int k = 0; k < 6; k++) { const double c = s[k] - F[k]; ST[i - 1][ST_CT + k] = c; th += fabs(c); }
+        for (int k = 0; k < 6; k++) th += fabs(s[k] - F[k]);
       }
       const double dv = s[3] - vref(i);
       fl = fma(0.5, fma(nv2(i) * s[3], s[3], fma(PC[LC_WV2] * dv, dv, fma(we2(i) * s[5], s[5], wc2(i) * s[4] * s[4]))), fl);
@@ -333,8 +334,6 @@ struct Lane {
         const double u0 = fma(a, ST[i][ST_DU + 0], ST[i][ST_U + 0]), u1 = fma(a, ST[i][ST_DU + 1], ST[i][ST_U + 1]);
         double tg[8];
         point_eval(s, u0, u1, tg, F);
-#pragma unroll
-        for (int k = 0; k < 8; k++) ST[i][ST_TT + k] = tg[k];
         fl = fma(0.5 * PC[LC_WD2] * u0, u0, fl);
         if (i >= 1) { const double dd = u0 - dprev; fl = fma(0.5 * PC[LC_CW] * dd, dd, fl); }
         dprev = u0;
@@ -451,10 +450,29 @@ struct Lane {
   __device__ void soc_rhs(bool first, double a) {
 #pragma unroll
     for (int k = 0; k < 6; k++) cs0[k] = a * (first ? c0[k] : cs0[k]) + c0t[k];
+    if (PAR) {
 #pragma unroll 1
-    for (int i = g0; i < N - 1; i += gstep) {
+      for (int i = g0; i < N - 1; i += gstep) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) ST[i][ST_CS + k] = a * (first ? ST[i][ST_CN + k] : ST[i][ST_CS + k]) + ST[i][ST_CT + k];
+        for (int k = 0; k < 6; k++) ST[i][ST_CS + k] = a * (first ? ST[i][ST_CN + k] : ST[i][ST_CS + k]) + ST[i][ST_CT + k];
+      }
+    } else {
+      // the residuals of the trial point just evaluated (step a along DS) are not kept: recompute them
+      double F[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+      for (int i = 0; i < N; i++) {
+        double t[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) t[k] = fma(a, ST[i][ST_DS + k], ST[i][ST_S + k]);
+        if (i >= 1) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) ST[i - 1][ST_CS + k] = a * (first ? ST[i - 1][ST_CN + k] : ST[i - 1][ST_CS + k]) + (t[k] - F[k]);
+        }
+        if (i < N - 1) {
+          double tg[8];
+          point_eval(t, fma(a, ST[i][ST_DU + 0], ST[i][ST_U + 0]), fma(a, ST[i][ST_DU + 1], ST[i][ST_U + 1]), tg, F);
+        }
+      }
     }
     gsync();
   }
@@ -478,6 +496,7 @@ struct Lane {
     double lp_n[6] = {0, 0, 0, 0, 0, 0};   // lambda+ of stage i+1
     double ln_n[6] = {0, 0, 0, 0, 0, 0};   // NEW multipliers of stage i+1
     double dnext = 0.0;                    // NEW delta_{i+1}
+    double sn[6] = {0, 0, 0, 0, 0, 0};     // NEW state of stage i+1
     double r = 0.0, cv = 0.0, l1 = 0.0, zz = 0.0, am = 1e300, aM = 0.0, lmax = 0.0;
 #pragma unroll 1
     for (int i = N - 1; i >= 0; i--) {
@@ -566,16 +585,21 @@ struct Lane {
       double cn[6] = {0, 0, 0, 0, 0, 0};
       if (hasu) {
         if (do_update) {
+          // the trial point the evaluation sweep accepted is the new iterate: same inputs, same bits
+          double F[6];
+          point_eval(s, u0, u1, tg, F);
 #pragma unroll
-          for (int k = 0; k < 6; k++) { cn[k] = ST[i][ST_CT + k]; ST[i][ST_CN + k] = cn[k]; }
+          for (int k = 0; k < 6; k++) { cn[k] = sn[k] - F[k]; ST[i][ST_CN + k] = cn[k]; }
 #pragma unroll
-          for (int k = 0; k < 8; k++) { tg[k] = ST[i][ST_TT + k]; ST[i][ST_TG + k] = tg[k]; }
+          for (int k = 0; k < 8; k++) ST[i][ST_TG + k] = tg[k];
           lin_at(tg, s[3], u0, L);
         } else {
 #pragma unroll
           for (int k = 0; k < 6; k++) cn[k] = ST[i][ST_CN + k];
         }
       }
+#pragma unroll
+      for (int k = 0; k < 6; k++) sn[k] = s[k];
       if (i == 0 && do_update) {
 #pragma unroll
         for (int k = 0; k < 6; k++) c0[k] = c0t[k];
@@ -1584,12 +1608,12 @@ struct Lane {
   // ---- migration: the complete state of a problem at a trip boundary as a flat record of doubles.  The
   // lane kernel and the coop kernel run the same arithmetic on the same state, so a problem can be moved
   // from one to the other between any two trips without changing a single bit of its result.
-  enum { CK_ROWS = NS * 76, CK_PC = CK_ROWS, CK_FLT = CK_PC + LC_SIZE, CK_C = CK_FLT + 2 * K_NFILT, CK_D = CK_C + 18,
+  enum { CK_ROWS = NS * ST_KEEP, CK_PC = CK_ROWS, CK_FLT = CK_PC + LC_SIZE, CK_C = CK_FLT + 2 * K_NFILT, CK_D = CK_C + 18,
          CK_I = CK_D + 32, CK_SIZE = CK_I + 12 };
   __device__ void save(double *r) const {
 #pragma unroll 1
     for (int i = g0; i < N; i += gstep)
-      for (int k = 0; k < 76; k++) r[i * 76 + k] = ST[i][k];
+      for (int k = 0; k < ST_KEEP; k++) r[i * ST_KEEP + k] = ST[i][k];
     if (g0 != 0) return;
     for (int k = 0; k < LC_SIZE; k++) r[CK_PC + k] = PC[k];
     for (int k = 0; k < 2 * K_NFILT; k++) r[CK_FLT + k] = FLT[k];
@@ -1605,7 +1629,7 @@ struct Lane {
     N = (int)r[CK_I + 1];
 #pragma unroll 1
     for (int i = g0; i < N; i += gstep)
-      for (int k = 0; k < 76; k++) ST[i][k] = r[i * 76 + k];
+      for (int k = 0; k < ST_KEEP; k++) ST[i][k] = r[i * ST_KEEP + k];
     for (int k = 0; k < LC_SIZE; k++) PC[k] = r[CK_PC + k];
     for (int k = 0; k < 2 * K_NFILT; k++) FLT[k] = r[CK_FLT + k];
     for (int k = 0; k < 6; k++) { c0[k] = r[CK_C + k]; c0t[k] = r[CK_C + 6 + k]; cs0[k] = r[CK_C + 12 + k]; }
