@@ -315,11 +315,24 @@ struct Lane {
     const double lo_d = PC[LC_LO + 2], hi_d = PC[LC_HI + 2], lo_a = PC[LC_LO + 3], hi_a = PC[LC_HI + 3];
     double F[6] = {0, 0, 0, 0, 0, 0};
     double th = 0.0, fl = 0.0, ll = 0.0, dprev = 0.0;
+    // the rows are a long way off (L2 or DRAM): the trial point of stage i+1 is loaded and formed at the top of
+    // iteration i, so that its latency runs under the transcendental work of stage i instead of being waited for
+    double sN[6], uN0, uN1;
+#pragma unroll
+    for (int k = 0; k < 6; k++) sN[k] = fma(a, ST[0][ST_DS + k], ST[0][ST_S + k]);
+    uN0 = fma(a, ST[0][ST_DU + 0], ST[0][ST_U + 0]); uN1 = fma(a, ST[0][ST_DU + 1], ST[0][ST_U + 1]);
 #pragma unroll 1
     for (int i = 0; i < N; i++) {
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) s[k] = fma(a, ST[i][ST_DS + k], ST[i][ST_S + k]);
+      for (int k = 0; k < 6; k++) s[k] = sN[k];
+      const double u0 = uN0, u1 = uN1;
+      {
+        const int j = i + 1 < N ? i + 1 : i;
+#pragma unroll
+        for (int k = 0; k < 6; k++) sN[k] = fma(a, ST[j][ST_DS + k], ST[j][ST_S + k]);
+        uN0 = fma(a, ST[j][ST_DU + 0], ST[j][ST_U + 0]); uN1 = fma(a, ST[j][ST_DU + 1], ST[j][ST_U + 1]);
+      }
       if (i == 0) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { const double c = s[k] - PC[LC_S0 + k]; c0t[k] = c; th += fabs(c); }
@@ -331,7 +344,6 @@ struct Lane {
       fl = fma(0.5, fma(nv2(i) * s[3], s[3], fma(PC[LC_WV2] * dv, dv, fma(we2(i) * s[5], s[5], wc2(i) * s[4] * s[4]))), fl);
       double prod = (s[2] - lo_p) * (hi_p - s[2]) * (s[3] - lo_v) * (hi_v - s[3]);
       if (i < N - 1) {
-        const double u0 = fma(a, ST[i][ST_DU + 0], ST[i][ST_U + 0]), u1 = fma(a, ST[i][ST_DU + 1], ST[i][ST_U + 1]);
         double tg[8];
         point_eval(s, u0, u1, tg, F);
         fl = fma(0.5 * PC[LC_WD2] * u0, u0, fl);
@@ -506,6 +518,14 @@ struct Lane {
       for (int k = 0; k < 6; k++) { s[k] = ST[i][ST_S + k]; lam[k] = ST[i][ST_LAM + k]; }
 #pragma unroll
       for (int k = 0; k < 4; k++) { zl[k] = ST[i][ST_ZL + k]; zu[k] = ST[i][ST_ZU + k]; }
+      // every load of the stage is issued here, needed on this lane's path or not (rows hold all fields for all stages):
+      // a load behind a branch is a second, third, ... latency to wait out
+      double ds_l[6], cn_l[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { ds_l[k] = ST[i][ST_DS + k]; cn_l[k] = ST[i][ST_CN + k]; }
+      const double du0_l = ST[i][ST_DU + 0], du1_l = ST[i][ST_DU + 1];
+      const int im = i >= 1 ? i - 1 : 0;
+      const double up_l = ST[im][ST_U + 0], dup_l = ST[im][ST_DU + 0];
       if (hasu) {
         u0 = ST[i][ST_U + 0]; u1 = ST[i][ST_U + 1];
 #pragma unroll
@@ -514,7 +534,7 @@ struct Lane {
 #pragma unroll
         for (int k = 0; k < 8; k++) tg[k] = 0.0;
       }
-      const double dprev_old = (hasu && i >= 1) ? ST[i - 1][ST_U + 0] : 0.0;
+      const double dprev_old = (hasu && i >= 1) ? up_l : 0.0;
       double dprev = dprev_old;            // NEW delta_{i-1}
       double lp[6] = {0, 0, 0, 0, 0, 0};
       StageLin L;
@@ -522,8 +542,8 @@ struct Lane {
       if (costate) {
         double ds[6], du0 = 0.0, du1 = 0.0, il[4], iu[4];
 #pragma unroll
-        for (int k = 0; k < 6; k++) ds[k] = ST[i][ST_DS + k];
-        if (hasu) { du0 = ST[i][ST_DU + 0]; du1 = ST[i][ST_DU + 1]; }
+        for (int k = 0; k < 6; k++) ds[k] = ds_l[k];
+        if (hasu) { du0 = du0_l; du1 = du1_l; }
         slack_rcp(s[2], s[3], u0, u1, hasu, il, iu);
         StageHess H;
         hess_at(i, ls, dwv, tg, s[3], s[4], s[5], u0, dprev_old, lo_n, zl, zu, il, iu, H);
@@ -558,7 +578,7 @@ struct Lane {
             u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
             ST[i][ST_U + 0] = u0; ST[i][ST_U + 1] = u1;
           }
-          if (i >= 1 && hasu) dprev = fma(a, ST[i - 1][ST_DU + 0], dprev_old);
+          if (i >= 1 && hasu) dprev = fma(a, dup_l, dprev_old);
           double iln[4], iun[4];
           slack_rcp(s[2], s[3], u0, u1, hasu, iln, iun);
 #pragma unroll
@@ -595,7 +615,7 @@ struct Lane {
           lin_at(tg, s[3], u0, L);
         } else {
 #pragma unroll
-          for (int k = 0; k < 6; k++) cn[k] = ST[i][ST_CN + k];
+          for (int k = 0; k < 6; k++) cn[k] = cn_l[k];
         }
       }
 #pragma unroll
@@ -1125,7 +1145,9 @@ struct Lane {
     for (int i = N - 2; i >= 0; i--) {
       StageLin L;
       StageHess H;
-      double d[6];
+      double d[6], cn_l[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cn_l[k] = ST[i][ST_CN + k];   // with the other loads of the stage, not behind them
       if (PAR) {
         load_lin(i, L);
         load_hess(i, ls ? 0.0 : dwv, H);
@@ -1151,7 +1173,7 @@ struct Lane {
         for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CS + k];
       } else {
 #pragma unroll
-        for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CN + k];
+        for (int k = 0; k < 6; k++) d[k] = -cn_l[k];
       }
       const bool cpl = i >= 1;
       const double cwe = cpl ? cwv : 0.0;
@@ -1292,17 +1314,25 @@ struct Lane {
     for (int i = 0; i < N; i++) {
       const bool hasu = i < N - 1;
       double du0 = 0.0, du1 = 0.0, u0 = 0.0, u1 = 0.0;
-      const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3];
+      // every load of the stage in one batch at the top (see advance): rows hold all fields for all stages
+      const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3], s4_l = ST[i][ST_S + 4], s5_l = ST[i][ST_S + 5];
+      double kg[12], tg[8], cn_l[6], zl_l[4], zu_l[4];
+#pragma unroll
+      for (int k = 0; k < 12; k++) kg[k] = ST[i][ST_KG + k];
+#pragma unroll
+      for (int k = 0; k < 8; k++) tg[k] = ST[i][ST_TG + k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cn_l[k] = ST[i][ST_CN + k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { zl_l[k] = ST[i][ST_ZL + k]; zu_l[k] = ST[i][ST_ZU + k]; }
+      const double u0_l = ST[i][ST_U + 0], u1_l = ST[i][ST_U + 1];
+      const double un_l = ST[i + 1 < N ? i + 1 : i][ST_U + 0];
 #pragma unroll
       for (int k = 0; k < 6; k++) ST[i][ST_DS + k] = t[k];
       double tn[6] = {0, 0, 0, 0, 0, 0};
       if (hasu) {
-        double kg[12], tg[8], d[6];
-#pragma unroll
-        for (int k = 0; k < 12; k++) kg[k] = ST[i][ST_KG + k];
-#pragma unroll
-        for (int k = 0; k < 8; k++) tg[k] = ST[i][ST_TG + k];
-        u0 = ST[i][ST_U + 0]; u1 = ST[i][ST_U + 1];
+        double d[6];
+        u0 = u0_l; u1 = u1_l;
         du0 = fma(kg[4], dp, fma(kg[3], t[3], fma(kg[2], t[2], fma(kg[1], t[1], fma(kg[0], t[0], kg[10])))));
         du1 = fma(kg[9], dp, fma(kg[8], t[3], fma(kg[7], t[2], fma(kg[6], t[1], fma(kg[5], t[0], kg[11])))));
         ST[i][ST_DU + 0] = du0; ST[i][ST_DU + 1] = du1;
@@ -1314,7 +1344,7 @@ struct Lane {
           for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CS + k];
         } else {
 #pragma unroll
-          for (int k = 0; k < 6; k++) d[k] = -ST[i][ST_CN + k];
+          for (int k = 0; k < 6; k++) d[k] = -cn_l[k];
         }
         StageLin L;
         lin_at(tg, v, u0, L);
@@ -1326,11 +1356,11 @@ struct Lane {
         tn[5] = fma(L.b3, du0, fma(L.a34, t[3], fma(L.a61, t[0], t[2]))) + d[5];
       }
       if (!ls) {
-        acc += fma(we2(i) * ST[i][ST_S + 5], t[5], fma(wc2(i) * ST[i][ST_S + 4], t[4], fma(nv2(i), v, wv2 * (v - vref(i))) * t[3]));
+        acc += fma(we2(i) * s5_l, t[5], fma(wc2(i) * s4_l, t[4], fma(nv2(i), v, wv2 * (v - vref(i))) * t[3]));
         if (hasu) {
           double gd = wd2 * u0;
           if (i >= 1) gd = fma(cw, u0 - dprev, gd);
-          if (i <= N - 3) gd = fma(-cw, ST[i + 1][ST_U + 0] - u0, gd);
+          if (i <= N - 3) gd = fma(-cw, un_l - u0, gd);
           acc = fma(gd, du0, acc);
           dprev = u0;
         }
@@ -1340,7 +1370,7 @@ struct Lane {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           if (k < 2 || hasu) {
-            const double zl = ST[i][ST_ZL + k], zu = ST[i][ST_ZU + k];
+            const double zl = zl_l[k], zu = zu_l[k];
             acc = fma(mu * (iu[k] - il[k]), dx[k], acc);
             rmax = dmax(rmax, dmax(-dx[k] * il[k], dx[k] * iu[k]));
             const double dzl = fma(fma(-zl, dx[k], mu), il[k], -zl);

@@ -27,8 +27,10 @@ for ln in dis.splitlines():
         line_of[int(m.group(1), 16)] = (cur, m.group(2))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hi = [i for i, r in enumerate(rows) if "Address" in r][0]
+his = [i for i, r in enumerate(rows) if "Address" in r]
+hi = his[0]                                   # first launch of the report
 hdr = rows[hi]
+if len(his) > 1: rows = rows[:his[1]]
 ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 ith = hdr.index("Thread Instructions Executed")
 ilsb = hdr.index("stall_long_sb")
