@@ -315,23 +315,24 @@ struct Lane {
     const double lo_d = PC[LC_LO + 2], hi_d = PC[LC_HI + 2], lo_a = PC[LC_LO + 3], hi_a = PC[LC_HI + 3];
     double F[6] = {0, 0, 0, 0, 0, 0};
     double th = 0.0, fl = 0.0, ll = 0.0, dprev = 0.0;
-    // the rows are a long way off (L2 or DRAM): the trial point of stage i+1 is loaded and formed at the top of
-    // iteration i, so that its latency runs under the transcendental work of stage i instead of being waited for
-    double sN[6], uN0, uN1;
+    // the rows are a long way off (L2 or DRAM): the iterate and step of stage i+1 are loaded at the top of iteration i
+    // and only touched at the top of iteration i+1, so that their latency runs under the transcendental work of
+    // stage i instead of being waited for
+    double sl[6], dl[6], ul0, ul1, dul0, dul1;
 #pragma unroll
-    for (int k = 0; k < 6; k++) sN[k] = fma(a, ST[0][ST_DS + k], ST[0][ST_S + k]);
-    uN0 = fma(a, ST[0][ST_DU + 0], ST[0][ST_U + 0]); uN1 = fma(a, ST[0][ST_DU + 1], ST[0][ST_U + 1]);
+    for (int k = 0; k < 6; k++) { sl[k] = ST[0][ST_S + k]; dl[k] = ST[0][ST_DS + k]; }
+    ul0 = ST[0][ST_U + 0]; ul1 = ST[0][ST_U + 1]; dul0 = ST[0][ST_DU + 0]; dul1 = ST[0][ST_DU + 1];
 #pragma unroll 1
     for (int i = 0; i < N; i++) {
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) s[k] = sN[k];
-      const double u0 = uN0, u1 = uN1;
+      for (int k = 0; k < 6; k++) s[k] = fma(a, dl[k], sl[k]);
+      const double u0 = fma(a, dul0, ul0), u1 = fma(a, dul1, ul1);
       {
         const int j = i + 1 < N ? i + 1 : i;
 #pragma unroll
-        for (int k = 0; k < 6; k++) sN[k] = fma(a, ST[j][ST_DS + k], ST[j][ST_S + k]);
-        uN0 = fma(a, ST[j][ST_DU + 0], ST[j][ST_U + 0]); uN1 = fma(a, ST[j][ST_DU + 1], ST[j][ST_U + 1]);
+        for (int k = 0; k < 6; k++) { sl[k] = ST[j][ST_S + k]; dl[k] = ST[j][ST_DS + k]; }
+        ul0 = ST[j][ST_U + 0]; ul1 = ST[j][ST_U + 1]; dul0 = ST[j][ST_DU + 0]; dul1 = ST[j][ST_DU + 1];
       }
       if (i == 0) {
 #pragma unroll
