@@ -1583,20 +1583,31 @@ struct Lane {
     const size_t B = (size_t)P.B;
     const double cw = PC[LC_CW], wd2 = PC[LC_WD2], wv2 = PC[LC_WV2];
     double fl = 0.0, dprev = 0.0;
+    // a few lanes of a warp retire per trip and the whole warp waits for their rows: load them one stage ahead
+    double sl[6], ul0 = ST[0][ST_U + 0], ul1 = ST[0][ST_U + 1];
+#pragma unroll
+    for (int k = 0; k < 6; k++) sl[k] = ST[0][ST_S + k];
 #pragma unroll 1
     for (int i = 0; i < N; i++) {
       const bool hasu = i < N - 1;
       double s[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) s[k] = ST[i][ST_S + k];
+      for (int k = 0; k < 6; k++) s[k] = sl[k];
+      const double ur0 = ul0, ur1 = ul1;
+      {
+        const int j = i + 1 < N ? i + 1 : i;
+#pragma unroll
+        for (int k = 0; k < 6; k++) sl[k] = ST[j][ST_S + k];
+        ul0 = ST[j][ST_U + 0]; ul1 = ST[j][ST_U + 1];
+      }
       s[2] = fmin(fmax(s[2], PC[LC_LO0]), PC[LC_HI0]);
       s[3] = fmin(fmax(s[3], PC[LC_LO0 + 1]), PC[LC_HI0 + 1]);
       const double dv = s[3] - vref(i);
       fl = fma(0.5, fma(nv2(i) * s[3], s[3], fma(wv2 * dv, dv, fma(we2(i) * s[5], s[5], wc2(i) * s[4] * s[4]))), fl);
       double u0 = 0.0, u1 = 0.0;
       if (hasu) {
-        u0 = fmin(fmax(ST[i][ST_U + 0], PC[LC_LO0 + 2]), PC[LC_HI0 + 2]);
-        u1 = fmin(fmax(ST[i][ST_U + 1], PC[LC_LO0 + 3]), PC[LC_HI0 + 3]);
+        u0 = fmin(fmax(ur0, PC[LC_LO0 + 2]), PC[LC_HI0 + 2]);
+        u1 = fmin(fmax(ur1, PC[LC_LO0 + 3]), PC[LC_HI0 + 3]);
         fl = fma(0.5 * wd2 * u0, u0, fl);
         if (i >= 1) { const double dd = u0 - dprev; fl = fma(0.5 * cw * dd, dd, fl); }
         dprev = u0;
