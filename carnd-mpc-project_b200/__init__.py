@@ -270,11 +270,11 @@ class Solver:
         """Pick the kernel (auto / one problem per warp / one problem per lane) and the lane grid."""
         _check(lib().mpc_set_kernel(self._h, kind, lane_threads, lane_ctas_per_sm), "mpc_set_kernel")
 
-    def set_tail(self, park_lanes, resume_launches, sort_ragged=True, solo_finisher=False, resume_min=0):
+    def set_tail(self, park_lanes, resume_launches, sort_ragged=True, solo_finisher=False, resume_min=0, late_copy=False):
         """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches (each runs only if it
         finds more than resume_min records), ragged sort, finisher."""
         _check(lib().mpc_set_tail(self._h, int(park_lanes), int(resume_launches), int(resume_min),
-                                  (1 if sort_ragged else 0) | (2 if solo_finisher else 0)), "mpc_set_tail")
+                                  (1 if sort_ragged else 0) | (2 if solo_finisher else 0) | (4 if late_copy else 0)), "mpc_set_tail")
 
     def measure_solve_latency(self, state, coeffs, yaw_lo, yaw_hi, reps=1000, warmup=200):
         """(p50, p99) in microseconds of mpc_solve_one called from native code on the given problems ([n,6], [n,5], [n], [n])."""

@@ -55,6 +55,13 @@ struct mpc_handle {
   int park_lanes;       // tail packing: a warp with at most this many problems left parks them once the queue is empty (0 = off)
   int resume_phases;    // lane-kernel resume launches between the main launch and the final one
   int resume_min;       // a resume launch with no more than this many records to work on leaves them to the next launch
+  // early copy-back (mpc_solve_batch_host): the device->host copies of a lane-kernel chain start before its final launch
+  cudaStream_t stream2;
+  cudaEvent_t ev_pre, ev_copy;
+  bool want_pre, pre_recorded;
+  bool no_early_copy;   // test switch: always copy back after the last launch
+  KParams pre_kp;       // parameters of the chain's final launch (its record list = the outputs still to come)
+  int pre_rec, pre_cki; // record size and offset of the problem index in a record
   double *d_ckpt;       // migration records, two buffers of cap_ckpt records (each launch of a chain reads one, writes the other)
   size_t cap_ckpt;      // records per buffer
   int ckpt_ns;
@@ -336,6 +343,9 @@ extern "C" void mpc_destroy(mpc_handle *h) {
   cudaFree(h->d_run);
   cudaFree(h->d_run_i);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
   delete h;
 }
 
@@ -436,6 +446,9 @@ static int launch_solo(mpc_handle *h, KParams &kp, cudaStream_t st, long long nm
 //   resume launches        the parked problems, 32 to a warp; park by rule 2 into the other buffer
 //   final launch           N <= 32: the coop kernel (one problem per lane group, rows in shared memory);
 //                          longer horizons: the solo kernel (one problem per lane, rows in shared memory)
+#ifndef MPC_LANE_MINB
+#define MPC_LANE_MINB 1   // CTAs per SM the lane kernel is compiled for (__launch_bounds__(256, MINB)): experiments only
+#endif
 template <int NS, int MINB>
 static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   static thread_local int cached_dev = -1;
@@ -522,6 +535,13 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   }
   kp.chain_pos = phases + 1;
   kp.park_lanes = 0;
+  if (h->want_pre && st == h->stream) {
+    // from here on only the final launch writes outputs, and only those of the problems in its record list
+    CK(cudaEventRecord(h->ev_pre, st));
+    h->pre_recorded = true;
+    h->pre_kp = kp;
+    h->pre_rec = (int)Lane<NS, false>::CK_SIZE; h->pre_cki = (int)Lane<NS, false>::CK_I;
+  }
   if (h->solo_finisher) {
     return launch_solo<NS, true>(h, kp, st, (long long)kp.ckpt_cap);
   } else {
@@ -589,6 +609,7 @@ extern "C" int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, 
   h->resume_min = resume_min_records;
   h->sort_ragged = (flags & MPC_TAIL_SORT_RAGGED) != 0;
   h->solo_finisher = (flags & MPC_TAIL_SOLO_FINISHER) != 0;
+  h->no_early_copy = (flags & MPC_TAIL_LATE_COPY) != 0;
   return MPC_OK;
 }
 
@@ -636,9 +657,13 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
     CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), (cudaStream_t)cuda_stream));
     kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = INT_MAX;
     if (c.N <= 10) return launch_solo<10, false>(h, kp, (cudaStream_t)cuda_stream, B);
+#ifndef MPC_DEV_N10
     if (c.N <= 20) return launch_solo<20, false>(h, kp, (cudaStream_t)cuda_stream, B);
     if (c.N <= 32) return launch_solo<32, false>(h, kp, (cudaStream_t)cuda_stream, B);
     return launch_solo<MPC_NMAX, false>(h, kp, (cudaStream_t)cuda_stream, B);
+#else
+    return MPC_EINVAL;   // development build (-DMPC_DEV_N10, a third of the compile time): N <= 10 only
+#endif
   }
   if (kind == MPC_KERNEL_WARP) {
     if (c.N > 32) { snprintf(g_err, sizeof(g_err), "warp kernel handles N <= 32"); return MPC_EINVAL; }
@@ -647,9 +672,13 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   if (kind == MPC_KERNEL_COOP) {
     if (h->one_shot) kp.counter = nullptr;   // mpc_solve_one: one group, no work queue
     if (c.N <= 10) return launch_coop<10>(h, kp, (cudaStream_t)cuda_stream);
+#ifndef MPC_DEV_N10
     if (c.N <= 20) return launch_coop<20>(h, kp, (cudaStream_t)cuda_stream);
     if (c.N <= 32) return launch_coop<32>(h, kp, (cudaStream_t)cuda_stream);
     return launch_coop<MPC_NMAX>(h, kp, (cudaStream_t)cuda_stream);
+#else
+    return MPC_EINVAL;   // development build (-DMPC_DEV_N10, a third of the compile time): N <= 10 only
+#endif
   }
   if (N_per && B >= MPC_TAIL_MIN_BATCH && h->sort_ragged) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -669,10 +698,42 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
     h->launches += 3;
     kp.perm = h->d_perm;
   }
-  if (c.N <= 10) return launch_lane<10, 1>(h, kp, (cudaStream_t)cuda_stream);
-  if (c.N <= 20) return launch_lane<20, 1>(h, kp, (cudaStream_t)cuda_stream);
-  if (c.N <= 32) return launch_lane<32, 1>(h, kp, (cudaStream_t)cuda_stream);
-  return launch_lane<MPC_NMAX, 1>(h, kp, (cudaStream_t)cuda_stream);
+  if (c.N <= 10) return launch_lane<10, MPC_LANE_MINB>(h, kp, (cudaStream_t)cuda_stream);
+#ifndef MPC_DEV_N10
+  if (c.N <= 20) return launch_lane<20, MPC_LANE_MINB>(h, kp, (cudaStream_t)cuda_stream);
+  if (c.N <= 32) return launch_lane<32, MPC_LANE_MINB>(h, kp, (cudaStream_t)cuda_stream);
+  return launch_lane<MPC_NMAX, MPC_LANE_MINB>(h, kp, (cudaStream_t)cuda_stream);
+#else
+  return MPC_EINVAL;   // development build (-DMPC_DEV_N10, a third of the compile time): N <= 10 only
+#endif
+}
+
+// Early copy-back: the outputs of the problems the final launch of a chain finished, written again -- straight into
+// the caller's (pinned, device-mapped) host arrays -- after the bulk copies that ran beside that launch.  Column b of
+// every output array, all rows, for every record of the final launch's list.
+struct PatchArrays {
+  const double *src[4]; double *dst[4]; int rows[4];     // result, traj_x, traj_y, full
+  const int *isrc[2]; int *idst[2];                      // status, iters
+};
+__global__ void mpc_patch_outputs_kernel(const KParams P, int rec_size, int cki, const PatchArrays A) {
+  const ChainIO io = chain_resolve(P);
+  const size_t B = (size_t)P.B;
+  const int R = A.rows[0] + A.rows[1] + A.rows[2] + A.rows[3] + 2;
+  const long long total = (long long)io.n * R;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % io.n);
+    int r = (int)(idx / io.n);
+    const int b = (int)io.in[(size_t)k * rec_size + cki];
+    if (r >= R - 2) {
+      const int a = r - (R - 2);
+      if (A.idst[a]) A.idst[a][b] = A.isrc[a][b];
+      continue;
+    }
+    for (int a = 0; a < 4; a++) {
+      if (r < A.rows[a]) { A.dst[a][(size_t)r * B + b] = A.src[a][(size_t)r * B + b]; break; }
+      r -= A.rows[a];
+    }
+  }
 }
 
 // ---- host-pointer entry points -------------------------------------------------------------------
@@ -729,16 +790,63 @@ extern "C" int mpc_solve_batch_host(mpc_handle *h, int B, const double *state, c
   if (weights) CK(stage(weights, d_w, 12 * sB, &u_w));
   if (dt_per) CK(stage(dt_per, d_dt, sB, &u_dt));
   if (N_per) CK(stage(N_per, d_N, (size_t)B * sizeof(int), &u_N));
+  // Early copy-back.  In a lane-kernel chain the final launch (the finisher) works for a quarter of the step on a few
+  // thousand long-running problems; every other result is final before it starts.  If all output arrays are pinned
+  // and device-mapped, the device->host copies run on a second stream beside the finisher, and a small kernel then
+  // rewrites the finisher's problems (columns of the output arrays) straight into the host arrays.
+  PatchArrays pa;
+  memset(&pa, 0, sizeof(pa));
+  auto mapped = [&](void *host) -> void * {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    (void)cudaGetLastError();
+    return nullptr;
+  };
+  bool early = !h->no_early_copy;
+  {
+    double *hostp[4] = {result, traj_x, traj_y, full};
+    const double *devp[4] = {d_res, d_tx, d_ty, d_full};
+    const int rows[4] = {9, N, N, 8 * N - 2};
+    for (int a = 0; a < 4 && early; a++) {
+      if (!hostp[a]) continue;
+      pa.dst[a] = (double *)mapped(hostp[a]); pa.src[a] = devp[a]; pa.rows[a] = rows[a];
+      if (!pa.dst[a]) early = false;
+    }
+    int *hosti[2] = {status, iters};
+    const int *devi[2] = {d_status, d_iters};
+    for (int a = 0; a < 2 && early; a++) {
+      if (!hosti[a]) continue;
+      pa.idst[a] = (int *)mapped(hosti[a]); pa.isrc[a] = devi[a];
+      if (!pa.idst[a]) early = false;
+    }
+  }
+  if (early && !h->stream2) {
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  }
+  h->want_pre = early; h->pre_recorded = false;
   rc = mpc_solve_batch(h, B, (const double *)u_state, (const double *)u_coef, (const double *)u_ylo, (const double *)u_yhi,
                        (const double *)u_w, (const int *)u_N, (const double *)u_dt, d_res, traj_x ? d_tx : nullptr, traj_y ? d_ty : nullptr,
                        full ? d_full : nullptr, d_status, d_iters, st);
+  h->want_pre = false;
   if (rc) return rc;
-  CK(cudaMemcpyAsync(result, d_res, 9 * sB, cudaMemcpyDeviceToHost, st));
-  if (traj_x) CK(cudaMemcpyAsync(traj_x, d_tx, (size_t)N * sB, cudaMemcpyDeviceToHost, st));
-  if (traj_y) CK(cudaMemcpyAsync(traj_y, d_ty, (size_t)N * sB, cudaMemcpyDeviceToHost, st));
-  if (full) CK(cudaMemcpyAsync(full, d_full, (8 * (size_t)N - 2) * sB, cudaMemcpyDeviceToHost, st));
-  if (status) CK(cudaMemcpyAsync(status, d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (iters) CK(cudaMemcpyAsync(iters, d_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  const bool pre = h->pre_recorded;
+  cudaStream_t cs = pre ? h->stream2 : st;
+  if (pre) CK(cudaStreamWaitEvent(cs, h->ev_pre, 0));
+  CK(cudaMemcpyAsync(result, d_res, 9 * sB, cudaMemcpyDeviceToHost, cs));
+  if (traj_x) CK(cudaMemcpyAsync(traj_x, d_tx, (size_t)N * sB, cudaMemcpyDeviceToHost, cs));
+  if (traj_y) CK(cudaMemcpyAsync(traj_y, d_ty, (size_t)N * sB, cudaMemcpyDeviceToHost, cs));
+  if (full) CK(cudaMemcpyAsync(full, d_full, (8 * (size_t)N - 2) * sB, cudaMemcpyDeviceToHost, cs));
+  if (status) CK(cudaMemcpyAsync(status, d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, cs));
+  if (iters) CK(cudaMemcpyAsync(iters, d_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, cs));
+  if (pre) {
+    CK(cudaEventRecord(h->ev_copy, cs));
+    CK(cudaStreamWaitEvent(st, h->ev_copy, 0));
+    mpc_patch_outputs_kernel<<<h->sm_count, 256, 0, st>>>(h->pre_kp, h->pre_rec, h->pre_cki, pa);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
   CK(cudaStreamSynchronize(st));
   return MPC_OK;
 }

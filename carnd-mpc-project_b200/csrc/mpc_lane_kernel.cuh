@@ -1852,8 +1852,11 @@ __device__ __forceinline__ ChainIO chain_resolve(const KParams &P) {
 // RESUME = true is the same kernel started from the records of the previous launch instead of fresh problems,
 // 32 consecutive records to a warp, warps dealt round-robin to the CTAs -- so the survivors of many sparse
 // warps run in a few full ones.  The last launch of a chain parks nothing (P.ckpt == NULL).
+#ifndef MPC_LANE_MAXT
+#define MPC_LANE_MAXT 256   // largest CTA the lane kernel is compiled for (register cap = 65536 / (MAXT * MINB)): experiments only
+#endif
 template <int NS, int MINB, bool RESUME>
-__global__ void __launch_bounds__(256, MINB) mpc_lane_kernel(const KParams P) {
+__global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KParams P) {
   Lane<NS, false> Z;
   Z.mode = LM_IDLE;
   Z.b = 0;

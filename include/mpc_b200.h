@@ -174,13 +174,17 @@ int mpc_set_handoff(mpc_handle *h, int iterations);
  * least MPC_TAIL_MIN_BATCH problems.
  * flags (default MPC_TAIL_SORT_RAGGED): MPC_TAIL_SORT_RAGGED -- batches with N_per hand the problems out longest
  * horizon first, so that the lanes of a warp hold horizons of similar length; MPC_TAIL_SOLO_FINISHER -- finish
- * with the solo kernel instead of the coop kernel. */
+ * with the solo kernel instead of the coop kernel; MPC_TAIL_LATE_COPY -- mpc_solve_batch_host starts its
+ * device->host copies only after the final launch (by default, when every output array is pinned, device-mapped
+ * host memory, they run beside the final launch and the few thousand problems that launch finishes are then
+ * rewritten in the host arrays by a small kernel: same bytes, ~0.25 ms less per 64K batch). */
 #define MPC_TAIL_MIN_BATCH 1024
 #define MPC_PARK_LANES_DEFAULT 16
 #define MPC_RESUME_PHASES_DEFAULT 3
 #define MPC_RESUME_MIN_DEFAULT 8192
 #define MPC_TAIL_SORT_RAGGED 1
 #define MPC_TAIL_SOLO_FINISHER 2
+#define MPC_TAIL_LATE_COPY 4
 int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int resume_min_records, int flags);
 /* accounting: parked[k] = problems parked by launch k (0 = main, 1.. = resume launches) of the last lane-kernel
  * chain of this handle; synchronises the device */

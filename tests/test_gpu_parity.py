@@ -537,6 +537,44 @@ def test_pinned_host_inputs_are_read_in_place(mpc, stable_cfg, stable_cd):
     S.close()
 
 
+def test_early_copy_back_gives_the_same_outputs(mpc, stable_cfg, stable_cd):
+    """mpc_solve_batch_host with every output array in pinned memory: the device->host copies run beside the final
+    launch of the chain and a small kernel rewrites the problems that launch finished (mpc_patch_outputs_kernel).
+    Every byte of every output array must equal the plain path (pageable outputs, copies after the last launch) and
+    the MPC_TAIL_LATE_COPY setting, call after call."""
+    import ctypes as C
+    import torch
+    B = 65536
+    b = mpc.workloads.batch_perturbed_states(B, 0, stable_cd)
+    N = stable_cfg.N
+    S = mpc.Solver(stable_cfg, 0)
+    ref = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"], want_full=True)   # pageable outputs
+    assert S.launches == 5
+    ins = [np.ascontiguousarray(a.T if a.ndim == 2 else a) for a in (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])]
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    pinz = lambda shape, dt: torch.zeros(*shape, dtype=dt).pin_memory().numpy()
+    for late, want_full, launches in ((False, True, 6), (False, False, 6), (True, True, 5), (False, True, 6)):
+        S.set_tail(16, 3, resume_min=8192, late_copy=late)
+        res, tx, ty = pinz((9, B), torch.float64), pinz((N, B), torch.float64), pinz((N, B), torch.float64)
+        full = pinz((8 * N - 2, B), torch.float64) if want_full else None
+        st, it = pinz((B,), torch.int32), pinz((B,), torch.int32)
+        for a in (res, tx, ty, full):
+            if a is not None:
+                a.fill(np.nan)
+        st.fill(-7); it.fill(-7)
+        before = S.launches
+        rc = mpc.lib().mpc_solve_batch_host(S._h, B, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), ptr(ins[3]), None, None, None,
+                                            ptr(res), ptr(tx), ptr(ty), ptr(full) if want_full else None, ptr(st), ptr(it))
+        assert rc == 0
+        assert S.launches - before == launches, (late, S.launches - before)      # + the patch kernel on the early path
+        assert np.array_equal(res.T, ref["result"]) and np.array_equal(st, ref["status"]) and np.array_equal(it, ref["iters"])
+        assert np.array_equal(tx.T, ref["traj_x"]) and np.array_equal(ty.T, ref["traj_y"])
+        if want_full:
+            assert np.array_equal(full.T, ref["full"])
+    assert sum(S.tail_counts(4)) > 0          # the final launch had problems to finish, so the patch kernel had work
+    S.close()
+
+
 def test_repeated_runs_give_the_same_bits(mpc, stable_cfg, stable_cd):
     """Which lane picks which problem up, which warps go sparse first and which launch of the chain finishes a
     problem all depend on the timing of atomics; none of it may show in the results."""
