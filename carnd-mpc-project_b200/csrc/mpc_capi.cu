@@ -466,6 +466,7 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
     if (threads < 32) threads = 32;
     if (threads > 256) threads = 256;
   }
+  if (threads > MPC_LANE_MAXT) threads = MPC_LANE_MAXT;
   long long want = ((long long)kp.B + threads - 1) / threads;
   long long grid = (long long)h->sm_count * (h->lane_ctas_per_sm > 0 ? h->lane_ctas_per_sm : 1);
   if (grid > want) grid = want;
@@ -521,9 +522,9 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   // resume launches: enough lanes for a full buffer in one pass, dealt over all SMs.  Each works out on the device
   // which buffer holds the live records (chain_resolve) and returns at once if there are too few to be worth a pass.
   int rthreads = (int)(((cap + h->sm_count - 1) / h->sm_count + 31) / 32) * 32;
-  if (rthreads > 256) rthreads = 256;
+  if (rthreads > MPC_LANE_MAXT) rthreads = MPC_LANE_MAXT;
   long long rgrid = ((long long)cap + rthreads - 1) / rthreads;
-  if (rgrid > h->sm_count) rgrid = h->sm_count;
+  if (rgrid > (long long)h->sm_count * MPC_LANE_MINB) rgrid = (long long)h->sm_count * MPC_LANE_MINB;
   kp.handoff_iter = INT_MAX;
   kp.perm = nullptr;
   kp.ckpt = nullptr; kp.ckpt_count = nullptr;
