@@ -434,7 +434,7 @@ def main():
                              "bytes_per_solve": BYTES_PER_SOLVE(N),
                              "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_tot.item() / args.steps, "api": "mpc_solve_batch_host (pinned host buffers: inputs read in place over PCIe by the kernels, outputs copied back)"},
+                    "ms_per_step": 1e3 * e2e_tot.item() / args.steps, "api": "mpc_solve_batch_host (pinned host buffers: inputs read in place over PCIe by the kernels; outputs copied back on a second stream beside the chain's final launch, whose problems a small kernel then rewrites in the host arrays)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,

@@ -133,7 +133,9 @@ int mpc_solve_batch(mpc_handle *h, int B,
                     int *status, int *iters, void *cuda_stream);
 
 /* Same contract with HOST pointers: copies inputs to the device, solves, copies the outputs
- * back and synchronises.  This is the call the reference-facing C++ `MPC` shim uses. */
+ * back and synchronises.  This is the call the reference-facing C++ `MPC` shim uses.
+ * Inputs in pinned, device-mapped host memory are read in place; if every output array is pinned too, the copies
+ * back start before the last launch of a large batch has finished (see MPC_TAIL_LATE_COPY).  Same results either way. */
 int mpc_solve_batch_host(mpc_handle *h, int B,
                          const double *state, const double *coeffs,
                          const double *yaw_lo, const double *yaw_hi,
