@@ -187,7 +187,7 @@ def run_reference(args, rank):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "status_ok_frac": ok_frac, "iters_mean": it_mean,
             "oracle_port_value": {"value": port_value, "unit": UNIT, "what": "the plain-C restatement (analytic derivatives, no tape) on the same cores, for comparison"}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def extras(mpc, torch, dev, rd, local_rank, fp64_peak=None):
@@ -269,7 +269,30 @@ def extras(mpc, torch, dev, rd, local_rank, fp64_peak=None):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line at the first
+    collective), so everything but that line goes to stderr: fd 1 is pointed at fd 2, the real stdout is kept aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -470,7 +493,7 @@ def main():
                                     "sample": "first %d problems of the same batch, one solve per host thread (%d threads), %.1f s; CPU restatement "
                                               "oracle/mpc_oracle.c (dense LDL^T), not Ipopt+CppAD+MUMPS" % (sample, cores, t),
                                     "max_abs_diff_vs_gpu": dmax}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
