@@ -1856,7 +1856,11 @@ __device__ __forceinline__ ChainIO chain_resolve(const KParams &P) {
 #define MPC_LANE_MAXT 256   // largest CTA the lane kernel is compiled for (register cap = 65536 / (MAXT * MINB)): experiments only
 #endif
 template <int NS, int MINB, bool RESUME>
+#ifdef MPC_LANE_MAXNREG
+__global__ void __maxnreg__(MPC_LANE_MAXNREG) mpc_lane_kernel(const KParams P) {
+#else
 __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KParams P) {
+#endif
   Lane<NS, false> Z;
   Z.mode = LM_IDLE;
   Z.b = 0;
