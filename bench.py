@@ -185,7 +185,7 @@ def run_reference(args, rank):
                        "batch_per_step": sample, "N": cfg.N, "dt": cfg.dt},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_txt},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "status_ok_frac": ok_frac, "iters_mean": it_mean,
+            "status_ok_frac": ok_frac, "iters_mean": it_mean, "host": {"cpu": cpu_model(), "logical_cpus": os.cpu_count()},
             "oracle_port_value": {"value": port_value, "unit": UNIT, "what": "the plain-C restatement (analytic derivatives, no tape) on the same cores, for comparison"}}
     emit(line)
 
@@ -267,6 +267,18 @@ def extras(mpc, torch, dev, rd, local_rank, fp64_peak=None):
                                            "median_abs_cte_final_m": float(rec[-1, 0].abs().median().item())}
     S5.close()
     return out
+
+
+def cpu_model():
+    """CPU model of the box (the host the cpu_baseline / reference arm runs on)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 _REAL_STDOUT = None
@@ -461,7 +473,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
-            "iters": {"mean": float(it.mean()), "p50": float(np.percentile(it, 50)), "p99": float(np.percentile(it, 99)), "max": int(it.max())},
+            "iters": {"mean": float(it.mean()), "p50": float(np.percentile(it, 50)), "p99": float(np.percentile(it, 99)), "max": int(it.max()),
+                      "hist": {str(k): int(c) for k, c in enumerate(np.bincount(np.asarray(it, dtype=np.int64).clip(0))) if c}},
+            "host": {"cpu": cpu_model(), "logical_cpus": os.cpu_count()},
             "status_ok_frac": float((st == 1).mean()),
         }
         if world == 1 and not args.no_latency:
