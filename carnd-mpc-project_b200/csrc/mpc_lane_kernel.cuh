@@ -1955,7 +1955,10 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
 // The coop kernel on the problems the lane kernel parked: each group takes a record, restores the state and
 // carries on from the trip where the lane stopped.
 template <int NS>
-__global__ void __launch_bounds__(128, 2) mpc_coop_resume_kernel(const KParams P) {
+#ifndef MPC_COOP_RESUME_MINB
+#define MPC_COOP_RESUME_MINB 2   // CTAs per SM the finisher is compiled for at N <= 10 (3 = 168 registers: experiment)
+#endif
+__global__ void __launch_bounds__(128, NS <= 10 ? MPC_COOP_RESUME_MINB : 2) mpc_coop_resume_kernel(const KParams P) {
   extern __shared__ double coop_smem[];
   const int G = Lane<NS, true>::NS_GROUP;
   const int lane = threadIdx.x & 31;
