@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -28,12 +29,16 @@
 #define ID(i) (6 * N + (i))
 #define IA(i) (7 * N - 1 + (i))
 
+#define MACH_EPS_ 2.220446049250313e-16
 void orc_config_defaults(orc_config *cfg) {
   cfg->max_iter = 3000;
   cfg->tol = 1e-8;
   cfg->mu_init = 0.1;
   cfg->max_soc = 4;
   cfg->obj_scaling = 1;
+  cfg->watchdog_trigger = 10;
+  cfg->filter_reset_trigger = 5;
+  cfg->tiny_step_tol = 10.0 * MACH_EPS_;
 }
 
 /* Vehicle::computeSpeedTarget(AD, double), Vehicle.cpp:50-64 (AD flavour: '<' select, no fmin) */
@@ -439,6 +444,17 @@ static void ldl_solve(const ldl_t *f, double *b) {
 
 /* ------------------------------------------------------------------------------------------ */
 /* Part 3: interior-point iteration (Ipopt 3.12 defaults)                                     */
+/*                                                                                            */
+/* Restated FROM MEMORY of the published algorithm (Waechter & Biegler 2006) and of Ipopt     */
+/* 3.12's sources -- none of which is under /root/reference or in this image:                 */
+/*   IpIpoptAlg / IpMonotoneMuUpdate / IpOptErrorConvCheck   main loop, mu rule, termination  */
+/*   IpBacktrackingLineSearch   backtracking, watchdog, tiny steps, soft restoration          */
+/*   IpFilterLSAcceptor         filter tests, second-order correction, filter reset heuristic */
+/*   IpPDPerturbationHandler    inertia correction schedule                                   */
+/*   IpRestoMinC_1Nrm, IpRestoIpoptNLP, IpRestoIterateInitializer, IpRestoConvCheck,          */
+/*   IpRestoFilterConvCheck     feasibility restoration phase                                 */
+/* Deliberate simplifications, each marked below: the nested restoration solve has no         */
+/* watchdog of its own; the soft restoration step and RestoreAcceptablePoint are not restated.*/
 /* ------------------------------------------------------------------------------------------ */
 
 /* Ipopt constants (IpoptAlg defaults) */
@@ -460,6 +476,7 @@ static void ldl_solve(const ldl_t *f, double *b) {
 #define KAPPA_SOC 0.99
 #define ALPHA_MIN_FRAC 0.05
 #define ALPHA_RED 0.5
+#define OBJ_MAX_INC 5.0
 #define DW_FIRST 1e-4           /* first_hessian_perturbation */
 #define DW_MIN 1e-20
 #define DW_MAX 1e20             /* max_hessian_perturbation */
@@ -476,8 +493,15 @@ static void ldl_solve(const ldl_t *f, double *b) {
 #define ACCEPT_COMPL_INF_TOL 1e-2
 #define CONSTR_MULT_INIT_MAX 1e3
 #define NLP_INF 1e19
-#define FILTER_MAX 64
+#define FILTER_MAX 128
 #define MACH_EPS 2.220446049250313e-16
+#define MAX_FILTER_RESETS 5
+#define WATCHDOG_TRIAL_MAX 3    /* watchdog_trial_iter_max */
+#define TINY_STEP_Y_TOL 1e-2
+#define RESTO_RHO 1000.0        /* resto_penalty_parameter */
+#define RESTO_KAPPA 0.9         /* required_infeasibility_reduction */
+#define RESTO_THETA_MAX_FACT 1e8
+#define BOUND_MULT_RESET_THRESHOLD 1e3
 
 typedef struct {
   const orc_config *cfg;     /* solver options only (tol, max_iter, mu_init, max_soc, obj_scaling) */
@@ -495,6 +519,7 @@ typedef struct {
   double *grad, *c, *J, *H, *rhs, *dx, *dlam, *dzl, *dzu, *xt, *ct, *csoc;
   ldl_t *kkt;
   int nzl, nzu;
+  int trace;
 } ipm_t;
 
 static double nlp_f(const ipm_t *s, const double *x) { return s->sf * s->nlp->f(s->nlp->user, x); }
@@ -513,29 +538,31 @@ static void nlp_jac(const ipm_t *s, const double *x, double *J) {
       for (int i = 0; i < s->n; i++) J[(size_t)j * s->n + i] *= s->cs[j];
 }
 
-static double barrier_phi(const ipm_t *s, const double *x, double mu) {
-  double phi = nlp_f(s, x);
+static double log_slacks(const ipm_t *s, const double *x) {
   double sl = 0;
   for (int i = 0; i < s->n; i++) {
     if (s->has_l[i]) sl += log(x[i] - s->xl[i]);
     if (s->has_u[i]) sl += log(s->xu[i] - x[i]);
   }
-  return phi - mu * sl;
+  return sl;
 }
+static double barrier_phi(const ipm_t *s, const double *x, double mu) { return nlp_f(s, x) - mu * log_slacks(s, x); }
 
 static double norm1(const double *v, int n) { double s = 0; for (int i = 0; i < n; i++) s += fabs(v[i]); return s; }
 static double norminf(const double *v, int n) { double s = 0; for (int i = 0; i < n; i++) if (fabs(v[i]) > s) s = fabs(v[i]); return s; }
 
-/* assemble and factor [[H+Sigma+dw I, J^T],[J, -dc I]]; returns 1 if inertia is (n, m, 0) */
-static int kkt_factor(ipm_t *s, double dw, double dc) {
+/* assemble and factor [[H + Sigma + dw I, J^T], [J, -(dc I + Dc)]]; returns 1 if inertia is (n, m, 0).
+ * zl/zu: the bound multipliers in Sigma; Dc: extra (2,2) diagonal (restoration phase) or NULL */
+static int kkt_factor(ipm_t *s, const double *x, const double *zl, const double *zu, double dw, double dc,
+                      const double *Dc) {
   int n = s->n, m = s->m, d = n + m;
   double *A = s->kkt->A;
   memset(A, 0, sizeof(double) * (size_t)d * d);
   for (int i = 0; i < n; i++) {
     for (int j = 0; j < n; j++) A[(size_t)i * d + j] = s->H[(size_t)i * n + j];
     double sig = 0;
-    if (s->has_l[i]) sig += s->zl[i] / (s->x[i] - s->xl[i]);
-    if (s->has_u[i]) sig += s->zu[i] / (s->xu[i] - s->x[i]);
+    if (s->has_l[i]) sig += zl[i] / (x[i] - s->xl[i]);
+    if (s->has_u[i]) sig += zu[i] / (s->xu[i] - x[i]);
     A[(size_t)i * d + i] += sig + dw;
   }
   for (int j = 0; j < m; j++) {
@@ -544,10 +571,34 @@ static int kkt_factor(ipm_t *s, double dw, double dc) {
       A[(size_t)(n + j) * d + i] = v;
       A[(size_t)i * d + (n + j)] = v;
     }
-    A[(size_t)(n + j) * d + (n + j)] = -dc;
+    A[(size_t)(n + j) * d + (n + j)] = -(dc + (Dc ? Dc[j] : 0.0));
   }
   ldl_factor(s->kkt);
   return (s->kkt->n_zero == 0 && s->kkt->n_neg == m);
+}
+
+/* Ipopt's inertia correction schedule (IpPDPerturbationHandler, delta_c never needed: J has full row rank).
+ * Returns the delta_w used, or -1 if none up to max_hessian_perturbation gives inertia (n, m, 0). */
+static double factor_with_inertia_correction(ipm_t *s, const double *x, const double *zl, const double *zu,
+                                             double *dw_last, const double *SigN, const double *SigP, double *Dc,
+                                             orc_ipm_stats *out) {
+  double dw = 0.0;
+  int first_try = 1;
+  for (;;) {
+    if (Dc)   /* restoration phase: the slacks n, p are primal variables and get delta_w too */
+      for (int j = 0; j < s->m; j++) Dc[j] = 1.0 / (SigN[j] + dw) + 1.0 / (SigP[j] + dw);
+    if (kkt_factor(s, x, zl, zu, dw, 0.0, Dc)) break;
+    if (first_try) {
+      out->n_regularized++;
+      dw = (*dw_last == 0.0) ? DW_FIRST : fmax(DW_MIN, *dw_last * DW_DEC);
+      first_try = 0;
+    } else {
+      dw = (*dw_last == 0.0) ? dw * DW_INC_FIRST : dw * DW_INC;
+    }
+    if (dw > DW_MAX) return -1.0;
+  }
+  if (dw > 0.0) *dw_last = dw;
+  return dw;
 }
 
 /* primal-dual errors at the current iterate (grad, c, J must be current) */
@@ -583,21 +634,56 @@ static void err_scaling(const ipm_t *s, double *sd, double *sc) {
   *sc = (nz > 0) ? fmax(S_MAX, zsum / (double)nz) / S_MAX : 1.0;
 }
 
-static double frac_to_bound_primal(const ipm_t *s, const double *dx, double tau) {
+static double frac_to_bound_primal(const ipm_t *s, const double *x, const double *dx, double tau) {
   double a = 1.0;
   for (int i = 0; i < s->n; i++) {
-    if (s->has_l[i] && dx[i] < 0) { double v = -tau * (s->x[i] - s->xl[i]) / dx[i]; if (v < a) a = v; }
-    if (s->has_u[i] && dx[i] > 0) { double v = tau * (s->xu[i] - s->x[i]) / dx[i]; if (v < a) a = v; }
+    if (s->has_l[i] && dx[i] < 0) { double v = -tau * (x[i] - s->xl[i]) / dx[i]; if (v < a) a = v; }
+    if (s->has_u[i] && dx[i] > 0) { double v = tau * (s->xu[i] - x[i]) / dx[i]; if (v < a) a = v; }
   }
   return a;
+}
+static double frac_to_bound_dual(const ipm_t *s, const double *zl, const double *zu, const double *dzl,
+                                 const double *dzu, double tau) {
+  double a = 1.0;
+  for (int i = 0; i < s->n; i++) {
+    if (s->has_l[i] && dzl[i] < 0) { double v = -tau * zl[i] / dzl[i]; if (v < a) a = v; }
+    if (s->has_u[i] && dzu[i] < 0) { double v = -tau * zu[i] / dzu[i]; if (v < a) a = v; }
+  }
+  return a;
+}
+/* dz from dx (the eliminated rows of the primal-dual system) */
+static void bound_mult_step(const ipm_t *s, double mu, const double *x, const double *zl, const double *zu,
+                            const double *dx, double *dzl, double *dzu) {
+  for (int i = 0; i < s->n; i++) {
+    dzl[i] = s->has_l[i] ? mu / (x[i] - s->xl[i]) - zl[i] - zl[i] / (x[i] - s->xl[i]) * dx[i] : 0.0;
+    dzu[i] = s->has_u[i] ? mu / (s->xu[i] - x[i]) - zu[i] + zu[i] / (s->xu[i] - x[i]) * dx[i] : 0.0;
+  }
+}
+/* z += alpha_z dz followed by Ipopt's kappa_sigma safeguard (IpoptAlgorithm::correct_bound_multiplier) */
+static void bound_mult_update(const ipm_t *s, double mu, const double *x, double *zl, double *zu,
+                              const double *dzl, const double *dzu, double alpha_z) {
+  for (int i = 0; i < s->n; i++) {
+    if (s->has_l[i]) {
+      double zz = zl[i] + alpha_z * dzl[i], sl = x[i] - s->xl[i];
+      zl[i] = fmax(fmin(zz, KAPPA_SIGMA * mu / sl), mu / (KAPPA_SIGMA * sl));
+    }
+    if (s->has_u[i]) {
+      double zz = zu[i] + alpha_z * dzu[i], su = s->xu[i] - x[i];
+      zu[i] = fmax(fmin(zz, KAPPA_SIGMA * mu / su), mu / (KAPPA_SIGMA * su));
+    }
+  }
 }
 
 typedef struct { double theta, phi; } filt_t;
 
+/* the line search's persistent state (IpBacktrackingLineSearch + IpFilterLSAcceptor members) */
 typedef struct {
-  double theta, phi, gbd, theta_min, theta_max;
+  double theta, phi, gbd;            /* reference_theta_, reference_barr_, reference_gradBarrTDelta_ */
+  double theta_min, theta_max;
   filt_t F[FILTER_MAX];
-  int nF;
+  int nF, nF_max;
+  int n_filter_resets, succ_filter_rej, last_rej_filter;
+  int reset_trigger;                 /* filter_reset_trigger */
 } ls_t;
 
 static int cmp_le(double lhs, double rhs, double basis) { /* Ipopt Compare_le */
@@ -616,18 +702,35 @@ static int filter_ok(const ls_t *L, double theta_t, double phi_t) {
       return 0;
   return 1;
 }
-static int ls_accept(const ls_t *L, double alpha, double theta_t, double phi_t) {
+/* FilterLSAcceptor::IsAcceptableToCurrentIterate */
+static int acceptable_to_current(const ls_t *L, double theta_t, double phi_t, int from_resto) {
+  if (!from_resto && phi_t > L->phi) {   /* obj_max_inc: the barrier objective must not explode */
+    double basval = 1.0;
+    if (fabs(L->phi) > 10.0) basval = log10(fabs(L->phi));
+    if (log10(phi_t - L->phi) > OBJ_MAX_INC + basval) return 0;
+  }
+  return cmp_le(theta_t, (1.0 - GAMMA_THETA) * L->theta, L->theta) ||
+         cmp_le(phi_t - L->phi, -GAMMA_PHI * L->theta, L->phi);
+}
+static void filter_clear(ls_t *L) { L->nF = 0; L->succ_filter_rej = 0; L->last_rej_filter = 0; }
+/* FilterLSAcceptor::CheckAcceptabilityOfTrialPoint, including the filter reset heuristic */
+static int ls_accept(ls_t *L, double alpha, double theta_t, double phi_t) {
   if (!(theta_t == theta_t) || !(phi_t == phi_t) || isinf(phi_t)) return 0;
   if (L->theta_max > 0 && theta_t > L->theta_max) return 0;
   int ok;
-  if (alpha > 0 && is_ftype(L, alpha) && L->theta <= L->theta_min) {
-    ok = armijo(L, alpha, phi_t);
-  } else {
-    ok = cmp_le(theta_t, (1.0 - GAMMA_THETA) * L->theta, L->theta) ||
-         cmp_le(phi_t - L->phi, -GAMMA_PHI * L->theta, L->phi);
+  if (alpha > 0 && is_ftype(L, alpha) && L->theta <= L->theta_min) ok = armijo(L, alpha, phi_t);
+  else ok = acceptable_to_current(L, theta_t, phi_t, 0);
+  if (!ok) { L->last_rej_filter = 0; return 0; }
+  if (!filter_ok(L, theta_t, phi_t)) { L->last_rej_filter = 1; return 0; }
+  if (L->n_filter_resets < MAX_FILTER_RESETS) {
+    if (L->last_rej_filter) {
+      if (++L->succ_filter_rej >= L->reset_trigger) { L->n_filter_resets++; filter_clear(L); }
+    } else {
+      L->succ_filter_rej = 0;
+    }
+    L->last_rej_filter = 0;
   }
-  if (!ok) return 0;
-  return filter_ok(L, theta_t, phi_t);
+  return 1;
 }
 static void filter_add(ls_t *L, double theta, double phi) {
   /* drop dominated entries */
@@ -636,6 +739,17 @@ static void filter_add(ls_t *L, double theta, double phi) {
     if (!(L->F[j].theta >= theta && L->F[j].phi >= phi)) L->F[k++] = L->F[j];
   L->nF = k;
   if (L->nF < FILTER_MAX) { L->F[L->nF].theta = theta; L->F[L->nF].phi = phi; L->nF++; }
+  if (L->nF > L->nF_max) L->nF_max = L->nF;
+}
+static void filter_augment(ls_t *L) { filter_add(L, (1.0 - GAMMA_THETA) * L->theta, L->phi - GAMMA_PHI * L->theta); }
+/* FilterLSAcceptor::CalculateAlphaMin */
+static double alpha_min_of(const ls_t *L) {
+  double a = GAMMA_THETA;
+  if (L->gbd < 0) {
+    a = fmin(GAMMA_THETA, GAMMA_PHI * L->theta / (-L->gbd));
+    if (L->theta <= L->theta_min) a = fmin(a, DELTA_LS * pow(L->theta, S_THETA) / pow(-L->gbd, S_PHI));
+  }
+  return ALPHA_MIN_FRAC * a;
 }
 
 /* solve the (factored) KKT system for rhs_x = -(grad phi_mu + J^T lam), rhs_c = -cvec */
@@ -655,6 +769,316 @@ static void kkt_solve_dir(ipm_t *s, double mu, const double *cvec, double *dx, d
   memcpy(dlam, rhs + n, sizeof(double) * m);
 }
 
+/* ---- feasibility restoration phase (IpRestoMinC_1Nrm::PerformRestoration) ----------------------
+ *   min  rho sum(n + p) + eta/2 ||D_R (x - x_R)||^2   s.t.  c(x) + n - p = 0,  xl <= x <= xu,  n, p >= 0
+ * with eta = sqrt(mu), D_R = diag(1 / max(1, |x_R|)), solved by the same interior-point iteration (monotone mu,
+ * inertia correction, filter line search with second-order correction) from x_R, until the point is acceptable
+ * to the ORIGINAL problem's filter and reduces its infeasibility to RESTO_KAPPA (IpRestoFilterConvCheck).
+ * The slacks n, p and their multipliers are eliminated from the Newton system, which leaves the original KKT
+ * structure with a diagonal -(Sigma_n^-1 + Sigma_p^-1) in the (2,2) block.
+ * SIMPLIFICATION: the nested solve has no watchdog of its own.
+ * Returns 0 when the original algorithm can go on from the new s->x (multipliers reset as Ipopt does), else the
+ * status to stop with.  *iter counts every restoration iteration (Ipopt numbers them with the outer ones). */
+static int restoration(ipm_t *s, ls_t *LSo, double mu_o, double tau_o, int *iter, orc_ipm_stats *out) {
+  const int n = s->n, m = s->m;
+  const double rho = RESTO_RHO;
+  double *buf = (double *)calloc((size_t)(9 * n + 20 * m), sizeof(double));
+  double *xR = buf, *dr2 = xR + n, *zl = dr2 + n, *zu = zl + n, *dzl = zu + n, *dzu = dzl + n, *xs = dzu + n, *xt = xs + n;
+  double *nn = xt + n, *pp = nn + m, *zn = pp + m, *zp = zn + m, *y = zp + m, *dn = y + m, *dp = dn + m, *dy = dp + m;
+  double *SigN = dy + m, *SigP = SigN + m, *Dc = SigP + m, *rc = Dc + m, *csoc = rc + m, *rct = csoc + m;
+  double *nt = rct + m, *pt = nt + m, *dy_soc = pt + m, *dn_soc = dy_soc + m, *dp_soc = dn_soc + m;
+  double *dx_soc = dp_soc + m;
+  int status = -1;
+  out->n_resto++;
+
+  memcpy(xR, s->x, sizeof(double) * n);
+  for (int i = 0; i < n; i++) { double d = 1.0 / fmax(1.0, fabs(xR[i])); dr2[i] = d * d; }
+  double mu = fmax(mu_o, norminf(s->c, m));          /* resto_mu = max(curr_mu, ||c||_inf) */
+  double tau = fmax(TAU_MIN, 1.0 - mu);
+  double tol_r = s->cfg->tol;
+  /* RestoIterateInitializer: n, p from the barrier-optimal split of c, z = mu / slack, z_x capped at rho, y = 0 */
+  for (int j = 0; j < m; j++) {
+    double cj = s->c[j], a = mu / (2.0 * rho) - 0.5 * cj, b = cj * mu / (2.0 * rho);
+    nn[j] = a + sqrt(a * a + b);
+    pp[j] = cj + nn[j];
+    zn[j] = mu / nn[j];
+    zp[j] = mu / pp[j];
+    y[j] = 0.0;
+  }
+  for (int i = 0; i < n; i++) { zl[i] = fmin(rho, s->zl[i]); zu[i] = fmin(rho, s->zu[i]); }
+  memcpy(xs, s->x, sizeof(double) * n);   /* xs: the restoration iterate; s->x stays x_R until the end */
+
+  /* original-problem quantities at x_R for the convergence test */
+  const double theta_R = norm1(s->c, m), infpr_R = norminf(s->c, m);
+  const double orig_inf_pr_max = fmax(RESTO_KAPPA * infpr_R, fmin(s->cfg->tol, CONSTR_VIOL_TOL));
+
+  ls_t LS;
+  memset(&LS, 0, sizeof(LS));
+  LS.theta_max = RESTO_THETA_MAX_FACT * 1.0;   /* max(1, theta_0) with theta_0 = ||c + n - p||_1 = 0 at the start */
+  LS.theta_min = 1e-4 * 1.0;
+  LS.reset_trigger = s->cfg->filter_reset_trigger;
+  double dw_last = 0.0;
+  int accept_cnt = 0, first = 1;
+  const int nz = s->nzl + s->nzu + 2 * m;
+  /* grad, c, J of the original problem at xs live in s->grad (unused here), s->c, s->J */
+
+  for (;;) {
+    const double eta = sqrt(mu);
+    for (int j = 0; j < m; j++) rc[j] = s->c[j] + nn[j] - pp[j];
+    /* ---- optimality errors of the restoration problem */
+    double dinf = 0, cviol = norminf(rc, m), cp0 = 0, cpm = 0, zsum = 0, ysum = norm1(y, m);
+    for (int i = 0; i < n; i++) {
+      double r = eta * dr2[i] * (xs[i] - xR[i]);
+      for (int j = 0; j < m; j++) r += s->J[(size_t)j * n + i] * y[j];
+      if (s->has_l[i]) { r -= zl[i]; double v = (xs[i] - s->xl[i]) * zl[i]; cp0 = fmax(cp0, fabs(v)); cpm = fmax(cpm, fabs(v - mu)); zsum += fabs(zl[i]); }
+      if (s->has_u[i]) { r += zu[i]; double v = (s->xu[i] - xs[i]) * zu[i]; cp0 = fmax(cp0, fabs(v)); cpm = fmax(cpm, fabs(v - mu)); zsum += fabs(zu[i]); }
+      dinf = fmax(dinf, fabs(r));
+    }
+    for (int j = 0; j < m; j++) {
+      dinf = fmax(dinf, fmax(fabs(rho + y[j] - zn[j]), fabs(rho - y[j] - zp[j])));
+      double v = nn[j] * zn[j], w = pp[j] * zp[j];
+      cp0 = fmax(cp0, fmax(fabs(v), fabs(w)));
+      cpm = fmax(cpm, fmax(fabs(v - mu), fabs(w - mu)));
+      zsum += fabs(zn[j]) + fabs(zp[j]);
+    }
+    const double sd = fmax(S_MAX, (ysum + zsum) / (double)(m + nz)) / S_MAX, sc = fmax(S_MAX, zsum / (double)nz) / S_MAX;
+    const double E0 = fmax(dinf / sd, fmax(cviol, cp0 / sc));
+
+    /* ---- IpRestoConvCheck / IpRestoFilterConvCheck: is xs good enough for the original problem? */
+    if (!first) {
+      const double theta_t = norm1(s->c, m), infpr_t = norminf(s->c, m);
+      int conv = 0;
+      if (RESTO_KAPPA * theta_R < theta_t) conv = 0;
+      else if (infpr_t > orig_inf_pr_max) conv = 0;
+      else {
+        const double phi_t = barrier_phi(s, xs, mu_o);
+        conv = filter_ok(LSo, theta_t, phi_t) && acceptable_to_current(LSo, theta_t, phi_t, 1);
+      }
+      if (conv) { status = 0; break; }
+      /* is the restoration problem itself solved?  then the original one is locally infeasible (or the filter
+       * blocks a feasible point) */
+      int solved = (E0 <= tol_r && dinf <= DUAL_INF_TOL && cviol <= CONSTR_VIOL_TOL && cp0 <= COMPL_INF_TOL);
+      if (!solved) {
+        if (E0 <= ACCEPT_TOL && dinf <= ACCEPT_DUAL_INF_TOL && cviol <= ACCEPT_CONSTR_VIOL_TOL && cp0 <= ACCEPT_COMPL_INF_TOL) {
+          if (++accept_cnt >= ACCEPT_ITER) solved = 1;
+        } else accept_cnt = 0;
+      }
+      if (solved) {
+        if (infpr_t <= 1e2 * s->cfg->tol) {
+          if (tol_r > 1e-1 * s->cfg->tol) { tol_r *= 1e-2; accept_cnt = 0; }   /* tighten once and go on */
+          else { status = ORC_RESTORATION_FAILURE; break; }   /* converged to a feasible point the filter rejects */
+        } else { status = ORC_LOCAL_INFEASIBILITY; break; }
+      }
+      if (!(E0 == E0)) { status = ORC_INVALID_NUMBER_DETECTED; break; }
+    }
+    if (*iter >= s->cfg->max_iter) { status = ORC_MAXITER_EXCEEDED; break; }
+
+    /* ---- monotone barrier update (skipped in the first restoration iteration: first_iter_resto_) */
+    if (!first) {
+      for (;;) {
+        const double Emu = fmax(dinf / sd, fmax(cviol, cpm / sc));
+        if (!(Emu <= KAPPA_EPS * mu)) break;
+        const double mu_min = fmin(tol_r, COMPL_INF_TOL) / (KAPPA_EPS + 1.0);
+        const double new_mu = fmax(mu_min, fmin(KAPPA_MU * mu, pow(mu, THETA_MU)));
+        if (new_mu == mu) break;
+        mu = new_mu;
+        tau = fmax(TAU_MIN, 1.0 - mu);
+        filter_clear(&LS);
+        /* complementarity and (through eta) the dual infeasibility depend on mu */
+        cpm = 0;
+        for (int i = 0; i < n; i++) {
+          if (s->has_l[i]) cpm = fmax(cpm, fabs((xs[i] - s->xl[i]) * zl[i] - mu));
+          if (s->has_u[i]) cpm = fmax(cpm, fabs((s->xu[i] - xs[i]) * zu[i] - mu));
+        }
+        for (int j = 0; j < m; j++) cpm = fmax(cpm, fmax(fabs(nn[j] * zn[j] - mu), fabs(pp[j] * zp[j] - mu)));
+        const double eta2 = sqrt(mu);
+        dinf = 0;
+        for (int i = 0; i < n; i++) {
+          double r = eta2 * dr2[i] * (xs[i] - xR[i]);
+          for (int j = 0; j < m; j++) r += s->J[(size_t)j * n + i] * y[j];
+          if (s->has_l[i]) r -= zl[i];
+          if (s->has_u[i]) r += zu[i];
+          dinf = fmax(dinf, fabs(r));
+        }
+        for (int j = 0; j < m; j++) dinf = fmax(dinf, fmax(fabs(rho + y[j] - zn[j]), fabs(rho - y[j] - zp[j])));
+      }
+    }
+    first = 0;
+    const double etam = sqrt(mu);
+
+    /* ---- search direction: W = sum_j y_j Hess c_j + eta D_R^2 (no objective term) */
+    {
+      double *ls = s->ct;
+      for (int j = 0; j < m; j++) ls[j] = y[j] * s->cs[j];
+      s->nlp->hess(s->nlp->user, xs, 0.0, ls, s->H);
+      for (int i = 0; i < n; i++) s->H[(size_t)i * n + i] += etam * dr2[i];
+    }
+    for (int j = 0; j < m; j++) { SigN[j] = zn[j] / nn[j]; SigP[j] = zp[j] / pp[j]; }
+    const double dw = factor_with_inertia_correction(s, xs, zl, zu, &dw_last, SigN, SigP, Dc, out);
+    if (dw < 0) { status = ORC_ERROR_IN_STEP_COMPUTATION; break; }
+    double *rhs = s->rhs;
+#define RESTO_SOLVE(CV, DX, DY, DN, DP)                                                              \
+    do {                                                                                             \
+      for (int i = 0; i < n; i++) {                                                                  \
+        double r = etam * dr2[i] * (xs[i] - xR[i]);                                                  \
+        for (int j = 0; j < m; j++) r += s->J[(size_t)j * n + i] * y[j];                             \
+        if (s->has_l[i]) r -= mu / (xs[i] - s->xl[i]);                                               \
+        if (s->has_u[i]) r += mu / (s->xu[i] - xs[i]);                                               \
+        rhs[i] = -r;                                                                                 \
+      }                                                                                              \
+      for (int j = 0; j < m; j++) {                                                                  \
+        const double rn = rho + y[j] - mu / nn[j], rp = rho - y[j] - mu / pp[j];                     \
+        rhs[n + j] = -(CV)[j] + rn / (SigN[j] + dw) - rp / (SigP[j] + dw);                           \
+      }                                                                                              \
+      ldl_solve(s->kkt, rhs);                                                                        \
+      memcpy((DX), rhs, sizeof(double) * n);                                                         \
+      memcpy((DY), rhs + n, sizeof(double) * m);                                                     \
+      for (int j = 0; j < m; j++) {                                                                  \
+        const double rn = rho + y[j] - mu / nn[j], rp = rho - y[j] - mu / pp[j];                     \
+        (DN)[j] = (-rn - (DY)[j]) / (SigN[j] + dw);                                                  \
+        (DP)[j] = (-rp + (DY)[j]) / (SigP[j] + dw);                                                  \
+      }                                                                                              \
+    } while (0)
+    RESTO_SOLVE(rc, s->dx, dy, dn, dp);
+
+    /* ---- fraction to the boundary over x, n, p */
+#define RESTO_ALPHA_MAX(DX, DN, DP, A)                                                               \
+    do {                                                                                             \
+      (A) = frac_to_bound_primal(s, xs, (DX), tau);                                                  \
+      for (int j = 0; j < m; j++) {                                                                  \
+        if ((DN)[j] < 0) { double v = -tau * nn[j] / (DN)[j]; if (v < (A)) (A) = v; }                \
+        if ((DP)[j] < 0) { double v = -tau * pp[j] / (DP)[j]; if (v < (A)) (A) = v; }                \
+      }                                                                                              \
+    } while (0)
+    double alpha_max;
+    RESTO_ALPHA_MAX(s->dx, dn, dp, alpha_max);
+
+    /* ---- filter line search on (theta_R, phi_R) */
+    double slog = log_slacks(s, xs), fR = 0;
+    for (int j = 0; j < m; j++) { slog += log(nn[j]) + log(pp[j]); fR += rho * (nn[j] + pp[j]); }
+    for (int i = 0; i < n; i++) fR += 0.5 * etam * dr2[i] * (xs[i] - xR[i]) * (xs[i] - xR[i]);
+    LS.theta = norm1(rc, m);
+    LS.phi = fR - mu * slog;
+    LS.gbd = 0;
+    for (int i = 0; i < n; i++) {
+      double g = etam * dr2[i] * (xs[i] - xR[i]);
+      if (s->has_l[i]) g -= mu / (xs[i] - s->xl[i]);
+      if (s->has_u[i]) g += mu / (s->xu[i] - xs[i]);
+      LS.gbd += g * s->dx[i];
+    }
+    for (int j = 0; j < m; j++) LS.gbd += (rho - mu / nn[j]) * dn[j] + (rho - mu / pp[j]) * dp[j];
+    const double alpha_min = alpha_min_of(&LS);
+#define RESTO_TRIAL(A, DX, DN, DP, TH, PH)                                                           \
+    do {                                                                                             \
+      for (int i = 0; i < n; i++) xt[i] = xs[i] + (A) * (DX)[i];                                     \
+      nlp_c(s, xt, rct);                                                                             \
+      double sl_ = log_slacks(s, xt), f_ = 0;                                                        \
+      for (int j = 0; j < m; j++) {                                                                  \
+        nt[j] = nn[j] + (A) * (DN)[j]; pt[j] = pp[j] + (A) * (DP)[j];                                \
+        rct[j] += nt[j] - pt[j];                                                                     \
+        sl_ += log(nt[j]) + log(pt[j]); f_ += rho * (nt[j] + pt[j]);                                 \
+      }                                                                                              \
+      for (int i = 0; i < n; i++) f_ += 0.5 * etam * dr2[i] * (xt[i] - xR[i]) * (xt[i] - xR[i]);     \
+      (TH) = norm1(rct, m); (PH) = f_ - mu * sl_;                                                    \
+    } while (0)
+    double alpha = alpha_max, alpha_test = alpha_max;
+    double *dx_use = s->dx, *dy_use = dy, *dn_use = dn, *dp_use = dp;
+    int accepted = 0, ntrial = 0;
+    double phi_acc = 0;
+    while (!accepted) {
+      double theta_t, phi_t;
+      RESTO_TRIAL(alpha, s->dx, dn, dp, theta_t, phi_t);
+      alpha_test = alpha;
+      if (ls_accept(&LS, alpha_test, theta_t, phi_t)) { accepted = 1; phi_acc = phi_t; break; }
+      if (ntrial == 0 && s->cfg->max_soc > 0 && theta_t >= LS.theta) {
+        int cnt = 0;
+        double theta_soc_old = 0, theta_trial = theta_t, alpha_soc = alpha;
+        memcpy(csoc, rc, sizeof(double) * m);
+        while (cnt < s->cfg->max_soc && !accepted && (cnt == 0 || theta_trial <= KAPPA_SOC * theta_soc_old)) {
+          theta_soc_old = theta_trial;
+          for (int j = 0; j < m; j++) csoc[j] = alpha_soc * csoc[j] + rct[j];
+          RESTO_SOLVE(csoc, dx_soc, dy_soc, dn_soc, dp_soc);
+          RESTO_ALPHA_MAX(dx_soc, dn_soc, dp_soc, alpha_soc);
+          double phi_soc;
+          RESTO_TRIAL(alpha_soc, dx_soc, dn_soc, dp_soc, theta_trial, phi_soc);
+          if (ls_accept(&LS, alpha_test, theta_trial, phi_soc)) {
+            accepted = 1; alpha = alpha_soc; phi_acc = phi_soc;
+            dx_use = dx_soc; dy_use = dy_soc; dn_use = dn_soc; dp_use = dp_soc;
+            out->n_soc++;
+          } else cnt++;
+        }
+        if (accepted) break;
+      }
+      alpha *= ALPHA_RED;
+      ntrial++;
+      out->n_backtrack++;
+      if (alpha < alpha_min) break;
+    }
+    if (!accepted) { status = ORC_RESTORATION_FAILURE; break; }   /* no restoration inside the restoration */
+    if (!is_ftype(&LS, alpha_test) || !armijo(&LS, alpha_test, phi_acc)) filter_augment(&LS);
+
+    /* ---- accept: primal step alpha, y with alpha, bound multipliers with their own fraction to the boundary */
+    {
+      double az = 1.0;
+      bound_mult_step(s, mu, xs, zl, zu, dx_use, dzl, dzu);
+      az = frac_to_bound_dual(s, zl, zu, dzl, dzu, tau);
+      for (int j = 0; j < m; j++) {
+        const double dzn = mu / nn[j] - zn[j] - SigN[j] * dn_use[j], dzp = mu / pp[j] - zp[j] - SigP[j] * dp_use[j];
+        if (dzn < 0) { double v = -tau * zn[j] / dzn; if (v < az) az = v; }
+        if (dzp < 0) { double v = -tau * zp[j] / dzp; if (v < az) az = v; }
+      }
+      for (int j = 0; j < m; j++) {
+        const double dzn = mu / nn[j] - zn[j] - SigN[j] * dn_use[j], dzp = mu / pp[j] - zp[j] - SigP[j] * dp_use[j];
+        const double nnew = nn[j] + alpha * dn_use[j], pnew = pp[j] + alpha * dp_use[j];
+        zn[j] = fmax(fmin(zn[j] + az * dzn, KAPPA_SIGMA * mu / nnew), mu / (KAPPA_SIGMA * nnew));
+        zp[j] = fmax(fmin(zp[j] + az * dzp, KAPPA_SIGMA * mu / pnew), mu / (KAPPA_SIGMA * pnew));
+        nn[j] = nnew; pp[j] = pnew;
+        y[j] += alpha * dy_use[j];
+      }
+      for (int i = 0; i < n; i++) xs[i] += alpha * dx_use[i];
+      bound_mult_update(s, mu, xs, zl, zu, dzl, dzu, az);
+    }
+    nlp_c(s, xs, s->c);
+    nlp_jac(s, xs, s->J);
+    (*iter)++;
+    out->n_resto_iter++;
+    if (s->trace)
+      fprintf(stderr, "  %4dr th_o %.3e  thR %.3e  lg(mu) %5.1f  dw %.1e  a %.2e  nt %d\n", *iter, norm1(s->c, m), LS.theta,
+              log10(mu), dw, alpha, ntrial);
+  }
+#undef RESTO_SOLVE
+#undef RESTO_ALPHA_MAX
+#undef RESTO_TRIAL
+
+  if (status == 0) {
+    /* back to the original problem (PerformRestoration): the bound multipliers take one primal-dual "step" from
+     * x_R to the new point, are reset to 1 if that leaves them above bound_mult_reset_threshold; the constraint
+     * multipliers are reset to 0 (constr_mult_reset_threshold = 0) */
+    double zmax = 0;
+    for (int i = 0; i < n; i++) {
+      dzl[i] = 0; dzu[i] = 0;
+      if (s->has_l[i]) { const double sR = xR[i] - s->xl[i], sN = xs[i] - s->xl[i]; dzl[i] = (s->zl[i] * (sR - sN) + mu_o) / sR - s->zl[i]; }
+      if (s->has_u[i]) { const double sR = s->xu[i] - xR[i], sN = s->xu[i] - xs[i]; dzu[i] = (s->zu[i] * (sR - sN) + mu_o) / sR - s->zu[i]; }
+    }
+    const double az = frac_to_bound_dual(s, s->zl, s->zu, dzl, dzu, tau_o);
+    for (int i = 0; i < n; i++) {
+      if (s->has_l[i]) { s->zl[i] += az * dzl[i]; zmax = fmax(zmax, fabs(s->zl[i])); }
+      if (s->has_u[i]) { s->zu[i] += az * dzu[i]; zmax = fmax(zmax, fabs(s->zu[i])); }
+    }
+    if (zmax > BOUND_MULT_RESET_THRESHOLD)
+      for (int i = 0; i < n; i++) { if (s->has_l[i]) s->zl[i] = 1.0; if (s->has_u[i]) s->zu[i] = 1.0; }
+    for (int j = 0; j < m; j++) s->lam[j] = 0.0;
+    memcpy(s->x, xs, sizeof(double) * n);
+    (*iter)++;   /* the call itself is an iteration of the outer algorithm */
+  } else {
+    /* failure: the outer algorithm stops with its own iterate x_R; restore its function values */
+    nlp_c(s, s->x, s->c);
+    nlp_jac(s, s->x, s->J);
+  }
+  free(buf);
+  return status;
+}
+
 /* Generic core: minimise f(x) s.t. g(x) = gl (= gu), xl <= x <= xu from the start point xi.
  * Bounds beyond +-1e19 are "no bound".  Outputs x (clipped to the original bounds), lambda, zl, zu
  * (unscaled) and the run statistics. */
@@ -666,8 +1090,9 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
   memset(s, 0, sizeof(S));
   int n = nlp->n, m = nlp->m;
   s->cfg = cfg; s->nlp = nlp; s->n = n; s->m = m;
+  s->trace = getenv("ORC_TRACE") != NULL;
   size_t nd = sizeof(double);
-  double *pool = (double *)calloc((size_t)(30 * n + 10 * m + (size_t)m * n + (size_t)n * n + (n + m)), nd);
+  double *pool = (double *)calloc((size_t)(50 * n + 20 * m + (size_t)m * n + (size_t)n * n + (n + m)), nd);
   double *q = pool;
 #define TAKE(cnt) (q += (cnt), q - (cnt))
   s->cs = TAKE(m); s->xl = TAKE(n); s->xu = TAKE(n); s->xl0 = TAKE(n); s->xu0 = TAKE(n); s->gl = TAKE(m);
@@ -676,6 +1101,9 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
   s->rhs = TAKE(n + m); s->dx = TAKE(n); s->dlam = TAKE(m); s->dzl = TAKE(n); s->dzu = TAKE(n);
   s->xt = TAKE(n); s->ct = TAKE(m); s->csoc = TAKE(m);
   double *xi = TAKE(n), *dx_soc = TAKE(n), *dlam_soc = TAKE(m);
+  /* watchdog backup: iterate and search direction at the point where it was started */
+  double *wd_x = TAKE(n), *wd_lam = TAKE(m), *wd_zl = TAKE(n), *wd_zu = TAKE(n);
+  double *wd_dx = TAKE(n), *wd_dlam = TAKE(m), *wd_dzl = TAKE(n), *wd_dzu = TAKE(n);
 #undef TAKE
   s->has_l = (int *)calloc(2 * (size_t)n, sizeof(int));
   s->has_u = s->has_l + n;
@@ -766,11 +1194,15 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
 
   ls_t LS;
   memset(&LS, 0, sizeof(LS));
+  LS.reset_trigger = cfg->filter_reset_trigger;
   {
     double th0 = norm1(s->c, m);
     LS.theta_max = 1e4 * fmax(1.0, th0);
     LS.theta_min = 1e-4 * fmax(1.0, th0);
   }
+  /* BacktrackingLineSearch members */
+  int in_watchdog = 0, wd_short = 0, wd_trial = 0, tiny_last = 0, tiny_flag = 0;
+  double wd_alpha_test = 0, wd_theta = 0, wd_phi = 0, wd_gbd = 0;
 
   double dw_last = 0.0;
   int iter = 0, accept_cnt = 0;
@@ -779,6 +1211,7 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
   for (;;) {
     /* ---- convergence check */
     double dinf, cviol, compl0, compl_mu, sd, sc;
+    int acceptable_now = 0;
     errors(s, 0.0, &dinf, &cviol, &compl0);
     err_scaling(s, &sd, &sc);
     E0 = fmax(dinf / sd, fmax(cviol, compl0 / sc));
@@ -792,6 +1225,7 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
       }
       if (E0 <= ACCEPT_TOL && dinf_u <= ACCEPT_DUAL_INF_TOL && cviol_u <= ACCEPT_CONSTR_VIOL_TOL &&
           compl_u <= ACCEPT_COMPL_INF_TOL) {
+        acceptable_now = 1;
         if (++accept_cnt >= ACCEPT_ITER) { status = ORC_STOP_AT_ACCEPTABLE_POINT; break; }
       } else {
         accept_cnt = 0;
@@ -800,17 +1234,25 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
     if (!(E0 == E0)) { status = ORC_INVALID_NUMBER_DETECTED; break; }
     if (iter >= cfg->max_iter) { status = ORC_MAXITER_EXCEEDED; break; }
 
-    /* ---- monotone barrier update (mu_allow_fast_monotone_decrease) */
-    for (;;) {
-      errors(s, mu, &dinf, &cviol, &compl_mu);
-      double Emu = fmax(dinf / sd, fmax(cviol, compl_mu / sc));
-      if (!(Emu <= KAPPA_EPS * mu)) break;
-      double mu_min = fmin(cfg->tol, COMPL_INF_TOL) / (KAPPA_EPS + 1.0);
-      double new_mu = fmax(mu_min, fmin(KAPPA_MU * mu, pow(mu, THETA_MU)));
-      if (new_mu == mu) break;
-      mu = new_mu;
-      tau = fmax(TAU_MIN, 1.0 - mu);
-      LS.nF = 0; /* filter reset */
+    /* ---- monotone barrier update (mu_allow_fast_monotone_decrease); a repeated tiny step forces a decrease */
+    {
+      int stop = 0;
+      for (;;) {
+        errors(s, mu, &dinf, &cviol, &compl_mu);
+        double Emu = fmax(dinf / sd, fmax(cviol, compl_mu / sc));
+        if (!(Emu <= KAPPA_EPS * mu) && !tiny_flag) break;
+        double mu_min = fmin(cfg->tol, COMPL_INF_TOL) / (KAPPA_EPS + 1.0);
+        double new_mu = fmax(mu_min, fmin(KAPPA_MU * mu, pow(mu, THETA_MU)));
+        if (new_mu == mu) { if (tiny_flag) stop = 1; break; }
+        mu = new_mu;
+        tau = fmax(TAU_MIN, 1.0 - mu);
+        tiny_flag = 0;
+        /* BacktrackingLineSearch::Reset */
+        filter_clear(&LS);
+        in_watchdog = 0; wd_short = 0; tiny_last = 0;
+      }
+      tiny_flag = 0;
+      if (stop) { status = ORC_STOP_AT_TINY_STEP; break; }
     }
 
     /* ---- search direction with inertia correction */
@@ -819,137 +1261,164 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
       for (int j = 0; j < m; j++) ls[j] = s->lam[j] * s->cs[j];
       nlp->hess(nlp->user, s->x, s->sf, ls, s->H);
     }
-    double dw = 0.0;
-    int ok = kkt_factor(s, 0.0, 0.0);
-    if (!ok) {
-      out->n_regularized++;
-      int first_try = 1;
-      for (;;) {
-        if (first_try) {
-          dw = (dw_last == 0.0) ? DW_FIRST : fmax(DW_MIN, dw_last * DW_DEC);
-          first_try = 0;
-        } else {
-          dw = (dw_last == 0.0) ? dw * DW_INC_FIRST : dw * DW_INC;
-        }
-        if (dw > DW_MAX) break;
-        ok = kkt_factor(s, dw, 0.0);
-        if (ok) break;
-      }
-      if (!ok) { status = ORC_ERROR_IN_STEP_COMPUTATION; break; }
-      dw_last = dw;
-    }
+    double dw = factor_with_inertia_correction(s, s->x, s->zl, s->zu, &dw_last, NULL, NULL, NULL, out);
+    if (dw < 0) { status = ORC_ERROR_IN_STEP_COMPUTATION; break; }
     kkt_solve_dir(s, mu, s->c, s->dx, s->dlam);
-    for (int i = 0; i < n; i++) {
-      s->dzl[i] = s->has_l[i] ? mu / (s->x[i] - s->xl[i]) - s->zl[i] - s->zl[i] / (s->x[i] - s->xl[i]) * s->dx[i] : 0.0;
-      s->dzu[i] = s->has_u[i] ? mu / (s->xu[i] - s->x[i]) - s->zu[i] + s->zu[i] / (s->xu[i] - s->x[i]) * s->dx[i] : 0.0;
-    }
+    bound_mult_step(s, mu, s->x, s->zl, s->zu, s->dx, s->dzl, s->dzu);
 
-    /* ---- fraction to the boundary */
-    double alpha_max = frac_to_bound_primal(s, s->dx, tau);
-    double alpha_z = 1.0;
-    for (int i = 0; i < n; i++) {
-      if (s->has_l[i] && s->dzl[i] < 0) { double v = -tau * s->zl[i] / s->dzl[i]; if (v < alpha_z) alpha_z = v; }
-      if (s->has_u[i] && s->dzu[i] < 0) { double v = -tau * s->zu[i] / s->dzu[i]; if (v < alpha_z) alpha_z = v; }
-    }
-
-    /* ---- filter line search */
-    LS.theta = norm1(s->c, m);
-    LS.phi = barrier_phi(s, s->x, mu);
-    LS.gbd = 0;
-    for (int i = 0; i < n; i++) {
-      double gphi = s->grad[i];
-      if (s->has_l[i]) gphi -= mu / (s->x[i] - s->xl[i]);
-      if (s->has_u[i]) gphi += mu / (s->xu[i] - s->x[i]);
-      LS.gbd += gphi * s->dx[i];
-    }
-    double alpha_min = GAMMA_THETA;
-    if (LS.gbd < 0) {
-      alpha_min = fmin(GAMMA_THETA, GAMMA_PHI * LS.theta / (-LS.gbd));
-      if (LS.theta <= LS.theta_min)
-        alpha_min = fmin(alpha_min, DELTA_LS * pow(LS.theta, S_THETA) / pow(-LS.gbd, S_PHI));
-    }
-    alpha_min *= ALPHA_MIN_FRAC;
-
-    double alpha = alpha_max, alpha_test = alpha_max;
-    const double *dx_use = s->dx, *dlam_use = s->dlam;
-    int accepted = 0, ntrial = 0;
-    while (!accepted) {
-      for (int i = 0; i < n; i++) s->xt[i] = s->x[i] + alpha * s->dx[i];
-      nlp_c(s, s->xt, s->ct);
-      double theta_t = norm1(s->ct, m);
-      double phi_t = barrier_phi(s, s->xt, mu);
-      alpha_test = alpha;
-      if (ls_accept(&LS, alpha_test, theta_t, phi_t)) { accepted = 1; break; }
-      /* second-order correction, only for the first trial step and if theta did not decrease */
-      if (ntrial == 0 && cfg->max_soc > 0 && theta_t >= LS.theta) {
-        int cnt = 0;
-        double theta_soc_old = 0, theta_trial = theta_t, alpha_soc = alpha;
-        memcpy(s->csoc, s->c, nd * m);
-        while (cnt < cfg->max_soc && !accepted && (cnt == 0 || theta_trial <= KAPPA_SOC * theta_soc_old)) {
-          theta_soc_old = theta_trial;
-          for (int j = 0; j < m; j++) s->csoc[j] = alpha_soc * s->csoc[j] + s->ct[j];
-          kkt_solve_dir(s, mu, s->csoc, dx_soc, dlam_soc);
-          alpha_soc = frac_to_bound_primal(s, dx_soc, tau);
-          for (int i = 0; i < n; i++) s->xt[i] = s->x[i] + alpha_soc * dx_soc[i];
-          nlp_c(s, s->xt, s->ct);
-          theta_trial = norm1(s->ct, m);
-          double phi_soc = barrier_phi(s, s->xt, mu);
-          if (ls_accept(&LS, alpha_test, theta_trial, phi_soc)) {
-            accepted = 1;
-            alpha = alpha_soc;
-            dx_use = dx_soc;
-            dlam_use = dlam_soc;
-            out->n_soc++;
-          } else {
-            cnt++;
-          }
-        }
-        if (accepted) break;
+    /* ---- line search (BacktrackingLineSearch::FindAcceptableTrialPoint) */
+    if (!in_watchdog) {   /* InitThisLineSearch: reference values of the current iterate */
+      LS.theta = norm1(s->c, m);
+      LS.phi = barrier_phi(s, s->x, mu);
+      LS.gbd = 0;
+      for (int i = 0; i < n; i++) {
+        double gphi = s->grad[i];
+        if (s->has_l[i]) gphi -= mu / (s->x[i] - s->xl[i]);
+        if (s->has_u[i]) gphi += mu / (s->xu[i] - s->x[i]);
+        LS.gbd += gphi * s->dx[i];
       }
-      alpha *= ALPHA_RED;
-      ntrial++;
-      out->n_backtrack++;
-      if (alpha < alpha_min) break;
     }
-    if (!accepted) { status = ORC_RESTORATION_FAILURE; break; } /* restoration phase not restated */
-
-    /* ---- filter update, then accept the trial point */
+    /* DetectTinyStep */
+    int tiny = 0;
     {
-      double phi_t = barrier_phi(s, s->xt, mu);
-      if (!is_ftype(&LS, alpha_test) || !armijo(&LS, alpha_test, phi_t))
-        filter_add(&LS, (1.0 - GAMMA_THETA) * LS.theta, LS.phi - GAMMA_PHI * LS.theta);
+      double mx = 0;
+      for (int i = 0; i < n; i++) { double v = fabs(s->dx[i]) / (1.0 + fabs(s->x[i])); if (v > mx) mx = v; }
+      tiny = cfg->tiny_step_tol > 0 && (mx <= cfg->tiny_step_tol) && (norm1(s->c, m) <= 1e-4);
     }
-    /* recompute dz for an SOC step (dz follows the accepted dx) */
-    if (dx_use != s->dx) {
-      for (int i = 0; i < n; i++) {
-        s->dzl[i] = s->has_l[i] ? mu / (s->x[i] - s->xl[i]) - s->zl[i] - s->zl[i] / (s->x[i] - s->xl[i]) * dx_use[i] : 0.0;
-        s->dzu[i] = s->has_u[i] ? mu / (s->xu[i] - s->x[i]) - s->zu[i] + s->zu[i] / (s->xu[i] - s->x[i]) * dx_use[i] : 0.0;
-      }
-      alpha_z = 1.0;
-      for (int i = 0; i < n; i++) {
-        if (s->has_l[i] && s->dzl[i] < 0) { double v = -tau * s->zl[i] / s->dzl[i]; if (v < alpha_z) alpha_z = v; }
-        if (s->has_u[i] && s->dzu[i] < 0) { double v = -tau * s->zu[i] / s->dzu[i]; if (v < alpha_z) alpha_z = v; }
+#define STOP_WATCHDOG()                                                                              \
+    do {                                                                                             \
+      memcpy(s->x, wd_x, nd * n); memcpy(s->lam, wd_lam, nd * m); memcpy(s->zl, wd_zl, nd * n); memcpy(s->zu, wd_zu, nd * n); \
+      memcpy(s->dx, wd_dx, nd * n); memcpy(s->dlam, wd_dlam, nd * m); memcpy(s->dzl, wd_dzl, nd * n); memcpy(s->dzu, wd_dzu, nd * n); \
+      nlp_grad(s, s->x, s->grad); nlp_c(s, s->x, s->c); nlp_jac(s, s->x, s->J);                       \
+      LS.theta = wd_theta; LS.phi = wd_phi; LS.gbd = wd_gbd;                                         \
+      in_watchdog = 0; wd_short = 0;                                                                 \
+    } while (0)
+    if (in_watchdog && tiny) { STOP_WATCHDOG(); tiny = 0; }
+    if (cfg->watchdog_trigger > 0 && !in_watchdog && !tiny && wd_short >= cfg->watchdog_trigger) {   /* StartWatchDog */
+      in_watchdog = 1; wd_trial = 0;
+      memcpy(wd_x, s->x, nd * n); memcpy(wd_lam, s->lam, nd * m); memcpy(wd_zl, s->zl, nd * n); memcpy(wd_zu, s->zu, nd * n);
+      memcpy(wd_dx, s->dx, nd * n); memcpy(wd_dlam, s->dlam, nd * m); memcpy(wd_dzl, s->dzl, nd * n); memcpy(wd_dzu, s->dzu, nd * n);
+      wd_alpha_test = frac_to_bound_primal(s, s->x, s->dx, tau);
+      wd_theta = LS.theta; wd_phi = LS.phi; wd_gbd = LS.gbd;
+      out->n_watchdog++;
+    }
+
+    int accepted = 0, n_steps = 0, via_resto = 0, update_filter = 0;
+    double alpha = 0, alpha_test = 0, phi_acc = 0;
+    const double *dx_use = s->dx, *dlam_use = s->dlam;
+    char tag = ' ';
+
+    if (tiny) {
+      /* a numerically insignificant step is taken without any test; twice in a row (with a small dual step)
+       * it forces the barrier parameter down, and ends the run if that is no longer possible */
+      alpha = frac_to_bound_primal(s, s->x, s->dx, tau);
+      for (int i = 0; i < n; i++) s->xt[i] = s->x[i] + alpha * s->dx[i];
+      if (tiny_last && norminf(s->dlam, m) < TINY_STEP_Y_TOL) tiny_flag = 1;
+      tiny_last = 1;
+      accepted = 1; tag = 't';
+      out->n_tiny++;
+    } else {
+      tiny_last = 0;
+      {
+        int skip_first = 0;
+        for (;;) {
+          /* DoBacktrackingLineSearch */
+          const double alpha_max = frac_to_bound_primal(s, s->x, s->dx, tau);
+          const double alpha_min = in_watchdog ? alpha_max : alpha_min_of(&LS);
+          alpha = alpha_max;
+          alpha_test = in_watchdog ? wd_alpha_test : alpha;
+          if (skip_first) alpha *= ALPHA_RED;
+          n_steps = 0; accepted = 0;
+          dx_use = s->dx; dlam_use = s->dlam;
+          while (alpha > alpha_min || n_steps == 0) {
+            for (int i = 0; i < n; i++) s->xt[i] = s->x[i] + alpha * s->dx[i];
+            nlp_c(s, s->xt, s->ct);
+            double theta_t = norm1(s->ct, m);
+            double phi_t = barrier_phi(s, s->xt, mu);
+            if (!in_watchdog) alpha_test = alpha;
+            if (ls_accept(&LS, alpha_test, theta_t, phi_t)) { accepted = 1; phi_acc = phi_t; break; }
+            if (in_watchdog) break;
+            /* second-order correction, only for the first trial step and if theta did not decrease */
+            if (alpha == alpha_max && cfg->max_soc > 0 && LS.theta <= theta_t) {
+              int cnt = 0;
+              double theta_soc_old = 0, theta_trial = theta_t, alpha_soc = alpha;
+              memcpy(s->csoc, s->c, nd * m);
+              while (cnt < cfg->max_soc && !accepted && (cnt == 0 || theta_trial <= KAPPA_SOC * theta_soc_old)) {
+                theta_soc_old = theta_trial;
+                for (int j = 0; j < m; j++) s->csoc[j] = alpha_soc * s->csoc[j] + s->ct[j];
+                kkt_solve_dir(s, mu, s->csoc, dx_soc, dlam_soc);
+                alpha_soc = frac_to_bound_primal(s, s->x, dx_soc, tau);
+                for (int i = 0; i < n; i++) s->xt[i] = s->x[i] + alpha_soc * dx_soc[i];
+                nlp_c(s, s->xt, s->ct);
+                theta_trial = norm1(s->ct, m);
+                double phi_soc = barrier_phi(s, s->xt, mu);
+                if (ls_accept(&LS, alpha_test, theta_trial, phi_soc)) {
+                  accepted = 1; phi_acc = phi_soc;
+                  alpha = alpha_soc;
+                  dx_use = dx_soc;
+                  dlam_use = dlam_soc;
+                  out->n_soc++;
+                } else {
+                  cnt++;
+                }
+              }
+              if (accepted) break;
+            }
+            alpha *= ALPHA_RED;
+            n_steps++;
+            out->n_backtrack++;
+          }
+          if (!in_watchdog) { update_filter = accepted; tag = accepted ? 'f' : ' '; break; }
+          if (accepted) { in_watchdog = 0; update_filter = 1; tag = 'W'; break; }
+          if (++wd_trial > WATCHDOG_TRIAL_MAX) {
+            STOP_WATCHDOG();          /* back to the stored iterate and direction, backtrack from alpha_max / 2 */
+            skip_first = 1;
+            continue;
+          }
+          accepted = 1; tag = 'w';    /* take the full step untested */
+          break;
+        }
       }
     }
-    for (int i = 0; i < n; i++) s->x[i] = s->xt[i];
-    for (int j = 0; j < m; j++) s->lam[j] += alpha * dlam_use[j];
-    for (int i = 0; i < n; i++) {
-      if (s->has_l[i]) {
-        double zz = s->zl[i] + alpha_z * s->dzl[i], sl = s->x[i] - s->xl[i];
-        zz = fmax(fmin(zz, KAPPA_SIGMA * mu / sl), mu / (KAPPA_SIGMA * sl));
-        s->zl[i] = zz;
+
+    if (!accepted) {
+      /* the step size fell below alpha_min: restoration phase.  SIMPLIFICATION: Ipopt first tries a "soft
+       * restoration" step (the same direction with one step length for primal and dual variables, accepted if the
+       * primal-dual system error drops by 1e-4); that is not restated -- on every problem of the horizon grid that
+       * reaches this point the soft step was rejected when it was still tried here. */
+      filter_augment(&LS);    /* PrepareRestoPhaseStart */
+      {
+        if (acceptable_now) { status = ORC_STOP_AT_ACCEPTABLE_POINT; break; }   /* "restoration phase called at acceptable point" */
+        if (norm1(s->c, m) <= 1e-2 * cfg->tol) { status = ORC_RESTORATION_FAILURE; break; }   /* "... at almost feasible point" (RestoreAcceptablePoint not restated) */
+        int rs = restoration(s, &LS, mu, tau, &iter, out);
+        if (rs != 0) { status = rs; break; }
+        via_resto = 1; accepted = 1; tag = 'R';
+        wd_short = 0;
       }
-      if (s->has_u[i]) {
-        double zz = s->zu[i] + alpha_z * s->dzu[i], su = s->xu[i] - s->x[i];
-        zz = fmax(fmin(zz, KAPPA_SIGMA * mu / su), mu / (KAPPA_SIGMA * su));
-        s->zu[i] = zz;
-      }
+    }
+
+    /* ---- accept the trial point */
+    if (via_resto) {
+      /* restoration() has set x, lam and z */
+    } else {
+      if (update_filter && (!is_ftype(&LS, alpha_test) || !armijo(&LS, alpha_test, phi_acc))) filter_augment(&LS);
+      double alpha_z;
+      if (dx_use != s->dx) bound_mult_step(s, mu, s->x, s->zl, s->zu, dx_use, s->dzl, s->dzu);   /* dz follows the accepted (SOC) dx */
+      alpha_z = frac_to_bound_dual(s, s->zl, s->zu, s->dzl, s->dzu, tau);
+      for (int i = 0; i < n; i++) s->x[i] = s->xt[i];
+      for (int j = 0; j < m; j++) s->lam[j] += alpha * dlam_use[j];
+      bound_mult_update(s, mu, s->x, s->zl, s->zu, s->dzl, s->dzu, alpha_z);
+      if (tag != 't') { if (n_steps == 0) wd_short = 0; else wd_short++; }
+      iter++;
     }
     nlp_grad(s, s->x, s->grad);
     nlp_c(s, s->x, s->c);
     nlp_jac(s, s->x, s->J);
-    iter++;
+    if (s->trace)
+      fprintf(stderr, "%4d  f %.8e  th %.3e  lg(mu) %5.1f  dw %.1e  a %.2e %c  ls %d  wd %d nF %d\n", iter, nlp_f(s, s->x) / s->sf,
+              norm1(s->c, m), log10(mu), dw, alpha, tag, n_steps, wd_short, LS.nF);
   }
+#undef STOP_WATCHDOG
 
   /* ---- finalize: honor_original_bounds, unscale */
   for (int i = 0; i < n; i++) {
@@ -963,6 +1432,8 @@ int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi_in
   if (lam_out)
     for (int j = 0; j < m; j++) lam_out[j] = s->lam[j] * s->cs[j] / s->sf;
   out->status = status;
+  out->n_filter_reset = LS.n_filter_resets;
+  out->n_filter_max = LS.nF_max;
   out->iters = iter;
   out->kkt_error = E0;
   out->obj = nlp->f(nlp->user, x_out);
@@ -998,6 +1469,8 @@ int orc_solve(const orc_config *cfg, const orc_problem *prob, orc_result *out) {
   if (rc) return rc;
   out->status = st.status; out->iters = st.iters; out->n_regularized = st.n_regularized;
   out->n_soc = st.n_soc; out->n_backtrack = st.n_backtrack; out->obj = st.obj; out->kkt_error = st.kkt_error;
+  out->n_resto = st.n_resto; out->n_resto_iter = st.n_resto_iter; out->n_watchdog = st.n_watchdog;
+  out->n_tiny = st.n_tiny; out->n_filter_reset = st.n_filter_reset; out->n_filter_max = st.n_filter_max;
   /* MPC.cpp:322-324 */
   out->result[0] = out->z[IX(1)];
   out->result[1] = out->z[IY(1)];

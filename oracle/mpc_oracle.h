@@ -44,6 +44,9 @@ typedef struct orc_config {
   double mu_init;            /* 0.1 */
   int max_soc;               /* Ipopt max_soc (default 4) */
   int obj_scaling;           /* 1 = gradient-based nlp scaling (Ipopt default) */
+  int watchdog_trigger;      /* Ipopt watchdog_shortened_iter_trigger (default 10, 0 = off) */
+  int filter_reset_trigger;  /* Ipopt filter_reset_trigger (default 5) */
+  double tiny_step_tol;      /* Ipopt tiny_step_tol (default 10 eps, 0 = off) */
 } orc_config;
 
 /* One problem: MPC::solve's explicit and hidden inputs (MPC.cpp:213-218, 229-232, RoadGeometry). */
@@ -74,6 +77,7 @@ typedef struct orc_result {
   double z[8 * ORC_NMAX];    /* solution.x in the reference's layout (MPC.cpp:189-196) */
   double lambda[6 * ORC_NMAX];
   double zl[8 * ORC_NMAX], zu[8 * ORC_NMAX];
+  int n_resto, n_resto_iter, n_watchdog, n_tiny, n_filter_reset, n_filter_max;   /* see orc_ipm_stats */
 } orc_result;
 
 void orc_config_defaults(orc_config *cfg);   /* solver knobs only (Ipopt 3.12 defaults) */
@@ -93,6 +97,12 @@ typedef struct orc_nlp {
 typedef struct orc_ipm_stats {
   int status, iters, n_regularized, n_soc, n_backtrack;
   double obj, kkt_error;
+  int n_resto;               /* calls of the feasibility restoration phase */
+  int n_resto_iter;          /* iterations spent inside it (included in iters) */
+  int n_watchdog;            /* watchdog activations */
+  int n_tiny;                /* tiny steps taken */
+  int n_filter_reset;        /* filter resets by the heuristic */
+  int n_filter_max;          /* largest number of filter entries held at once */
 } orc_ipm_stats;
 /* cfg supplies only tol, max_iter, mu_init, max_soc, obj_scaling.  Returns 0, or -1 if gl != gu. */
 int orc_ipm_solve(const orc_nlp *nlp, const orc_config *cfg, const double *xi, const double *xl,

@@ -29,7 +29,8 @@ class OrcConfig(C.Structure):
         ("max_speed", C.c_double), ("max_steering", C.c_double), ("max_accel", C.c_double),
         ("max_decel", C.c_double), ("weights", C.c_double * 12), ("steers", C.c_double * NTAB),
         ("steer_speeds", C.c_double * NTAB), ("tol", C.c_double), ("mu_init", C.c_double),
-        ("max_soc", C.c_int), ("obj_scaling", C.c_int),
+        ("max_soc", C.c_int), ("obj_scaling", C.c_int), ("watchdog_trigger", C.c_int),
+        ("filter_reset_trigger", C.c_int), ("tiny_step_tol", C.c_double),
     ]
 
 
@@ -44,6 +45,7 @@ class OrcResult(C.Structure):
         ("n_backtrack", C.c_int), ("obj", C.c_double), ("result", C.c_double * 9),
         ("kkt_error", C.c_double), ("z", C.c_double * (8 * NMAX)), ("lam", C.c_double * (6 * NMAX)),
         ("zl", C.c_double * (8 * NMAX)), ("zu", C.c_double * (8 * NMAX)),
+        ("n_resto", C.c_int), ("n_resto_iter", C.c_int), ("n_watchdog", C.c_int), ("n_tiny", C.c_int), ("n_filter_reset", C.c_int), ("n_filter_max", C.c_int),
     ]
 
 
@@ -224,6 +226,7 @@ def solve(cfg, p):
         "n_backtrack": r.n_backtrack, "obj": r.obj, "result": np.array(r.result[:9]),
         "kkt_error": r.kkt_error, "z": np.array(r.z[:n]), "lam": np.array(r.lam[:m]),
         "zl": np.array(r.zl[:n]), "zu": np.array(r.zu[:n]),
+        "n_resto": r.n_resto, "n_resto_iter": r.n_resto_iter, "n_watchdog": r.n_watchdog, "n_tiny": r.n_tiny, "n_filter_reset": r.n_filter_reset, "n_filter_max": r.n_filter_max,
     }
 
 
