@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("MPC_B200_LIB") or os.path.join(_HERE, "libmpc_b200.so
 CSRC = os.path.join(_HERE, "csrc")
 
 NCOEF, NTAB, NWEIGHTS, NMAX = 5, 16, 12, 64
-KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE, KERNEL_COOP, KERNEL_SOLO = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_LANE, KERNEL_COOP = 0, 2, 3
 LANE_MIN_BATCH = 9216
 
 STATUS_SUCCESS = 1
@@ -49,6 +49,7 @@ class MpcConfig(C.Structure):
         ("max_speed", C.c_double), ("max_steering", C.c_double), ("max_accel", C.c_double),
         ("max_decel", C.c_double), ("weights", C.c_double * NWEIGHTS), ("steers", C.c_double * NTAB),
         ("steer_speeds", C.c_double * NTAB), ("tol", C.c_double),
+        ("watchdog_trigger", C.c_int), ("filter_reset_trigger", C.c_int), ("tiny_step_tol", C.c_double),
         ("max_fit_order", C.c_int), ("latency_ms", C.c_int), ("max_fit_error", C.c_double),
         ("lookahead", C.c_double), ("ipopt_timeout", C.c_double), ("steer_adjust_thresh", C.c_double),
         ("steer_adjust_ratio", C.c_double), ("n_yaw_changes", C.c_int), ("n_yaw_change_speeds", C.c_int),
@@ -270,11 +271,11 @@ class Solver:
         """Pick the kernel (auto / one problem per warp / one problem per lane) and the lane grid."""
         _check(lib().mpc_set_kernel(self._h, kind, lane_threads, lane_ctas_per_sm), "mpc_set_kernel")
 
-    def set_tail(self, park_lanes, resume_launches, sort_ragged=True, solo_finisher=False, resume_min=0, late_copy=False):
+    def set_tail(self, park_lanes, resume_launches, sort_ragged=True, resume_min=0, late_copy=False):
         """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches (each runs only if it
-        finds more than resume_min records), ragged sort, finisher."""
+        finds more than resume_min records), ragged sort, copy-back timing."""
         _check(lib().mpc_set_tail(self._h, int(park_lanes), int(resume_launches), int(resume_min),
-                                  (1 if sort_ragged else 0) | (2 if solo_finisher else 0) | (4 if late_copy else 0)), "mpc_set_tail")
+                                  (1 if sort_ragged else 0) | (4 if late_copy else 0)), "mpc_set_tail")
 
     def measure_solve_latency(self, state, coeffs, yaw_lo, yaw_hi, reps=1000, warmup=200):
         """(p50, p99) in microseconds of mpc_solve_one called from native code on the given problems ([n,6], [n,5], [n], [n])."""

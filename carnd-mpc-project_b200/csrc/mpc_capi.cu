@@ -39,7 +39,8 @@ static int cuda_fail(cudaError_t e, const char *what) {
 
 // device counters of a handle: [0] work queue, [1 + 2k] records parked by launch k of a lane-kernel chain,
 // [2 + 2k] cursor of the coop kernel over them, [MPC_HIST0 ..] horizon histogram of a ragged batch
-enum { MPC_MAX_PHASES = 6, MPC_HIST0 = 20, MPC_NCOUNTER = MPC_HIST0 + MPC_NMAX + 1 };
+// [MPC_RESTART_COUNT] problems handed to the final launch without a record, [MPC_RESTART_CURSOR] its cursor over them
+enum { MPC_MAX_PHASES = 6, MPC_RESTART_COUNT = 17, MPC_RESTART_CURSOR = 18, MPC_HIST0 = 20, MPC_NCOUNTER = MPC_HIST0 + MPC_NMAX + 1 };
 
 struct mpc_handle {
   mpc_config cfg;
@@ -47,7 +48,7 @@ struct mpc_handle {
   int sm_count;
   int *d_counter;
   long long launches;
-  int kernel_kind;      // MPC_KERNEL_AUTO / WARP / LANE
+  int kernel_kind;      // MPC_KERNEL_AUTO / LANE / COOP
   int lane_threads;     // threads per CTA of the lane kernel
   int lane_ctas_per_sm; // CTAs per SM of the lane kernel (0 = occupancy maximum)
   bool one_shot;        // set by mpc_solve_one around its launch
@@ -66,7 +67,10 @@ struct mpc_handle {
   size_t cap_ckpt;      // records per buffer
   int ckpt_ns;
   bool sort_ragged;     // ragged batches (N_per given): hand the problems out longest horizon first
-  bool solo_finisher;   // finish the tail with the solo kernel instead of the coop kernel (experiments)
+  int *d_restart;       // indices of the problems the lane kernel handed over without a record
+  size_t cap_restart;
+  double *d_scratch;    // coop kernels: global scratch per lane group (watchdog backup, restoration rows)
+  size_t cap_scratch;
   int *d_perm;          // ragged batches: problem order of the work queue (longest horizon first)
   size_t cap_perm;
   double *dual_lam, *dual_zl, *dual_zu;   // caller's device buffers for the multipliers (or NULL)
@@ -183,6 +187,9 @@ extern "C" int mpc_config_defaults(mpc_config *c) {
   c->steer_speeds[2] = mph2mps(30); c->steer_speeds[3] = mph2mps(25);
   c->max_iter = 3000;
   c->tol = 1e-8;
+  c->watchdog_trigger = 10;
+  c->filter_reset_trigger = 5;
+  c->tiny_step_tol = 10.0 * 2.220446049250313e-16;
   return MPC_OK;
 }
 
@@ -291,6 +298,16 @@ static int check_config(const mpc_config *c) {
   if (c->N < 2 || c->N > MPC_NMAX) return MPC_EINVAL;
   if (c->n_steers < 0 || c->n_steers > MPC_NTAB || c->n_steer_speeds < 1 || c->n_steer_speeds > MPC_NTAB) return MPC_EINVAL;
   if (!(c->dt > 0) || !(c->Lf > 0) || c->max_iter < 0 || !(c->tol > 0)) return MPC_EINVAL;
+  // the run()-level tables index fixed-size arrays on the device: keep the counts inside them
+  if (c->n_yaw_changes < 0 || c->n_yaw_changes > MPC_NTAB || c->n_yaw_change_speeds < 0 || c->n_yaw_change_speeds > MPC_NTAB) return MPC_EINVAL;
+  if (c->watchdog_trigger < 0 || c->filter_reset_trigger < 1 || !(c->tiny_step_tol >= 0)) return MPC_EINVAL;
+  return MPC_OK;
+}
+// what the MPC::run-level entry points need on top: a speed-limit table to read (the reference calls .back() on an
+// empty vector there, Vehicle.cpp:66-79 -- undefined behaviour; here it is an argument error) and a fit order that
+// fits MPC_NCOEF coefficients
+static int check_run_config(const mpc_config *c) {
+  if (c->n_yaw_change_speeds < 1 || c->max_fit_order < 3 || c->max_fit_order > MPC_NCOEF) return MPC_EINVAL;
   return MPC_OK;
 }
 
@@ -314,10 +331,12 @@ extern "C" int mpc_create(const mpc_config *cfg, int device, mpc_handle **out) {
   h->cfg = *cfg;
   h->device = device;
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+  cudaError_t ce = cudaGetDeviceProperties(&prop, device);
   h->sm_count = prop.multiProcessorCount;
-  CK(cudaMalloc(&h->d_counter, MPC_NCOUNTER * sizeof(int)));   // work-queue counter, per launch of a chain: records written / taken; horizon histogram
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  // work-queue counter, per launch of a chain: records written / taken; horizon histogram
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_counter, MPC_NCOUNTER * sizeof(int));
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { mpc_destroy(h); return cuda_fail(ce, "mpc_create"); }
   h->kernel_kind = MPC_KERNEL_AUTO;
   h->lane_threads = 0;
   h->lane_ctas_per_sm = 0;
@@ -336,6 +355,8 @@ extern "C" void mpc_destroy(mpc_handle *h) {
   cudaFree(h->d_counter);
   cudaFree(h->d_ckpt);
   cudaFree(h->d_perm);
+  cudaFree(h->d_restart);
+  cudaFree(h->d_scratch);
   cudaFree(h->d_in);
   cudaFree(h->d_out);
   cudaFree(h->d_iout);
@@ -354,33 +375,6 @@ extern "C" int mpc_set_config(mpc_handle *h, const mpc_config *cfg) {
   int rc = check_config(cfg);
   if (rc) return rc;
   h->cfg = *cfg;
-  return MPC_OK;
-}
-
-template <int G>
-static int launch(mpc_handle *h, KParams &kp, cudaStream_t st) {
-  const int threads = 128;
-  const int groups = threads / G;
-  kp.ws_stride = workspace_doubles(kp.Nmax);
-  const size_t smem = (size_t)groups * kp.ws_stride * sizeof(double);
-  static thread_local int cached_dev = -1;
-  static thread_local size_t cached_smem = 0;
-  if (cached_dev != h->device || cached_smem < smem) {
-    CK(cudaFuncSetAttribute(mpc_ipm_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cached_dev = h->device;
-    cached_smem = smem;
-  }
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_ipm_kernel<G>, threads, smem));
-  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "kernel does not fit on an SM (smem %zu)", smem); return MPC_ECUDA; }
-  long long want = ((long long)kp.B + groups - 1) / groups;
-  long long grid = (long long)h->sm_count * per_sm;
-  if (grid > want) grid = want;
-  if (grid < 1) grid = 1;
-  CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
-  mpc_ipm_kernel<G><<<(unsigned)grid, threads, smem, st>>>(kp);
-  CK(cudaGetLastError());
-  h->launches++;
   return MPC_OK;
 }
 
@@ -416,28 +410,30 @@ __global__ void mpc_horizon_scatter_kernel(const int *N_pp, int B, int *cursor, 
   }
 }
 
-// The solo kernel: one problem per lane, rows in shared memory, one-warp CTAs (mpc_lane_kernel.cuh).
-template <int NS, bool RESUME>
-static int launch_solo(mpc_handle *h, KParams &kp, cudaStream_t st, long long nmax) {
-  const size_t per = (size_t)NS * ST_ROW * sizeof(double);
-  int L = (int)((45 * 1024) / per);
-  if (L < 1) L = 1;
-  if (L > 32) L = 32;
-  const size_t smem = per * L;
-  static thread_local int cached_dev = -1;
-  if (cached_dev != h->device) {
-    CK(cudaFuncSetAttribute(mpc_solo_kernel<NS, RESUME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cached_dev = h->device;
+// Global scratch of the coop kernels (one block per resident lane group) and the restart list of a chain.
+template <int NS>
+static int ensure_coop_scratch(mpc_handle *h, KParams &kp, long long groups_total) {
+  const size_t per = (size_t)Lane<NS, true>::SC_SIZE;
+  const size_t need = per * (size_t)groups_total;
+  if (!h->d_scratch || h->cap_scratch < need) {
+    cudaFree(h->d_scratch);
+    h->d_scratch = nullptr; h->cap_scratch = 0;
+    CK(cudaMalloc(&h->d_scratch, need * sizeof(double)));
+    h->cap_scratch = need;
   }
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_solo_kernel<NS, RESUME>, 32, smem));
-  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "solo kernel does not fit on an SM (smem %zu)", smem); return MPC_ECUDA; }
-  long long grid = (long long)h->sm_count * per_sm, want = (nmax + L - 1) / L;
-  if (grid > want) grid = want;
-  if (grid < 1) grid = 1;
-  mpc_solo_kernel<NS, RESUME><<<(unsigned)grid, 32, smem, st>>>(kp, L);
-  CK(cudaGetLastError());
-  h->launches++;
+  kp.scratch = h->d_scratch; kp.scratch_stride = (long long)per;
+  return MPC_OK;
+}
+static int ensure_restart(mpc_handle *h, KParams &kp) {
+  if (!h->d_restart || h->cap_restart < (size_t)kp.B) {
+    cudaFree(h->d_restart);
+    h->d_restart = nullptr; h->cap_restart = 0;
+    CK(cudaMalloc(&h->d_restart, (size_t)kp.B * sizeof(int)));
+    h->cap_restart = kp.B;
+  }
+  kp.restart_list = h->d_restart;
+  kp.restart_count = h->d_counter + MPC_RESTART_COUNT;
+  kp.restart_cursor = h->d_counter + MPC_RESTART_CURSOR;
   return MPC_OK;
 }
 
@@ -449,6 +445,30 @@ static int launch_solo(mpc_handle *h, KParams &kp, cudaStream_t st, long long nm
 #ifndef MPC_LANE_MINB
 #define MPC_LANE_MINB 1   // CTAs per SM the lane kernel is compiled for (__launch_bounds__(256, MINB)): experiments only
 #endif
+// the final launch of a lane-kernel chain: the coop kernel on the parked / handed-over records and the restart list
+template <int NS>
+static int launch_finisher(mpc_handle *h, KParams &kp, cudaStream_t st, long long max_work) {
+  const int ct = 128, G = NS <= 16 ? 16 : 32, groups = ct / G;
+  const size_t smem = (size_t)groups * NS * ST_ROW_SH * sizeof(double);
+  static thread_local int cached_dev2 = -1;
+  if (cached_dev2 != h->device) {
+    CK(cudaFuncSetAttribute(mpc_coop_resume_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cached_dev2 = h->device;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_resume_kernel<NS>, ct, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long g2 = (long long)h->sm_count * per_sm, w2 = (max_work + groups - 1) / groups;
+  if (g2 > w2) g2 = w2;
+  if (g2 < 1) g2 = 1;
+  int rc = ensure_coop_scratch<NS>(h, kp, g2 * groups);
+  if (rc) return rc;
+  mpc_coop_resume_kernel<NS><<<(unsigned)g2, ct, smem, st>>>(kp);
+  CK(cudaGetLastError());
+  h->launches++;
+  return MPC_OK;
+}
+
 template <int NS, int MINB>
 static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   static thread_local int cached_dev = -1;
@@ -480,13 +500,13 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   int *cnt = h->d_counter + 1;   // [2k] records written by launch k of the chain, [2k + 1] cursor of the coop kernel
   kp.ckpt = nullptr; kp.ckpt_in = nullptr; kp.ckpt_cap = 0; kp.park_lanes = 0; kp.handoff_iter = INT_MAX;
   kp.ckpt_count = cnt; kp.ckpt_next = cnt + 1; kp.ckpt_in_count = cnt;
+  kp.chain_counts = nullptr;
+  int rc = ensure_restart(h, kp);
+  if (rc) return rc;
   CK(cudaMemsetAsync(kp.counter, 0, MPC_HIST0 * sizeof(int), st));
-  if (!rule1 && park <= 0) {
-    mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
-    CK(cudaGetLastError());
-    h->launches++;
-    return MPC_OK;
-  }
+  // The lane kernel hands every problem that needs a rare branch of the algorithm (restoration phase, watchdog, a
+  // large filter, tiny steps) to the coop kernel: as a record where a slot is free, else through the restart list.
+  // So a chain always ends with a launch of the coop kernel; it returns at once when it has nothing to do.
   const size_t rec = Lane<NS, false>::CK_SIZE;
   size_t cap = (size_t)kp.B / 8;
   const size_t sparse = (size_t)grid * threads * (park > 0 ? park : 0) / 32 + 1024;
@@ -502,14 +522,17 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
       h->d_ckpt = nullptr;
       cap /= 4;
     }
-    if (!h->d_ckpt) {
-      mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
-      CK(cudaGetLastError());
-      h->launches++;
-      return MPC_OK;
-    }
-    h->cap_ckpt = cap; h->ckpt_ns = NS;
+    if (h->d_ckpt) { h->cap_ckpt = cap; h->ckpt_ns = NS; }
   }
+  if (!h->d_ckpt) {
+    // no record buffers at all: one launch, hand-overs go through the restart list
+    mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
+    CK(cudaGetLastError());
+    h->launches++;
+    h->pre_recorded = false;
+    return launch_finisher<NS>(h, kp, st, kp.B);
+  }
+  cap = h->cap_ckpt;
   double *buf[2] = {h->d_ckpt, h->d_ckpt + h->cap_ckpt * rec};
   kp.ckpt_cap = (int)cap;
   kp.ckpt = buf[0]; kp.ckpt_count = cnt;
@@ -543,26 +566,7 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
     h->pre_kp = kp;
     h->pre_rec = (int)Lane<NS, false>::CK_SIZE; h->pre_cki = (int)Lane<NS, false>::CK_I;
   }
-  if (h->solo_finisher) {
-    return launch_solo<NS, true>(h, kp, st, (long long)kp.ckpt_cap);
-  } else {
-    const int ct = 128, G = NS <= 16 ? 16 : 32, groups = ct / G;
-    const size_t smem = (size_t)groups * NS * ST_ROW_SH * sizeof(double);
-    static thread_local int cached_dev2 = -1;
-    if (cached_dev2 != h->device) {
-      CK(cudaFuncSetAttribute(mpc_coop_resume_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cached_dev2 = h->device;
-    }
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_resume_kernel<NS>, ct, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long g2 = (long long)h->sm_count * per_sm, w2 = ((long long)kp.ckpt_cap + groups - 1) / groups;
-    if (g2 > w2) g2 = w2;
-    mpc_coop_resume_kernel<NS><<<(unsigned)g2, ct, smem, st>>>(kp);
-    CK(cudaGetLastError());
-    h->launches++;
-  }
-  return MPC_OK;
+  return launch_finisher<NS>(h, kp, st, (long long)kp.B < (long long)cap * 2 ? kp.B : (long long)cap * 2);
 }
 
 // The coop kernel: one problem per group of 16 or 32 lanes, per-stage rows in shared memory.
@@ -584,6 +588,8 @@ static int launch_coop(mpc_handle *h, KParams &kp, cudaStream_t st) {
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = INT_MAX; kp.ckpt_count = h->d_counter + 1; kp.ckpt_next = h->d_counter + 2;
+  int rc = ensure_coop_scratch<NS>(h, kp, grid * groups);
+  if (rc) return rc;
   if (kp.counter) CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), st));
   mpc_coop_kernel<NS><<<(unsigned)grid, threads, smem, st>>>(kp);
   CK(cudaGetLastError());
@@ -609,13 +615,12 @@ extern "C" int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, 
   h->resume_phases = resume_launches;
   h->resume_min = resume_min_records;
   h->sort_ragged = (flags & MPC_TAIL_SORT_RAGGED) != 0;
-  h->solo_finisher = (flags & MPC_TAIL_SOLO_FINISHER) != 0;
   h->no_early_copy = (flags & MPC_TAIL_LATE_COPY) != 0;
   return MPC_OK;
 }
 
 extern "C" int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm) {
-  if (!h || kind < MPC_KERNEL_AUTO || kind > MPC_KERNEL_SOLO) return MPC_EINVAL;
+  if (!h || (kind != MPC_KERNEL_AUTO && kind != MPC_KERNEL_LANE && kind != MPC_KERNEL_COOP)) return MPC_EINVAL;
   if (lane_threads != 0 && (lane_threads < 32 || lane_threads > 256 || lane_threads % 32)) return MPC_EINVAL;
   h->kernel_kind = kind;
   h->lane_threads = lane_threads;
@@ -637,6 +642,7 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   kp.dt = c.dt; kp.Lf = c.Lf; kp.cte_panic = c.cte_panic; kp.epsi_panic = c.epsi_panic;
   kp.max_speed = c.max_speed; kp.max_steering = c.max_steering; kp.max_accel = c.max_accel; kp.max_decel = c.max_decel;
   kp.tol = c.tol;
+  kp.watchdog_trigger = c.watchdog_trigger; kp.filter_reset_trigger = c.filter_reset_trigger; kp.tiny_step_tol = c.tiny_step_tol;
   memcpy(kp.weights, c.weights, sizeof(kp.weights));
   memcpy(kp.steers, c.steers, sizeof(kp.steers));
   memcpy(kp.steer_speeds, c.steer_speeds, sizeof(kp.steer_speeds));
@@ -648,27 +654,11 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   // Kernel choice (crossovers measured on B200, profiles/r01_kernel_crossover.txt): below MPC_LANE_MIN_BATCH
   // problems there are fewer problems than lanes and the time is set by the longest-running problem, so the
   // coop kernel (one problem per group of 16/32 lanes) wins; above it the lane kernel (one problem per lane)
-  // has the throughput.  The warp kernel is the first version, kept selectable as a cross-check.
+  // has the throughput.
   int kind = h->kernel_kind;
   if (kind == MPC_KERNEL_AUTO) {
     if (c.N > 32) kind = B <= MPC_COOP_MAX_BATCH_LONG ? MPC_KERNEL_COOP : MPC_KERNEL_LANE;
     else kind = B >= MPC_LANE_MIN_BATCH ? MPC_KERNEL_LANE : MPC_KERNEL_COOP;
-  }
-  if (kind == MPC_KERNEL_SOLO) {
-    CK(cudaMemsetAsync(kp.counter, 0, sizeof(int), (cudaStream_t)cuda_stream));
-    kp.ckpt = nullptr; kp.ckpt_cap = 0; kp.handoff_iter = INT_MAX;
-    if (c.N <= 10) return launch_solo<10, false>(h, kp, (cudaStream_t)cuda_stream, B);
-#ifndef MPC_DEV_N10
-    if (c.N <= 20) return launch_solo<20, false>(h, kp, (cudaStream_t)cuda_stream, B);
-    if (c.N <= 32) return launch_solo<32, false>(h, kp, (cudaStream_t)cuda_stream, B);
-    return launch_solo<MPC_NMAX, false>(h, kp, (cudaStream_t)cuda_stream, B);
-#else
-    return MPC_EINVAL;   // development build (-DMPC_DEV_N10, a third of the compile time): N <= 10 only
-#endif
-  }
-  if (kind == MPC_KERNEL_WARP) {
-    if (c.N > 32) { snprintf(g_err, sizeof(g_err), "warp kernel handles N <= 32"); return MPC_EINVAL; }
-    return launch<32>(h, kp, (cudaStream_t)cuda_stream);
   }
   if (kind == MPC_KERNEL_COOP) {
     if (h->one_shot) kp.counter = nullptr;   // mpc_solve_one: one group, no work queue
@@ -720,11 +710,14 @@ __global__ void mpc_patch_outputs_kernel(const KParams P, int rec_size, int cki,
   const ChainIO io = chain_resolve(P);
   const size_t B = (size_t)P.B;
   const int R = A.rows[0] + A.rows[1] + A.rows[2] + A.rows[3] + 2;
-  const long long total = (long long)io.n * R;
+  int n_restart = *P.restart_count;   // problems the final launch solved from the start (no record)
+  if (n_restart > P.B) n_restart = P.B;
+  const int n_all = io.n + n_restart;
+  const long long total = (long long)n_all * R;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % io.n);
-    int r = (int)(idx / io.n);
-    const int b = (int)io.in[(size_t)k * rec_size + cki];
+    const int k = (int)(idx % n_all);
+    int r = (int)(idx / n_all);
+    const int b = k < io.n ? (int)io.in[(size_t)k * rec_size + cki] : P.restart_list[k - io.n];
     if (r >= R - 2) {
       const int a = r - (R - 2);
       if (A.idst[a]) A.idst[a][b] = A.isrc[a][b];
@@ -742,6 +735,7 @@ static int ensure_staging(mpc_handle *h, size_t B, int N, bool with_w) {
   if (h->d_in && h->cap_B >= B && h->cap_N >= N && (h->cap_w || !with_w)) return MPC_OK;
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_iout); cudaFreeHost(h->h_pin);
   h->d_in = h->d_out = nullptr; h->d_iout = nullptr; h->h_pin = nullptr;
+  h->cap_B = 0; h->cap_N = 0; h->cap_w = false;   // a failed allocation below must not leave a capacity behind
   size_t cap = B < 256 ? 256 : B;
   size_t nin = (6 + 5 + 2 + 12 + 1) * cap;            // state, coeffs, yaw, weights, dt
   size_t nout = (9 + 2 * (size_t)N + (8 * (size_t)N - 2)) * cap;
@@ -825,6 +819,13 @@ extern "C" int mpc_solve_batch_host(mpc_handle *h, int B, const double *state, c
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  }
+  if (N_per) {
+    // ragged batch: rows at or beyond a problem's horizon are left untouched by the kernels, and the copies back
+    // are whole arrays -- so the staging buffers start as copies of the caller's arrays
+    if (traj_x) CK(cudaMemcpyAsync(d_tx, traj_x, (size_t)N * sB, cudaMemcpyHostToDevice, st));
+    if (traj_y) CK(cudaMemcpyAsync(d_ty, traj_y, (size_t)N * sB, cudaMemcpyHostToDevice, st));
+    if (full) CK(cudaMemcpyAsync(d_full, full, (8 * (size_t)N - 2) * sB, cudaMemcpyHostToDevice, st));
   }
   h->want_pre = early; h->pre_recorded = false;
   rc = mpc_solve_batch(h, B, (const double *)u_state, (const double *)u_coef, (const double *)u_ylo, (const double *)u_yhi,
@@ -991,6 +992,7 @@ static int ensure_run_ws(mpc_handle *h, size_t B) {
   if (h->d_run && h->cap_run >= B) return MPC_OK;
   cudaFree(h->d_run); cudaFree(h->d_run_i);
   h->d_run = nullptr; h->d_run_i = nullptr;
+  h->cap_run = 0;
   size_t cap = B < 1024 ? 1024 : B;
   CK(cudaMalloc(&h->d_run, 26 * cap * sizeof(double)));
   CK(cudaMalloc(&h->d_run_i, 2 * cap * sizeof(int)));
@@ -1003,6 +1005,7 @@ extern "C" int mpc_run_batch(mpc_handle *h, int B, const double *pose, const dou
                              double *coeffs_out, double *ptsx_v, double *ptsy_v, int *status, int *iters,
                              void *cuda_stream) {
   if (!h || B < 0 || !pose || !ptsx || !ptsy || !out8 || npts < 3 || npts > MPC_MAX_WAYPOINTS) return MPC_EINVAL;
+  if (check_run_config(&h->cfg)) return MPC_EINVAL;
   if (B == 0) return MPC_OK;
   CK(cudaSetDevice(h->device));
   int rc = ensure_run_ws(h, (size_t)B);
@@ -1033,6 +1036,7 @@ extern "C" int mpc_rollout(mpc_handle *h, int V, int T, const double *track_x, c
                            void *cuda_stream) {
   if (!h || V < 0 || T < 0 || !track_x || !track_y || n_track < 6 || !veh || !seg || !(dt_ctrl > 0)) return MPC_EINVAL;
   if (h->cfg.latency_ms && !pending) return MPC_EINVAL;
+  if (check_run_config(&h->cfg)) return MPC_EINVAL;
   if (V == 0 || T == 0) return MPC_OK;
   CK(cudaSetDevice(h->device));
   int rc = ensure_run_ws(h, (size_t)V);
@@ -1119,4 +1123,4 @@ extern "C" int mpc_tail_counts(mpc_handle *h, int *parked, int n) {
 
 extern "C" long long mpc_launch_count(const mpc_handle *h) { return h ? h->launches : 0; }
 extern "C" const char *mpc_last_error(void) { return g_err; }
-extern "C" const char *mpc_version(void) { return "mpc_b200 0.2 (sm_100a, fp64 interior point; lane, coop and solo kernels, explicit fma)"; }
+extern "C" const char *mpc_version(void) { return "mpc_b200 0.3 (sm_100a, fp64 interior point with restoration phase and watchdog; lane and coop kernels, explicit fma)"; }

@@ -7,6 +7,11 @@ extern "C" int mpc_run_prepare(const mpc_config *cfg, const double *pose, double
                                double *ptsy, int npts, double *state, double *coeffs, double *yaw_lo,
                                double *yaw_hi, mpc_run_aux *aux) {
   if (!cfg || !pose || !ptsx || !ptsy || !state || !coeffs || !yaw_lo || !yaw_hi || !aux) return MPC_EINVAL;
+  // an empty speed-limit table is undefined behaviour in the reference (.back() of an empty vector, Vehicle.cpp:66-79)
+  if (cfg->n_yaw_changes < 0 || cfg->n_yaw_changes > MPC_NTAB || cfg->n_yaw_change_speeds < 1 ||
+      cfg->n_yaw_change_speeds > MPC_NTAB || cfg->n_steers < 0 || cfg->n_steers > MPC_NTAB || cfg->n_steer_speeds < 1 ||
+      cfg->n_steer_speeds > MPC_NTAB || cfg->max_fit_order < 3 || cfg->max_fit_order > MPC_NCOEF)
+    return MPC_EINVAL;
   return mpcrun::run_prepare(cfg, pose, steering, ptsx, ptsy, npts, state, coeffs, yaw_lo, yaw_hi, aux);
 }
 

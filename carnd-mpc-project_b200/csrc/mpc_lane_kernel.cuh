@@ -42,7 +42,8 @@ enum {
   LM_SOC_TRIAL,   // evaluate the corrected trial point
   LM_RESOLVE,     // SOC failed: recompute the uncorrected direction, then backtrack
   LM_FINISH,      // write the outputs
-  LM_DONE         // queue empty
+  LM_DONE,        // queue empty
+  LM_LSFAIL       // the step size fell below alpha_min: Ipopt's restoration phase (coop kernel only)
 };
 
 // constants of one problem (thread-private)
@@ -99,10 +100,16 @@ struct Lane {
   // sweeps that are parallel over the horizon run one stage per lane (mpc_coop_kernel); PAR = false with SH: one
   // problem per lane as in the lane kernel, only the rows live in shared memory (mpc_solo_kernel).
   enum { NS_GROUP = PAR ? (NS <= 16 ? 16 : 32) : 1, NPASS = (NS + NS_GROUP - 1) / NS_GROUP };   // stages per lane of a group
+  // FULL: the kernel carries every branch of the algorithm.  The one-problem-per-lane kernel keeps to the branches
+  // that occur on almost every problem (Newton step, inertia correction, second-order correction, backtracking); a
+  // problem that needs another one -- restoration phase, watchdog, tiny step, a 9th filter entry -- sets `escalate`
+  // at a point where nothing of the trip has been committed, and the coop kernel repeats that trip and goes on.
+  static constexpr bool FULL = PAR;
+  enum { NFILT = PAR ? K_NFILT_FULL : K_NFILT };
   typedef typename LaneRows<NS, SH, PAR>::type Rows;
   alignas(16) Rows ST;
   alignas(16) double PC[LC_SIZE];
-  alignas(16) double FLT[2 * K_NFILT];
+  alignas(16) double FLT[2 * NFILT];
   double c0[6], c0t[6], cs0[6];
   // ---- lane group (coop kernel): this lane's index in its group, group size, member mask; (0, 1, -) for
   // the one-problem-per-lane kernel
@@ -113,6 +120,16 @@ struct Lane {
   int m1, m3;
   bool solve_ok, lh_stale, no_handoff;
   int b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt;
+  // line-search state beyond one iteration (Ipopt's BacktrackingLineSearch / FilterLSAcceptor members)
+  int wd_short;                    // watchdog_shortened_iter_: successive iterations that needed backtracking
+  int n_filter_resets, succ_filter_rej;
+  bool last_rej_filter, acceptable_now, escalate, tiny_screen;
+  double tiny_tol;                 // KParams::tiny_step_tol
+  // FULL only
+  bool in_watchdog, wd_skip, force_accept, tiny_last, tiny_flag, was_tiny;
+  int wd_trial;
+  double alpha_max, wd_alpha_test, tiny_all, dy_max;
+  double *scratch;                 // this group's global scratch (watchdog backup, restoration rows)
   double mu, tau, theta_min, theta_max, dw, dw_last, dw_used;
   double alpha, alpha_z, alpha_test, alpha_soc, alpha_min;
   double ls_theta, ls_phi, ls_gbd, pow_gbd, pow_theta;
@@ -208,8 +225,17 @@ struct Lane {
     dw = 0.0; dw_last = 0.0; dw_used = 0.0;
     nfilt = 0; iter = 0; accept_cnt = 0; status = 0; ntrial = 0; soc_cnt = 0;
     alpha = 0.0; alpha_z = 0.0;
+    reset_line_search();
+    n_filter_resets = 0; acceptable_now = false; escalate = false; tiny_screen = false; tiny_flag = false;
+    force_accept = false; wd_skip = false; was_tiny = false; wd_trial = 0;
+    tiny_tol = P.tiny_step_tol;
     mode = LM_EV0;
     gsync();
+  }
+  // BacktrackingLineSearch::Reset (at every change of the barrier parameter): empty filter, no watchdog
+  __device__ __forceinline__ void reset_line_search() {
+    nfilt = 0; succ_filter_rej = 0; last_rej_filter = false;
+    wd_short = 0; in_watchdog = false; tiny_last = false;
   }
 
 
@@ -705,7 +731,7 @@ struct Lane {
     for (int k = 0; k < 6; k++) { const double t = __shfl_down_sync(gm, lam[k], 1, G); lo_n[k] = hasu ? t : 0.0; }
     StageLin L;
     lin_at(tg, s[3], u0, L);
-    double lp[6] = {0, 0, 0, 0, 0, 0}, lmax = 0.0;
+    double lp[6] = {0, 0, 0, 0, 0, 0}, lmax = 0.0, dym = 0.0;
     double ds[6] = {0, 0, 0, 0, 0, 0}, du0 = 0.0, du1 = 0.0, il[4], iu[4];
     if (costate) {
       double h[6] = {0, 0, 0, 0, 0, 0};
@@ -746,7 +772,7 @@ struct Lane {
       }
       if (act) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) lmax = nanmax(lmax, fabs(lp[k]));
+        for (int k = 0; k < 6; k++) { lmax = nanmax(lmax, fabs(lp[k])); dym = nanmax(dym, fabs(lp[k] - lam[k])); }
       }
       if (do_update) {
         if (act) {
@@ -854,6 +880,7 @@ struct Lane {
     }
     dinf = gmax<NS_GROUP>(r, gm); cviol = gmax<NS_GROUP>(cv, gm); lam1 = gsum<NS_GROUP>(l1, gm); z1 = gsum<NS_GROUP>(zz, gm);
     amin = gmin<NS_GROUP>(am, gm); amax = gmax<NS_GROUP>(aM, gm); lsq_lmax = gmax<NS_GROUP>(lmax, gm);
+    dy_max = gmax<NS_GROUP>(dym, gm);
     gsync();
   }
   // More stages than lanes in the group: the neighbours' old values are read from their rows before anything is
@@ -866,7 +893,7 @@ struct Lane {
     const double dwv = ls ? 0.0 : dw_used;
     const double zcap = K_KAPPA_SIGMA * mu, zfloor = mu / K_KAPPA_SIGMA;
     const bool costate = do_update || ls;
-    double lp[NPASS][6], h[NPASS][6], lmax = 0.0;
+    double lp[NPASS][6], h[NPASS][6], lmax = 0.0, dym = 0.0;
     StageLin L[NPASS];
     // ---- phase 1: h_i = (W + Sigma) d_i + grad terms at the OLD iterate (reads only)
 #pragma unroll
@@ -947,7 +974,7 @@ struct Lane {
         for (int k = 0; k < 6; k++) lmax = nanmax(lmax, fabs(lp[p][k]));
         double lam[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) lam[k] = ST[i][ST_LAM + k];
+        for (int k = 0; k < 6; k++) { lam[k] = ST[i][ST_LAM + k]; dym = nanmax(dym, fabs(lp[p][k] - lam[k])); }
         if (do_update) {
           double sv[6], ds[6], zl[4], zu[4], il[4], iu[4], iln[4], iun[4];
           double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
@@ -1061,6 +1088,7 @@ struct Lane {
     }
     dinf = gmax<NS_GROUP>(r, gm); cviol = gmax<NS_GROUP>(cv, gm); lam1 = gsum<NS_GROUP>(l1, gm); z1 = gsum<NS_GROUP>(zz, gm);
     amin = gmin<NS_GROUP>(am, gm); amax = gmax<NS_GROUP>(aM, gm); lsq_lmax = gmax<NS_GROUP>(lmax, gm);
+    dy_max = gmax<NS_GROUP>(dym, gm);
     gsync();
   }
   // max_i |slack_i * z_i - m|  from the extreme complementarity products
@@ -1337,6 +1365,8 @@ struct Lane {
         du0 = fma(kg[4], dp, fma(kg[3], t[3], fma(kg[2], t[2], fma(kg[1], t[1], fma(kg[0], t[0], kg[10])))));
         du1 = fma(kg[9], dp, fma(kg[8], t[3], fma(kg[7], t[2], fma(kg[6], t[1], fma(kg[5], t[0], kg[11])))));
         ST[i][ST_DU + 0] = du0; ST[i][ST_DU + 1] = du1;
+        // a "tiny step" (Ipopt's DetectTinyStep) needs every component of the step relatively tiny: screen on one
+        if (i == 0) tiny_screen = fabs(du0) <= 2.0 * tiny_tol * (1.0 + fabs(u0));
         if (ls) {
 #pragma unroll
           for (int k = 0; k < 6; k++) d[k] = 0.0;
@@ -1455,7 +1485,7 @@ struct Lane {
       for (int k = 0; k < 6; k++) t[k] = tn[k];
       dp = du0;
     }
-    double rmax = 0.0, zn = 1.0, zd = 0.0, gbd = 0.0;
+    double rmax = 0.0, zn = 1.0, zd = 0.0, gbd = 0.0, tall = 1.0;
 #pragma unroll
     for (int p = 0; p < NPASS; p++) {
     const int i = g0 + p * G;
@@ -1465,6 +1495,12 @@ struct Lane {
       const bool hasu = i < N - 1;
       const double psi = ST[i][ST_S + 2], v = ST[i][ST_S + 3];
       const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+      {   // DetectTinyStep: |dx| <= tiny_step_tol (1 + |x|) in every component
+        bool t = fabs(mdu0) <= tiny_tol * (1.0 + fabs(u0)) && fabs(mdu1) <= tiny_tol * (1.0 + fabs(u1));
+#pragma unroll
+        for (int k = 0; k < 6; k++) t = t && fabs(mt[k]) <= tiny_tol * (1.0 + fabs(ST[i][ST_S + k]));
+        if (!t) tall = 0.0;
+      }
       double acc = fma(we2(i) * ST[i][ST_S + 5], mt[5], fma(wc2(i) * ST[i][ST_S + 4], mt[4], fma(nv2(i), v, wv2 * (v - vref(i))) * mt[3]));
       if (hasu) {
         double gd = wd2 * u0;
@@ -1500,6 +1536,7 @@ struct Lane {
     }
     rmax = gmax<NS_GROUP>(rmax, gm);
     gbd_new = gsum<NS_GROUP>(gbd, gm);
+    tiny_all = gmin<NS_GROUP>(tall, gm);
     if (ls) return;
     alpha_soc = (rmax > tau) ? tau / rmax : 1.0;
     alpha_z = (zd > 0.0 && tau * zn < zd) ? tau * zn / zd : 1.0;
@@ -1513,35 +1550,49 @@ struct Lane {
   __device__ __forceinline__ bool armijo(double a, double phi_t) const {
     return cmp_le(phi_t - ls_phi, K_ETA_PHI * a * ls_gbd, ls_phi);
   }
-  __device__ bool ls_accept(double a, double theta_t, double phi_t) const {
-    if (!(theta_t == theta_t) || !(phi_t == phi_t) || isinf(phi_t)) return false;
-    if (theta_t > theta_max) return false;
-    bool ok;
-    if (a > 0.0 && is_ftype(a) && ls_theta <= theta_min) {
-      ok = armijo(a, phi_t);
-    } else {
-      ok = cmp_le(theta_t, (1.0 - K_GAMMA_THETA) * ls_theta, ls_theta) ||
-           cmp_le(phi_t - ls_phi, -K_GAMMA_PHI * ls_theta, ls_phi);
+  // FilterLSAcceptor::IsAcceptableToCurrentIterate (obj_max_inc test unless called from the restoration phase)
+  __device__ bool acceptable_to_current(double theta_t, double phi_t, bool from_resto) const {
+    if (!from_resto && phi_t > ls_phi) {
+      double basval = 1.0;
+      if (fabs(ls_phi) > 10.0) basval = log10(fabs(ls_phi));
+      if (log10(phi_t - ls_phi) > K_OBJ_MAX_INC + basval) return false;
     }
-    if (!ok) return false;
+    return cmp_le(theta_t, (1.0 - K_GAMMA_THETA) * ls_theta, ls_theta) ||
+           cmp_le(phi_t - ls_phi, -K_GAMMA_PHI * ls_theta, ls_phi);
+  }
+  __device__ bool filter_ok(double theta_t, double phi_t) const {
     for (int k = 0; k < nfilt; k++) {
       const double f_t = FLT[2 * k], f_p = FLT[2 * k + 1];
       if (!(cmp_le(theta_t, f_t, f_t) || cmp_le(phi_t, f_p, f_p))) return false;
     }
     return true;
   }
+  // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint without its side effects: 2 = acceptable, 1 = rejected by the
+  // filter, 0 = rejected by the tests against the current iterate, -1 = not a number / above theta_max
+  __device__ int ls_accept(double a, double theta_t, double phi_t) const {
+    if (!(theta_t == theta_t) || !(phi_t == phi_t) || isinf(phi_t)) return -1;
+    if (theta_t > theta_max) return -1;
+    bool ok;
+    if (a > 0.0 && is_ftype(a) && ls_theta <= theta_min) ok = armijo(a, phi_t);
+    else ok = acceptable_to_current(theta_t, phi_t, false);
+    if (!ok) return 0;
+    return filter_ok(theta_t, phi_t) ? 2 : 1;
+  }
+  // entries the filter would hold after filter_add(th, ph) if it had room
+  __device__ int filter_count_after(double th, double ph) const {
+    int k = 1;
+    for (int j = 0; j < nfilt; j++) k += !(FLT[2 * j] >= th && FLT[2 * j + 1] >= ph);
+    return k;
+  }
+  // drop the entries the new one dominates, then add it (a full filter keeps what it has, like the oracle's)
   __device__ void filter_add(double th, double ph) {
     int k = 0;
     for (int j = 0; j < nfilt; j++) {
       const double f_t = FLT[2 * j], f_p = FLT[2 * j + 1];
       if (!(f_t >= th && f_p >= ph)) { FLT[2 * k] = f_t; FLT[2 * k + 1] = f_p; k++; }
     }
-    if (k == K_NFILT) {   // full: drop the oldest entry
-      for (int j = 1; j < k; j++) { FLT[2 * (j - 1)] = FLT[2 * j]; FLT[2 * (j - 1) + 1] = FLT[2 * j + 1]; }
-      k--;
-    }
-    FLT[2 * k] = th; FLT[2 * k + 1] = ph;
-    nfilt = k + 1;
+    if (k < NFILT) { FLT[2 * k] = th; FLT[2 * k + 1] = ph; k++; }
+    nfilt = k;
   }
 
   // Ipopt's convergence tests and monotone barrier update at the (new) iterate; sets mode
@@ -1556,24 +1607,34 @@ struct Lane {
     if (E0 <= P.tol && dinf_u <= K_DUAL_INF_TOL && cviol <= K_CONSTR_VIOL_TOL && compl_u <= K_COMPL_INF_TOL) {
       status = 1; mode = LM_FINISH; return;
     }
+    acceptable_now = false;
     if (E0 <= K_ACCEPT_TOL && cviol <= K_ACCEPT_CONSTR_VIOL_TOL && compl_u <= K_ACCEPT_COMPL_INF_TOL) {
+      acceptable_now = true;
       if (++accept_cnt >= K_ACCEPT_ITER) { status = 4; mode = LM_FINISH; return; }
     } else {
       accept_cnt = 0;
     }
     if (!(E0 == E0)) { status = 11; mode = LM_FINISH; return; }
     if (iter >= P.max_iter) { status = 2; mode = LM_FINISH; return; }
+    // monotone barrier update; a repeated tiny step (FULL kernels only) forces a decrease, and ends the run when
+    // the barrier parameter is at its floor
+    bool tf = FULL && tiny_flag;
     for (;;) {
       const double cm = compl_err(mu);
       const double Emu = nanmax(dinf / sd, nanmax(cviol, cm / sc));
-      if (!(Emu <= K_KAPPA_EPS * mu)) break;
+      if (!(Emu <= K_KAPPA_EPS * mu) && !tf) break;
       const double mu_min = fmin(P.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0);
       const double new_mu = fmax(mu_min, fmin(K_KAPPA_MU * mu, mu * sqrt(mu)));
-      if (new_mu == mu) break;
+      if (new_mu == mu) {
+        if (tf) { status = 3; mode = LM_FINISH; return; }
+        break;
+      }
       mu = new_mu;
       tau = fmax(K_TAU_MIN, 1.0 - mu);
-      nfilt = 0;
+      tf = false;
+      reset_line_search();
     }
+    tiny_flag = false;
     dw = 0.0;
     mode = LM_NEWTON;
   }
@@ -1664,7 +1725,8 @@ struct Lane {
                           alpha_min, ls_theta, ls_phi, ls_gbd, pow_gbd, pow_theta, fx, lsum, theta, ft, lt, tht,
                           theta_soc_old, dinf, cviol, amin, amax, lam1, z1, lsq_lmax, gbd_new};
     for (int k = 0; k < 32; k++) r[CK_D + k] = d[k];
-    const int n[12] = {b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt, 0, 0, 0};
+    const int n[12] = {b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt, wd_short,
+                       n_filter_resets * 8 + succ_filter_rej, (last_rej_filter ? 1 : 0) | (acceptable_now ? 2 : 0)};
     for (int k = 0; k < 12; k++) r[CK_I + k] = (double)n[k];
   }
   __device__ void load(const double *r) {
@@ -1684,8 +1746,50 @@ struct Lane {
     const double *n = r + CK_I;
     b = (int)n[0]; mode = (int)n[2]; status = (int)n[3]; iter = (int)n[4]; accept_cnt = (int)n[5]; nfilt = (int)n[6];
     ntrial = (int)n[7]; soc_cnt = (int)n[8];
+    wd_short = (int)n[9]; n_filter_resets = (int)n[10] >> 3; succ_filter_rej = (int)n[10] & 7;
+    last_rej_filter = ((int)n[11] & 1) != 0; acceptable_now = ((int)n[11] & 2) != 0;
+    escalate = false; tiny_screen = false; tiny_flag = false; tiny_last = false; in_watchdog = false;
+    force_accept = false; wd_skip = false; was_tiny = false; wd_trial = 0;
     lh_stale = true;
     gsync();
+  }
+
+  // ---- global scratch of a lane group (FULL kernels): watchdog backup, restoration-phase backup and rows
+  enum { SC_WD_ROWS = 0, SC_WD_SC = NS * ST_KEEP, SC_BK_ROWS = SC_WD_SC + 32, SC_BK_SC = SC_BK_ROWS + NS * ST_KEEP,
+         SC_RS = SC_BK_SC + 32, SC_SIZE = SC_RS + NS * 64 };
+  // StartWatchDog: remember the iterate, the search direction and the line search's reference values
+  __device__ void watchdog_start() {
+    in_watchdog = true; wd_trial = 0; wd_alpha_test = alpha_max;
+    double *r = scratch + SC_WD_ROWS;
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep)
+      for (int k = 0; k < ST_KEEP; k++) r[i * ST_KEEP + k] = ST[i][k];
+    if (g0 == 0) {
+      double *q = scratch + SC_WD_SC;
+      const double d[26] = {alpha_max, alpha_z, ls_theta, ls_phi, ls_gbd, pow_gbd, pow_theta, alpha_min, fx, lsum, theta,
+                            dw_used, dinf, cviol, amin, amax, lam1, z1, c0[0], c0[1], c0[2], c0[3], c0[4], c0[5], 0.0, 0.0};
+      for (int k = 0; k < 26; k++) q[k] = d[k];
+    }
+    gsync();
+  }
+  // StopWatchDog: back to that iterate and direction; the line search goes on from there by backtracking
+  __device__ void watchdog_stop() {
+    gsync();
+    const double *r = scratch + SC_WD_ROWS;
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep)
+      for (int k = 0; k < ST_KEEP; k++) ST[i][k] = r[i * ST_KEEP + k];
+    const double *q = scratch + SC_WD_SC;
+    alpha_max = q[0]; alpha_z = q[1]; ls_theta = q[2]; ls_phi = q[3]; ls_gbd = q[4]; pow_gbd = q[5]; pow_theta = q[6];
+    alpha_min = q[7]; fx = q[8]; lsum = q[9]; theta = q[10]; dw_used = q[11]; dinf = q[12]; cviol = q[13]; amin = q[14];
+    amax = q[15]; lam1 = q[16]; z1 = q[17];
+    for (int k = 0; k < 6; k++) c0[k] = q[18 + k];
+    in_watchdog = false; wd_short = 0; lh_stale = true;
+    gsync();
+  }
+  // Ipopt's feasibility restoration phase (placeholder until the next commit: stop with restoration_failure)
+  __device__ void restoration(const KParams &P) {
+    status = 9; mode = LM_FINISH;
   }
 
   // ---- one trip of the state machine, in four slots (shared by the lane kernel and the coop kernel) -------
@@ -1696,6 +1800,27 @@ struct Lane {
       const double a = m1 == LM_EV0 ? 0.0 : (m1 == LM_TRIAL ? alpha : alpha_soc);
       eval_sweep(a);
     }
+  }
+  // the trial point is the new iterate: filter reset heuristic, filter update (FilterLSAcceptor::
+  // CheckAcceptabilityOfTrialPoint's tail and UpdateForNextIteration), watchdog counter.  Returns false if a
+  // one-problem-per-lane kernel cannot hold the filter entry: nothing has been changed, the problem escalates.
+  __device__ __forceinline__ bool commit_accept(const KParams &P, double phi_t) {
+    const bool add = !is_ftype(alpha_test) || !armijo(alpha_test, phi_t);
+    const bool heur = n_filter_resets < K_MAX_FILTER_RESETS;
+    const bool reset = heur && last_rej_filter && succ_filter_rej + 1 >= P.filter_reset_trigger;
+    const double th_add = (1.0 - K_GAMMA_THETA) * ls_theta, ph_add = ls_phi - K_GAMMA_PHI * ls_theta;
+    if (!FULL && add && !reset && filter_count_after(th_add, ph_add) > NFILT) return false;
+    if (heur) {
+      if (last_rej_filter) {
+        if (reset) { n_filter_resets++; nfilt = 0; succ_filter_rej = 0; } else succ_filter_rej++;
+      } else {
+        succ_filter_rej = 0;
+      }
+      last_rej_filter = false;
+    }
+    if (add) filter_add(th_add, ph_add);
+    if (ntrial == 0) wd_short = 0; else wd_short++;
+    return true;
   }
   // slot 2: acceptance logic, then the sweep that accepts the step and measures the KKT error
   __device__ __forceinline__ void trip_accept(const KParams &P) {
@@ -1709,35 +1834,63 @@ struct Lane {
       lsq = true; err = true;
     } else if (m1 == LM_LSQ_ZERO) {
       zero = true; err = true;
+    } else if (FULL && m1 == LM_LSFAIL) {
+      restoration(P);
+      return;
     } else if (m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
       const double phi_t = fma(-mu, lt, ft);
-      if (m1 == LM_TRIAL) alpha_test = alpha;
-      if (ls_accept(alpha_test, tht, phi_t)) {
+      if (m1 == LM_TRIAL && !(FULL && in_watchdog)) alpha_test = alpha;
+      bool take = false;
+      if (FULL && force_accept) {
+        // a tiny step (trip_solve): taken untested, the filter and the watchdog counter stay as they are
+        force_accept = false;
+        take = true;
+      } else {
+        const int acc = ls_accept(alpha_test, tht, phi_t);
+        if (acc == 2) {
+          if (!commit_accept(P, phi_t)) { escalate = true; return; }
+          if (FULL) in_watchdog = false;
+          take = true;
+        } else {
+          if (acc >= 0) last_rej_filter = acc == 1;
+          if (FULL && in_watchdog) {
+            // BacktrackingLineSearch's watchdog: up to watchdog_trial_iter_max full steps without a test; if none of
+            // the points they lead to is acceptable to the point where it started, go back there and backtrack
+            if (++wd_trial > K_WATCHDOG_TRIAL_MAX) {
+              watchdog_stop();
+              alpha = 0.5 * alpha_max; ntrial = 0; wd_skip = true;
+              mode = LM_TRIAL;
+            } else {
+              wd_short = 0;
+              take = true;
+            }
+          } else if (m1 == LM_TRIAL) {
+            if (ntrial == 0 && !(FULL && wd_skip) && tht >= ls_theta) {
+              // second-order correction (Ipopt max_soc = 4): same matrix, corrected constraint rhs
+              soc_cnt = 0;
+              theta_soc_old = tht;
+              soc_rhs(true, alpha);
+              mode = LM_SOC;
+            } else {
+              alpha *= 0.5;
+              ntrial++;
+              if (alpha < alpha_min) line_search_failed();
+            }
+          } else {   // rejected SOC trial
+            soc_cnt++;
+            if (soc_cnt < K_MAX_SOC && tht <= K_KAPPA_SOC * theta_soc_old) {
+              theta_soc_old = tht;
+              soc_rhs(false, alpha_soc);
+              mode = LM_SOC;
+            } else {
+              mode = LM_RESOLVE;
+            }
+          }
+        }
+      }
+      if (take) {
         if (m1 == LM_SOC_TRIAL) alpha = alpha_soc;
-        if (!is_ftype(alpha_test) || !armijo(alpha_test, phi_t))
-          filter_add((1.0 - K_GAMMA_THETA) * ls_theta, ls_phi - K_GAMMA_PHI * ls_theta);
         upd = true; err = true;
-      } else if (m1 == LM_TRIAL) {
-        if (ntrial == 0 && tht >= ls_theta) {
-          // second-order correction (Ipopt max_soc = 4): same matrix, corrected constraint rhs
-          soc_cnt = 0;
-          theta_soc_old = tht;
-          soc_rhs(true, alpha);
-          mode = LM_SOC;
-        } else {
-          alpha *= 0.5;
-          ntrial++;
-          if (alpha < alpha_min) { status = 9; mode = LM_FINISH; }   // Ipopt would enter restoration
-        }
-      } else {   // rejected SOC trial
-        soc_cnt++;
-        if (soc_cnt < K_MAX_SOC && tht <= K_KAPPA_SOC * theta_soc_old) {
-          theta_soc_old = tht;
-          soc_rhs(false, alpha_soc);
-          mode = LM_SOC;
-        } else {
-          mode = LM_RESOLVE;
-        }
       }
     }
     // one copy of the sweep for every path: keep the compiler from cloning it per state (a clone run
@@ -1754,16 +1907,27 @@ struct Lane {
         mode = LM_LSQ_ZERO;
       } else {
         if (upd) iter++;
+        if (FULL && was_tiny) {
+          // the second tiny step in a row with a small dual step asks for a smaller barrier parameter
+          if (tiny_last && dy_max < K_TINY_STEP_Y_TOL) tiny_flag = true;
+          tiny_last = true; was_tiny = false;
+        }
+        if (FULL) wd_skip = false;
         check_and_update_mu(P);
       }
     }
+  }
+  // the line search ran below alpha_min: Ipopt's restoration phase.  One-problem-per-lane kernels hand over.
+  __device__ __forceinline__ void line_search_failed() {
+    mode = LM_LSFAIL;
+    if (!FULL) escalate = true;
   }
   // slot 3: factor
   __device__ __forceinline__ void trip_factor() {
     m3 = mode;
     const bool solve = m3 == LM_LSQ || m3 == LM_NEWTON || m3 == LM_SOC || m3 == LM_RESOLVE;
     solve_ok = true;
-    if (solve) {
+    if (solve && !escalate) {
       const bool ls = m3 == LM_LSQ;
       const double dwv = ls ? 0.0 : (m3 == LM_NEWTON ? dw : dw_used);
       if (PAR && (lh_stale || ls || (m3 == LM_NEWTON && dw == 0.0))) { build_lh(ls); lh_stale = false; }
@@ -1773,7 +1937,7 @@ struct Lane {
     }
   }
   // slot 4: solve, step lengths, line-search set-up
-  __device__ __forceinline__ void trip_solve() {
+  __device__ __forceinline__ void trip_solve(const KParams &P) {
     if (m3 == LM_IDLE) return;
     if (m3 == LM_NEWTON && !solve_ok) {
       // Ipopt's inertia correction schedule (delta_w)
@@ -1789,29 +1953,47 @@ struct Lane {
       dw_used = 0.0;
       mode = LM_LSQ_DONE;
     } else if (m3 == LM_NEWTON) {
+      if (!FULL && ((tiny_tol > 0.0 && tiny_screen) || (P.watchdog_trigger > 0 && wd_short >= P.watchdog_trigger))) {
+        // a step that may be "tiny", or the watchdog's trigger: nothing of this trip is committed (mode and dw are
+        // as they were when it began), the coop kernel repeats it and takes the branch
+        escalate = true;
+        return;
+      }
       if (dw > 0.0) dw_last = dw;
       dw_used = dw;
-      alpha = alpha_soc;   // alpha_max
-      ls_gbd = gbd_new;
-      ls_theta = theta;
-      ls_phi = fma(-mu, lsum, fx);
-      pow_gbd = ls_gbd < 0.0 ? pow(-ls_gbd, K_S_PHI) : 0.0;
-      pow_theta = pow(ls_theta, K_S_THETA);
-      double amin_ = K_GAMMA_THETA;
-      if (ls_gbd < 0.0) {
-        amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * ls_theta / (-ls_gbd));
-        if (ls_theta <= theta_min) amin_ = fmin(amin_, pow_theta / pow_gbd);
+      alpha_max = alpha_soc;
+      bool tiny = false;
+      if (FULL) {
+        // DetectTinyStep: every component of the step is relatively tiny and the point is (almost) feasible
+        tiny = tiny_tol > 0.0 && tiny_all != 0.0 && theta <= 1e-4;
+        if (in_watchdog && tiny) { watchdog_stop(); tiny = false; }
       }
-      alpha_min = amin_ * K_ALPHA_MIN_FRAC;
+      if (!(FULL && in_watchdog)) {   // InitThisLineSearch: reference values of the current iterate
+        ls_gbd = gbd_new;
+        ls_theta = theta;
+        ls_phi = fma(-mu, lsum, fx);
+        pow_gbd = ls_gbd < 0.0 ? pow(-ls_gbd, K_S_PHI) : 0.0;
+        pow_theta = pow(ls_theta, K_S_THETA);
+        double amin_ = K_GAMMA_THETA;
+        if (ls_gbd < 0.0) {
+          amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * ls_theta / (-ls_gbd));
+          if (ls_theta <= theta_min) amin_ = fmin(amin_, pow_theta / pow_gbd);
+        }
+        alpha_min = amin_ * K_ALPHA_MIN_FRAC;
+      }
+      if (FULL && P.watchdog_trigger > 0 && !in_watchdog && !tiny && wd_short >= P.watchdog_trigger) watchdog_start();
+      alpha = alpha_max;
       ntrial = 0;
+      if (FULL && tiny) { force_accept = true; was_tiny = true; }
+      else if (FULL) tiny_last = false;
       mode = LM_TRIAL;
     } else if (m3 == LM_SOC) {
       mode = LM_SOC_TRIAL;
     } else {   // LM_RESOLVE: the uncorrected direction is back; continue backtracking
       alpha *= 0.5;
       ntrial++;
-      mode = (alpha < alpha_min) ? LM_FINISH : LM_TRIAL;
-      if (mode == LM_FINISH) status = 9;
+      mode = LM_TRIAL;
+      if (alpha < alpha_min) line_search_failed();
     }
   }
 };
@@ -1865,7 +2047,9 @@ __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KPa
   Z.mode = LM_IDLE;
   Z.b = 0;
   Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;
-  Z.lh_stale = false; Z.no_handoff = false;
+  Z.lh_stale = false; Z.no_handoff = false; Z.escalate = false;
+  Z.tiny_tol = P.tiny_step_tol;
+  Z.scratch = nullptr;
   int n_in = 0, next_in = 0;
   double *park_buf = P.ckpt;
   int *park_count = P.ckpt_count;
@@ -1879,20 +2063,29 @@ __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KPa
   for (;;) {
     // ---- slot 0: retire / migrate / fetch
     if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
-    // two passes over one copy of the park / fetch code: rule 1 then fetch, rule 2 after the fetch
+    // two passes over one copy of the park / fetch code: rule 1 and escalation then fetch, rule 2 after the fetch
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
       unsigned live = 0xffffffffu;
       if (pass == 1) live = __ballot_sync(0xffffffffu, Z.mode != LM_DONE);
-      const bool can = park_buf && Z.mode != LM_IDLE && Z.mode != LM_DONE && !Z.no_handoff;
+      const bool esc = pass == 0 && Z.escalate;
+      const bool can = park_buf && Z.mode != LM_IDLE && Z.mode != LM_DONE && (!Z.no_handoff || esc);
       // rule 2: a lane is only ever DONE when the queue had nothing left for it
-      const bool park = can && (pass == 0 ? Z.iter >= P.handoff_iter
+      const bool park = can && (pass == 0 ? (Z.iter >= P.handoff_iter || esc)
                                           : (live != 0xffffffffu && __popc(live) <= P.park_lanes));
+      bool parked = false;
       if (park) {
         const int slot = atomicAdd(park_count, 1);
-        if (slot < P.ckpt_cap) { Z.save(park_buf + (size_t)slot * Lane<NS, false>::CK_SIZE); Z.mode = pass == 0 ? LM_IDLE : LM_DONE; }
+        if (slot < P.ckpt_cap) { Z.save(park_buf + (size_t)slot * Lane<NS, false>::CK_SIZE); Z.mode = pass == 0 ? LM_IDLE : LM_DONE; parked = true; }
         else Z.no_handoff = true;
       }
+      if (esc && !parked) {
+        // no record slot: the final launch of the chain solves this problem from the start with every branch of the
+        // algorithm on board -- same arithmetic, so it walks the same path up to here and then takes the branch
+        P.restart_list[atomicAdd(P.restart_count, 1)] = Z.b;
+        Z.mode = LM_IDLE;
+      }
+      if (pass == 0) Z.escalate = false;
       if (pass == 0 && Z.mode == LM_IDLE) {
         Z.no_handoff = false;
         if (RESUME) {
@@ -1908,7 +2101,7 @@ __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KPa
     Z.trip_eval();
     Z.trip_accept(P);
     Z.trip_factor();
-    Z.trip_solve();
+    Z.trip_solve(P);
   }
 }
 
@@ -1929,6 +2122,7 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
   Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
   Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
   Z.lh_stale = false; Z.no_handoff = false;
+  Z.scratch = P.scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / G) * P.scratch_stride;
   int pass = 0;
   for (;;) {
     int nb = 0;
@@ -1945,15 +2139,16 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
       Z.trip_accept(P);
       if (Z.mode == LM_FINISH) break;
       Z.trip_factor();
-      Z.trip_solve();
+      Z.trip_solve(P);
     }
     if (Z.g0 == 0) Z.write_outputs(P);
     Z.gsync();
   }
 }
 
-// The coop kernel on the problems the lane kernel parked: each group takes a record, restores the state and
-// carries on from the trip where the lane stopped.
+// The coop kernel on the problems the lane kernel parked or handed over: each group takes a record, restores the
+// state and carries on from the trip where the lane stopped; then the problems that were handed over when no record
+// slot was free (restart_list) are solved from the start.
 template <int NS>
 #ifndef MPC_COOP_RESUME_MINB
 #define MPC_COOP_RESUME_MINB 2   // CTAs per SM the finisher is compiled for at N <= 10 (3 = 168 registers: experiment)
@@ -1967,62 +2162,38 @@ __global__ void __launch_bounds__(128, NS <= 10 ? MPC_COOP_RESUME_MINB : 2) mpc_
   Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
   Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
   Z.no_handoff = true;
-  const ChainIO io = chain_resolve(P);
-  const int n = io.n;
-  for (;;) {
-    int k = 0;
-    if (Z.g0 == 0) k = atomicAdd(io.cursor, 1);
-    k = __shfl_sync(Z.gm, k, 0, G);
-    if (k >= n) break;
-    Z.load(io.in + (size_t)k * Lane<NS, true>::CK_SIZE);
-    while (Z.mode != LM_FINISH) {
-      Z.trip_eval();
-      Z.trip_accept(P);
-      if (Z.mode == LM_FINISH) break;
-      Z.trip_factor();
-      Z.trip_solve();
-    }
-    if (Z.g0 == 0) Z.write_outputs(P);
-    Z.gsync();
-  }
-}
-
-// One problem per WARP-lane with the rows in shared memory (the lane kernel's sequential sweeps, Lane<NS, true, false>):
-// the finisher for horizons the coop kernel does not take (N > 32), and the kernel for a handful of such problems.
-// A lane that is alone in its warp still touches one 128-byte line of thread-private memory per word (the lanes of
-// a warp are interleaved word by word), N * 20 KB per sweep: beyond N ~ 12 that no longer fits the L1 and every
-// access of the last long-running problems goes to L2.  Here the rows of a problem are N * 624 contiguous bytes of
-// shared memory.  lanes_per_warp lanes of every one-warp CTA hold a problem (1 for NS = 64: five CTAs per SM).
-template <int NS, bool RESUME>
-__global__ void __launch_bounds__(32, 1) mpc_solo_kernel(const KParams P, int lanes_per_warp) {
-  extern __shared__ double solo_smem[];
-  Lane<NS, true, false> Z;
-  Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;
-  Z.lh_stale = false; Z.no_handoff = true;
-  Z.b = 0;
-  const bool has = (int)threadIdx.x < lanes_per_warp;
-  Z.ST = reinterpret_cast<double (*)[ST_ROW]>(solo_smem + (size_t)(has ? threadIdx.x : 0) * NS * ST_ROW);
-  Z.mode = has ? LM_IDLE : LM_DONE;
-  int n = P.B;
+  Z.scratch = P.scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / G) * P.scratch_stride;
+  Z.tiny_tol = P.tiny_step_tol;
+  int n = 0;
   const double *rec_in = nullptr;
-  int *cursor = P.counter;
-  if (RESUME) {
+  int *cursor = P.restart_cursor;
+  if (P.chain_counts) {
     const ChainIO io = chain_resolve(P);
     n = io.n; rec_in = io.in; cursor = io.cursor;
   }
-  for (;;) {
-    if (Z.mode == LM_FINISH) { Z.write_outputs(P); Z.mode = LM_IDLE; }
-    if (Z.mode == LM_IDLE) {
-      const int k = atomicAdd(cursor, 1);
-      if (k >= n) Z.mode = LM_DONE;
-      else if (RESUME) Z.load(rec_in + (size_t)k * Lane<NS, true, false>::CK_SIZE);
-      else Z.init(P, P.perm ? P.perm[k] : k);
+  int n_restart = *P.restart_count;
+  if (n_restart > P.B) n_restart = P.B;
+  for (int phase = 0; phase < 2; phase++) {
+    if (phase == 0 && !rec_in) continue;
+    const int cnt = phase == 0 ? n : n_restart;
+    int *cur = phase == 0 ? cursor : P.restart_cursor;
+    for (;;) {
+      int k = 0;
+      if (Z.g0 == 0) k = atomicAdd(cur, 1);
+      k = __shfl_sync(Z.gm, k, 0, G);
+      if (k >= cnt) break;
+      if (phase == 0) Z.load(rec_in + (size_t)k * Lane<NS, true>::CK_SIZE);
+      else Z.init(P, P.restart_list[k]);
+      while (Z.mode != LM_FINISH) {
+        Z.trip_eval();
+        Z.trip_accept(P);
+        if (Z.mode == LM_FINISH) break;
+        Z.trip_factor();
+        Z.trip_solve(P);
+      }
+      if (Z.g0 == 0) Z.write_outputs(P);
+      Z.gsync();
     }
-    if (__all_sync(0xffffffffu, Z.mode == LM_DONE)) break;
-    Z.trip_eval();
-    Z.trip_accept(P);
-    Z.trip_factor();
-    Z.trip_solve();
   }
 }
 

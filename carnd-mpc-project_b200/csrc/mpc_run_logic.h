@@ -44,6 +44,7 @@ MPC_HD double orientation(const double *c, int n, double px, double dir) {   // 
 }
 MPC_HD double table_limit(const double *keys, int nk, const double *vals, int nv, double angle, double mx) {
   const double y = fabs(angle);
+  if (nv < 1) return mx;   // no table: no limit (callers reject such configs; this keeps the read in bounds)
   for (int i = 0; i < nk; i++)
     if (y <= keys[i]) return fmin(nv > i ? vals[i] : vals[nv - 1], mx);
   return fmin(vals[nv - 1], mx);

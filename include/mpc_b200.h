@@ -43,7 +43,7 @@ extern "C" {
 #define MPC_STATUS_STOP_AT_TINY_STEP 3
 #define MPC_STATUS_STOP_AT_ACCEPTABLE_POINT 4
 #define MPC_STATUS_LOCAL_INFEASIBILITY 5
-#define MPC_STATUS_RESTORATION_FAILURE 9
+#define MPC_STATUS_RESTORATION_FAILURE 9        /* the restoration phase itself failed (it is entered like Ipopt's) */
 #define MPC_STATUS_ERROR_IN_STEP_COMPUTATION 10
 #define MPC_STATUS_INVALID_NUMBER_DETECTED 11
 #define MPC_STATUS_INTERNAL_ERROR 13
@@ -68,6 +68,9 @@ typedef struct mpc_config {
   double steers[MPC_NTAB];       /* Config::steers            [rad] */
   double steer_speeds[MPC_NTAB]; /* Config::steerSpeeds       [m/s] */
   double tol;                    /* Ipopt tol, default 1e-8 */
+  int watchdog_trigger;          /* Ipopt watchdog_shortened_iter_trigger, default 10 (0 = no watchdog) */
+  int filter_reset_trigger;      /* Ipopt filter_reset_trigger, default 5 */
+  double tiny_step_tol;          /* Ipopt tiny_step_tol, default 10 * machine epsilon (0 = off) */
   /* ---- fields below are only used by MPC::run-level helpers (not by the NLP) ---- */
   int max_fit_order;             /* Config::maxFitOrder */
   int latency_ms;                /* Config::latency */
@@ -151,10 +154,10 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
  * lane_threads (CTA size 32..256, multiple of 32; 0 = automatic, balanced over the SMs) and
  * lane_ctas_per_sm (0 = one) tune the persistent grid of the lane kernel. */
 #define MPC_KERNEL_AUTO 0
-#define MPC_KERNEL_WARP 1   /* one problem per warp, stage per lane: the first version, kept as a cross-check (N <= 32) */
-#define MPC_KERNEL_LANE 2
-#define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory */
-#define MPC_KERNEL_SOLO 4   /* one problem per lane of one-warp CTAs, rows in shared memory (kept as a cross-check) */
+#define MPC_KERNEL_LANE 2   /* one problem per lane; problems that need a rare branch of the algorithm (restoration phase,
+                               watchdog, tiny steps, more than 8 filter entries) finish in a last launch of the coop kernel */
+#define MPC_KERNEL_COOP 3   /* one problem per group of 16/32 lanes, rows in shared memory: every branch of the algorithm
+                               (values 1 and 4 were the first-version warp kernel and the solo kernel, removed in round 2) */
 #define MPC_LANE_MIN_BATCH 9216
 #define MPC_COOP_MAX_BATCH_LONG 8192   /* AUTO, N > 32: up to this many problems run the coop kernel */
 int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lane_ctas_per_sm);
@@ -175,8 +178,7 @@ int mpc_set_handoff(mpc_handle *h, int iterations);
  * launches are on the caller's stream, results are bit-identical for every setting.  Applies to batches of at
  * least MPC_TAIL_MIN_BATCH problems.
  * flags (default MPC_TAIL_SORT_RAGGED): MPC_TAIL_SORT_RAGGED -- batches with N_per hand the problems out longest
- * horizon first, so that the lanes of a warp hold horizons of similar length; MPC_TAIL_SOLO_FINISHER -- finish
- * with the solo kernel instead of the coop kernel; MPC_TAIL_LATE_COPY -- mpc_solve_batch_host starts its
+ * horizon first, so that the lanes of a warp hold horizons of similar length; MPC_TAIL_LATE_COPY -- mpc_solve_batch_host starts its
  * device->host copies only after the final launch (by default, when every output array is pinned, device-mapped
  * host memory, they run beside the final launch and the few thousand problems that launch finishes are then
  * rewritten in the host arrays by a small kernel: same bytes, ~0.25 ms less per 64K batch). */
@@ -185,7 +187,6 @@ int mpc_set_handoff(mpc_handle *h, int iterations);
 #define MPC_RESUME_PHASES_DEFAULT 3
 #define MPC_RESUME_MIN_DEFAULT 8192
 #define MPC_TAIL_SORT_RAGGED 1
-#define MPC_TAIL_SOLO_FINISHER 2
 #define MPC_TAIL_LATE_COPY 4
 int mpc_set_tail(mpc_handle *h, int park_lanes, int resume_launches, int resume_min_records, int flags);
 /* accounting: parked[k] = problems parked by launch k (0 = main, 1.. = resume launches) of the last lane-kernel

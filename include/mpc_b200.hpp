@@ -54,6 +54,12 @@ class MPC {
   int lastStatus() const { return status_; }     // CppAD::ipopt::solve_result::status_type integer
   int lastIters() const { return iters_; }
   const mpc_config &config() const { return cfg_; }
+  // Config::load on a live controller: the handle (device workspace, stream) is kept
+  void setConfig(const mpc_config &cfg) {
+    const int rc = mpc_set_config(h_, &cfg);
+    if (rc != MPC_OK) throw std::runtime_error(std::string("mpc_set_config failed (") + std::to_string(rc) + ")");
+    cfg_ = cfg;
+  }
 
   // MPC::solve, MPC.cpp:183-325.  Returns {x1, y1, psi1, v1, cte1, epsi1, delta0, a0, cost}; appends the N
   // predicted points (stage 0 included) to *x_trajectory / *y_trajectory.  target_velocity and dir are

@@ -4,7 +4,9 @@
 // the tree (mpc_main.cpp, test.cpp, Vehicle, RoadGeometry, Config) is untouched.
 //
 // Replaces: FG_eval (MPC.cpp:15-154), MPC::MPC (:160-179), MPC::solve (:183-325), MPC::run (:327-382).
+#include <cstring>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 #include "MPC.h"
 #include "../utils/Config.h"
@@ -33,6 +35,25 @@ mpc_config config_from_statics() {
   tab(Config::yawChangeSpeeds, c.yaw_change_speeds, &c.n_yaw_change_speeds);
   return c;
 }
+// One solver object (device workspace, stream, pinned staging block) for the life of the process.  The reference
+// builds a new MPC -- and with it a new tape and a new Ipopt problem -- for every telemetry message
+// (mpc_main.cpp:99) and reads the Config statics afresh on every call; here the handle is kept and only told about
+// a configuration when the statics have changed since the last call (Config::load, or the -speed / -latency
+// overrides of mpc_main.cpp:244-246).  Creating and destroying a handle per call costs four cudaMalloc, a
+// cudaMallocHost and a stream, far more than the ~200 us solve.
+mpcb200::MPC &solver_for_statics() {
+  static std::unique_ptr<mpcb200::MPC> impl;
+  static mpc_config last;
+  const mpc_config c = config_from_statics();   // starts from mpc_config_defaults, which zeroes the padding too
+  if (!impl) {
+    impl.reset(new mpcb200::MPC(c, 0));
+    last = c;
+  } else if (std::memcmp(&last, &c, sizeof(c)) != 0) {
+    impl->setConfig(c);
+    last = c;
+  }
+  return *impl;
+}
 }  // namespace
 
 MPC::MPC() {}
@@ -40,8 +61,7 @@ MPC::~MPC() {}
 
 vector<double> MPC::solve(VectorXd &state, double target_velocity, vector<double> *x_trajectory,
                           vector<double> *y_trajectory, double dir) {
-  // the reference rebuilds its tape and Ipopt problem on every call and reads the statics afresh; so do we
-  mpcb200::MPC impl(config_from_statics(), 0);
+  mpcb200::MPC &impl = solver_for_statics();
   VectorXd &poly = roadGeometry.getPolynomial();
   impl.setRoad(poly.data(), (int)poly.size(), Config::yawLow, Config::yawHigh);
   return impl.solve(state, target_velocity, x_trajectory, y_trajectory, dir);
@@ -49,7 +69,7 @@ vector<double> MPC::solve(VectorXd &state, double target_velocity, vector<double
 
 vector<double> MPC::run(Vehicle &vehicle, vector<double> &ptsx, vector<double> &ptsy,
                         std::vector<double> *x_trajectory, std::vector<double> *y_trajectory) {
-  mpcb200::MPC impl(config_from_statics(), 0);
+  mpcb200::MPC &impl = solver_for_statics();
   mpcb200::VehiclePose pose = {vehicle.getX(), vehicle.getY(), vehicle.getOrientation(), vehicle.getVelocity(),
                                vehicle.getSteering(), vehicle.getAcceleration()};
   vector<double> out = impl.run(pose, ptsx, ptsy, x_trajectory, y_trajectory);

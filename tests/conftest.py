@@ -46,12 +46,11 @@ def stable_cfg(mpc, refdata):
     return mpc.config_from_json_text(json.dumps(refdata["configs"]["stable"]))
 
 
-@pytest.fixture(scope="session", params=[1, 2, 3, 4], ids=["warp-kernel", "lane-kernel", "coop-kernel", "solo-kernel"])
+@pytest.fixture(scope="session", params=[2, 3], ids=["lane-kernel", "coop-kernel"])
 def kernel_kind(request):
-    """Every CUDA kernel is held to the same parity bar: 1 = one problem per warp (first version, kept as a
-    cross-check), 2 = one problem per lane (throughput path), 3 = one problem per lane group with the rows in
-    shared memory (latency / small-batch / tail path), 4 = one problem per lane with the rows in shared memory (the
-    lane kernel's sweeps on the coop kernel's storage; a third, independently scheduled instantiation)."""
+    """Every CUDA kernel is held to the same parity bar: 2 = one problem per lane (throughput path; problems that need
+    a rare branch of the algorithm finish in the coop kernel), 3 = one problem per lane group with the rows in shared
+    memory (latency / small-batch / tail path, every branch of the algorithm)."""
     return request.param
 
 

@@ -27,16 +27,15 @@ def test_binding_constants_match_the_header(mpc):
     """The ctypes binding passes kernel kinds and tail flags as literals: they must be the header's."""
     hdr = open(os.path.join(ROOT, "include", "mpc_b200.h")).read()
     macro = lambda name: int(re.search(r"#define\s+%s\s+(-?\d+)" % name, hdr).group(1))
-    for name, val in (("MPC_KERNEL_AUTO", mpc.KERNEL_AUTO), ("MPC_KERNEL_WARP", mpc.KERNEL_WARP), ("MPC_KERNEL_LANE", mpc.KERNEL_LANE),
-                      ("MPC_KERNEL_COOP", mpc.KERNEL_COOP), ("MPC_KERNEL_SOLO", mpc.KERNEL_SOLO)):
+    for name, val in (("MPC_KERNEL_AUTO", mpc.KERNEL_AUTO), ("MPC_KERNEL_LANE", mpc.KERNEL_LANE), ("MPC_KERNEL_COOP", mpc.KERNEL_COOP)):
         assert macro(name) == val, name
-    # Solver.set_tail builds flags as 1 | 2 | 4
-    assert (macro("MPC_TAIL_SORT_RAGGED"), macro("MPC_TAIL_SOLO_FINISHER"), macro("MPC_TAIL_LATE_COPY")) == (1, 2, 4)
+    # Solver.set_tail builds flags as 1 | 4
+    assert (macro("MPC_TAIL_SORT_RAGGED"), macro("MPC_TAIL_LATE_COPY")) == (1, 4)
 
 
 def test_config_struct_size_matches_header(mpc):
-    # 4 ints + 8 doubles + 12 + 16 + 16 doubles + tol + 2 ints + 5 doubles + 2 ints + 32 doubles
-    assert C.sizeof(mpc.MpcConfig) == 16 + 8 * (8 + 12 + 16 + 16 + 1) + 8 + 8 * 5 + 8 + 8 * 32
+    # 4 ints + 8 doubles + 12 + 16 + 16 doubles + tol + 2 ints + tiny_step_tol + 2 ints + 5 doubles + 2 ints + 32 doubles
+    assert C.sizeof(mpc.MpcConfig) == 16 + 8 * (8 + 12 + 16 + 16 + 1) + 8 + 8 + 8 + 8 * 5 + 8 + 8 * 32
 
 
 @pytest.mark.parametrize("name", ["stable", "fast", "no-latency"])

@@ -81,10 +81,7 @@ def test_other_shipped_configs(mpc, po, refdata, name, kernel_kind):
 @pytest.mark.parametrize("N,dt", [(2, 0.1), (3, 0.1), (10, 0.05), (10, 0.02), (11, 0.05), (20, 0.05), (21, 0.05),
                                   (25, 0.025), (30, 0.02), (32, 0.05), (40, 0.05), (50, 0.02), (64, 0.02)])
 def test_horizon_and_timestep_grid(mpc, po, refdata, N, dt, kernel_kind):
-    """N x dt cells of the reference's examples/ grid (submission-report.md:250-265).  The warp kernel
-    holds one stage per lane (N <= 32); the lane, coop and solo kernels go to MPC_NMAX = 64."""
-    if kernel_kind == 1 and N > 32:
-        pytest.skip("warp kernel: N <= 32")
+    """N x dt cells of the reference's examples/ grid (submission-report.md:250-265), up to MPC_NMAX = 64."""
     js = dict(refdata["configs"]["stable"], N=N, dt=dt)
     cfg = mpc.config_from_json_text(json.dumps(js))
     cd = po.load_config_dict(js)
@@ -212,7 +209,7 @@ def test_edge_cases(solver, mpc, stable_cfg, stable_cd):
 def test_auto_dispatch_and_kernels_agree(mpc, stable_cfg, stable_cd):
     """MPC_KERNEL_AUTO: small batches take the coop kernel, large ones the lane kernel.  Those two run the same
     arithmetic in the same order per problem, so they agree to the last bit (which is what makes migrating a
-    problem between them safe); the first-version warp kernel sums in a different order and agrees to ~1e-7."""
+    problem between them safe)."""
     S = mpc.Solver(stable_cfg, 0)
     b = mpc.workloads.batch_perturbed_states(mpc.LANE_MIN_BATCH, 77, stable_cd)
     args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
@@ -221,14 +218,9 @@ def test_auto_dispatch_and_kernels_agree(mpc, stable_cfg, stable_cd):
     lane = S.solve_batch_host(*args)
     S.set_kernel(mpc.KERNEL_COOP)
     coop = S.solve_batch_host(*args)
-    S.set_kernel(mpc.KERNEL_WARP)
-    warp = S.solve_batch_host(*(a[:2048] for a in args))
     assert np.array_equal(auto["result"], lane["result"])          # B >= MPC_LANE_MIN_BATCH
     assert np.array_equal(coop["status"], lane["status"]) and np.array_equal(coop["iters"], lane["iters"])
     assert np.abs(coop["result"] - lane["result"]).max() < 1e-9
-    ok = (lane["status"][:2048] == 1) & (warp["status"] == 1)
-    assert ok.mean() > 0.99
-    assert np.abs(lane["result"][:2048][ok, :8] - warp["result"][ok, :8]).max() < 1e-5
     S.set_kernel(mpc.KERNEL_AUTO)
     small = S.solve_batch_host(*(a[:100] for a in args))
     assert np.array_equal(small["result"], coop["result"][:100])   # 100 < MPC_LANE_MIN_BATCH
@@ -236,8 +228,9 @@ def test_auto_dispatch_and_kernels_agree(mpc, stable_cfg, stable_cd):
     S.set_kernel(mpc.KERNEL_LANE, 64, 3)
     lane2 = S.solve_batch_host(*args)
     assert np.array_equal(lane2["result"], lane["result"]) and np.array_equal(lane2["iters"], lane["iters"])
-    with pytest.raises(mpc.MpcError):
-        S.set_kernel(7)
+    for gone in (1, 4, 7):   # 1 and 4 were the first-version warp kernel and the solo kernel
+        with pytest.raises(mpc.MpcError):
+            S.set_kernel(gone)
     S.close()
 
 
@@ -302,7 +295,7 @@ def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
     # threshold -- none skipped, some skipped, all skipped -- same bits, and the counters show who did the work
     for rmin in (0, 1500, 100000):
         S.set_handoff(0)
-        S.set_tail(16, 3, True, False, rmin)
+        S.set_tail(16, 3, True, rmin)
         got = S.solve_batch_host(*args, want_full=True)
         for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
             assert np.array_equal(got[k], ref[k]), (rmin, k)
@@ -321,8 +314,8 @@ def test_migration_between_kernels_is_invisible(mpc, stable_cfg, stable_cd):
 
 def test_long_horizon_kernels_agree_bit_for_bit(mpc, stable_cd, refdata):
     """N > 32: the coop kernel gives every lane of a 32-lane group two stages (neighbour values through the shared rows
-    instead of shuffles), the solo kernel runs the lane kernel's sweeps on rows in shared memory, and a big batch is the
-    lane kernel with resume launches and either of them as the finisher.  All of them are the same arithmetic (the
+    instead of shuffles), and a big batch is the lane kernel with resume launches and the coop kernel as the
+    finisher.  All of them are the same arithmetic (the
     library is built without implicit multiply-add contraction), so: same bits -- including N = 64, the maximum, N = 33,
     one stage into the second pass, and a horizon of 25 run through the two-stages-per-lane code."""
     import json
@@ -337,10 +330,9 @@ def test_long_horizon_kernels_agree_bit_for_bit(mpc, stable_cd, refdata):
         assert (ref["status"] == 1).mean() > 0.9
         if N == 40:
             assert ref["iters"].max() > 40
-        for kind, park, resume, solo in ((mpc.KERNEL_COOP, 0, 0, False), (mpc.KERNEL_SOLO, 0, 0, False), (mpc.KERNEL_LANE, 8, 0, False),
-                                         (mpc.KERNEL_LANE, 16, 2, True), (mpc.KERNEL_AUTO, 31, 1, False)):
+        for kind, park, resume in ((mpc.KERNEL_COOP, 0, 0), (mpc.KERNEL_LANE, 8, 0), (mpc.KERNEL_LANE, 16, 2), (mpc.KERNEL_AUTO, 31, 1)):
             S.set_kernel(kind)
-            S.set_tail(park, resume, True, solo)
+            S.set_tail(park, resume, True)
             got = S.solve_batch_host(*args, want_full=True)
             for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
                 assert np.array_equal(got[k], ref[k]), (N, kind, park, resume, k)
@@ -400,8 +392,6 @@ def test_full_size_kkt_certificate(mpc, stable_cfg, stable_cd, kernel_kind):
     stationarity, primal feasibility, dual feasibility, complementarity.  Ipopt's own acceptance test is
     max(scaled errors) <= 1e-8 with scaling s_d, s_c >= 1 and an unscaled dual-infeasibility cap of 1."""
     import torch
-    if kernel_kind == 1:
-        pytest.skip("the first-version warp kernel has no multiplier outputs")
     B, N = 65536, stable_cd["N"]
     cd = stable_cd
     b = mpc.workloads.batch_perturbed_states(B, 0, cd)
