@@ -1787,9 +1787,987 @@ struct Lane {
     in_watchdog = false; wd_short = 0; lh_stale = true;
     gsync();
   }
-  // Ipopt's feasibility restoration phase (placeholder until the next commit: stop with restoration_failure)
+  // ==========================================================================================================
+  // Ipopt's feasibility restoration phase (IpRestoMinC_1Nrm, restated in oracle/mpc_oracle.c: restoration()):
+  //     min  rho sum(n + p) + eta/2 ||D_R (x - x_R)||^2     s.t.  c(x) + n - p = 0,  bounds on x,  n, p >= 0
+  // with eta = sqrt(mu), D_R = diag(1 / max(1, |x_R|)), solved from x_R by the same interior-point iteration until
+  // the point is acceptable to the ORIGINAL problem's filter and has reduced its infeasibility by K_RESTO_KAPPA.
+  // The slacks n, p (one pair per constraint row) and their multipliers are eliminated from the Newton system; what
+  // remains is the original stage structure with "soft" dynamics: row block i reads  ds_i = w_i + D_i y+_i  with
+  // D_i = 1/Sigma_n + 1/Sigma_p > 0, where w_i is the successor the hard constraint would give.  In the Riccati
+  // recursion that is one extra step per stage, P~ = (I + P D)^-1 P and p~ = (I + P D)^-1 p (computed as a 5x5
+  // Cholesky of I + D^1/2 P D^1/2, whose pivots join the 2x2 control pivots in the inertia test), and the new
+  // multipliers fall out of the forward sweep: y+_i = -(P~ w_i + p~).
+  // FULL (coop) kernels only; runs to completion inside one trip.  Iterate x lives in the rows as usual, the
+  // multipliers y of the restoration problem in ST_LAM, its bound multipliers in ST_ZL / ST_ZU; x_R and the original
+  // multipliers are the backup rows in the group's global scratch, which also holds n, p, z_n, z_p, y+, P~, D.
+  // ==========================================================================================================
+  enum { RS_N = 0, RS_P = 6, RS_ZN = 12, RS_ZP = 18, RS_YP = 24, RS_PT = 30, RS_D = 52, RS_DH = 58, RS_ROW = 64 };
+  __device__ __forceinline__ double *rs(int blk) const { return scratch + SC_RS + (size_t)blk * RS_ROW; }
+  __device__ __forceinline__ const double *bk(int i) const { return scratch + SC_BK_ROWS + (size_t)i * ST_KEEP; }
+  __device__ __forceinline__ static double dr2_of(double xr) { const double d = 1.0 / fmax(1.0, fabs(xr)); return d * d; }
+  // restoration-phase scalars (uniform over the group)
+  double mu_r, tau_r, dw_r, eta_r, alpha_max_r, alpha_z_r, gbd_r;
+  double r_dinf, r_cviol, r_infpr, r_amin, r_amax, r_ysum, r_zsum, r_thR, r_fR, r_lR;
+
+  // optimality error terms of the restoration problem at its current iterate (eta_r, mu-independent parts)
+  __device__ void resto_errors() {
+    const double dt = PC[LC_DT], eta = eta_r;
+    double r = 0.0, cv = 0.0, ip = 0.0, ys = 0.0, zs = 0.0, am = 1e300, aM = 0.0;
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const bool hasu = i < N - 1;
+      const double *b = bk(i);
+      const double *q = rs(i);
+      double s[6], y[6], yn[6], zl[4], zu[4], tg[8], u0 = 0.0, u1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { s[k] = ST[i][ST_S + k]; y[k] = ST[i][ST_LAM + k]; yn[k] = hasu ? ST[i + 1][ST_LAM + k] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { zl[k] = (k < 2 || hasu) ? ST[i][ST_ZL + k] : 0.0; zu[k] = (k < 2 || hasu) ? ST[i][ST_ZU + k] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) tg[k] = hasu ? ST[i][ST_TG + k] : 0.0;
+      if (hasu) { u0 = ST[i][ST_U + 0]; u1 = ST[i][ST_U + 1]; }
+      StageLin L;
+      lin_at(tg, s[3], u0, L);
+      double os[6] = {0, 0, 0, 0, 0, 0}, ou0 = 0.0, ou1 = 0.0;
+      if (hasu) {
+        const double l25 = yn[2] + yn[5];
+        os[0] = fma(L.a61, yn[5], fma(L.a51, yn[4], yn[0]));
+        os[1] = yn[1] - yn[4];
+        os[2] = fma(L.a23, yn[1], L.a13 * yn[0]) + l25;
+        os[3] = fma(L.a54, yn[4], fma(L.a34, l25, fma(L.a24, yn[1], L.a14 * yn[0])) + yn[3]);
+        os[5] = L.a56 * yn[4];
+        ou0 = L.b3 * l25;
+        ou1 = dt * yn[3];
+      }
+      double g[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) g[k] = eta * dr2_of(b[ST_S + k]) * (s[k] - b[ST_S + k]);
+      g[2] += -zl[0] + zu[0];
+      g[3] += -zl[1] + zu[1];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        r = nanmax(r, fabs(g[k] + y[k] - os[k]));
+        ys += fabs(y[k]);
+        const double c = (i == 0) ? c0[k] : ST[i - 1][ST_CN + k];
+        const double n = q[RS_N + k], p = q[RS_P + k], zn = q[RS_ZN + k], zp = q[RS_ZP + k];
+        cv = nanmax(cv, fabs(c + n - p));
+        ip = nanmax(ip, fabs(c));
+        r = nanmax(r, nanmax(fabs(K_RESTO_RHO + y[k] - zn), fabs(K_RESTO_RHO - y[k] - zp)));
+        const double v = n * zn, w = p * zp;
+        am = dmin(am, dmin(v, w));
+        aM = dmax(aM, dmax(v, w));
+        zs += fabs(zn) + fabs(zp);
+      }
+      zs += fabs(zl[0]) + fabs(zu[0]) + fabs(zl[1]) + fabs(zu[1]);
+      {
+        const double p0 = (s[2] - PC[LC_LO]) * zl[0], p1 = (PC[LC_HI] - s[2]) * zu[0];
+        const double p2 = (s[3] - PC[LC_LO + 1]) * zl[1], p3 = (PC[LC_HI + 1] - s[3]) * zu[1];
+        am = dmin(am, dmin(dmin(p0, p1), dmin(p2, p3)));
+        aM = dmax(aM, dmax(dmax(p0, p1), dmax(p2, p3)));
+      }
+      if (hasu) {
+        const double gd = eta * dr2_of(b[ST_U + 0]) * (u0 - b[ST_U + 0]);
+        const double ga = eta * dr2_of(b[ST_U + 1]) * (u1 - b[ST_U + 1]);
+        r = nanmax(r, fabs(gd - ou0 - zl[2] + zu[2]));
+        r = nanmax(r, fabs(ga - ou1 - zl[3] + zu[3]));
+        zs += fabs(zl[2]) + fabs(zu[2]) + fabs(zl[3]) + fabs(zu[3]);
+        const double p0 = (u0 - PC[LC_LO + 2]) * zl[2], p1 = (PC[LC_HI + 2] - u0) * zu[2];
+        const double p2 = (u1 - PC[LC_LO + 3]) * zl[3], p3 = (PC[LC_HI + 3] - u1) * zu[3];
+        am = dmin(am, dmin(dmin(p0, p1), dmin(p2, p3)));
+        aM = dmax(aM, dmax(dmax(p0, p1), dmax(p2, p3)));
+      }
+    }
+    r_dinf = gmax<NS_GROUP>(r, gm); r_cviol = gmax<NS_GROUP>(cv, gm); r_infpr = gmax<NS_GROUP>(ip, gm);
+    r_ysum = gsum<NS_GROUP>(ys, gm); r_zsum = gsum<NS_GROUP>(zs, gm);
+    r_amin = gmin<NS_GROUP>(am, gm); r_amax = gmax<NS_GROUP>(aM, gm);
+  }
+
+  // derivative pieces of every stage for the restoration problem's Newton system, into the shared rows (ST_LH):
+  // W = sum_j y_j Hess c_j + eta D_R^2 (no objective term), gradient eta D_R^2 (x - x_R) + barrier terms
+  __device__ void resto_build_lh() {
+    const double dt = PC[LC_DT], dtLf = PC[LC_DTLF], eta = eta_r;
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const bool hasu = i < N - 1;
+      const double *b = bk(i);
+      double tg[8], ln[6], zl[4], zu[4], il[4], iu[4], s[6];
+#pragma unroll
+      for (int k = 0; k < 8; k++) tg[k] = hasu ? ST[i][ST_TG + k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { ln[k] = hasu ? ST[i + 1][ST_LAM + k] : 0.0; s[k] = ST[i][ST_S + k]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { zl[k] = (k < 2 || hasu) ? ST[i][ST_ZL + k] : 0.0; zu[k] = (k < 2 || hasu) ? ST[i][ST_ZU + k] : 0.0; }
+      const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+      slack_rcp(s[2], s[3], u0, u1, hasu, il, iu);
+      StageLin L;
+      lin_at(tg, s[3], u0, L);
+      double sig[4], gb[4], e[8];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { sig[k] = fma(zl[k], il[k], zu[k] * iu[k]); gb[k] = mu_r * (iu[k] - il[k]); }
+#pragma unroll
+      for (int k = 0; k < 6; k++) e[k] = eta * dr2_of(b[ST_S + k]);
+      e[6] = hasu ? eta * dr2_of(b[ST_U + 0]) : 0.0;
+      e[7] = hasu ? eta * dr2_of(b[ST_U + 1]) : 0.0;
+      const double vdt = s[3] * dt;
+      double *q = &ST[i][ST_LH];
+      q[0] = L.a13; q[1] = L.a14; q[2] = L.a23; q[3] = L.a24; q[4] = L.a34; q[5] = L.b3; q[6] = L.a51; q[7] = L.a54;
+      q[8] = L.a56; q[9] = L.a61;
+      q[10] = (hasu ? fma(ln[5], tg[7], -(ln[4] * tg[5])) : 0.0) + e[0];                       // qxx
+      q[11] = e[1];                                                                             // qyy
+      q[12] = (hasu ? fma(ln[0], tg[1], ln[1] * tg[0]) * vdt : 0.0) + sig[0] + e[2];           // qpp
+      q[13] = hasu ? fma(ln[0], tg[0], -(ln[1] * tg[1])) * dt : 0.0;                           // qpv
+      q[14] = sig[1] + e[3];                                                                    // qvv
+      q[15] = hasu ? -ln[4] * tg[3] * dt : 0.0;                                                // qve
+      q[16] = e[4];                                                                             // qcc
+      q[17] = (hasu ? ln[4] * tg[2] * vdt : 0.0) + e[5];                                       // qee
+      q[18] = hasu ? -(ln[2] + ln[5]) * dtLf : 0.0;                                            // svd
+      q[19] = hasu ? e[6] + sig[2] : 0.0;                                                      // rdd
+      q[20] = hasu ? e[7] + sig[3] : 0.0;                                                      // raa
+      q[21] = e[2] * (s[2] - b[ST_S + 2]) + gb[0];                                             // gp
+      q[22] = e[3] * (s[3] - b[ST_S + 3]) + gb[1];                                             // gv
+      q[23] = e[4] * (s[4] - b[ST_S + 4]);                                                     // gc
+      q[24] = e[5] * (s[5] - b[ST_S + 5]);                                                     // ge
+      q[25] = 0.0;                                                                              // gdp
+      q[26] = hasu ? e[6] * (u0 - b[ST_U + 0]) + gb[2] : 0.0;                                  // gd
+      q[27] = hasu ? e[7] * (u1 - b[ST_U + 1]) + gb[3] : 0.0;                                  // ga
+      q[28] = e[0] * (s[0] - b[ST_S + 0]);                                                     // gx
+      q[29] = e[1] * (s[1] - b[ST_S + 1]);                                                     // gy
+    }
+    gsync();
+  }
+
+  // (2,2) diagonal D and right-hand side of every constraint block after the elimination of n and p:
+  //   D = 1/(Sigma_n + dw) + 1/(Sigma_p + dw),   dh = rc - (rho - mu/n)/(Sigma_n + dw) + (rho - mu/p)/(Sigma_p + dw)
+  // rc = c + n - p, or the accumulated second-order-correction residual (ST_CS / cs0)
+  __device__ void resto_rhs(bool soc, double dwv) {
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      double *q = rs(i);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double n = q[RS_N + k], p = q[RS_P + k];
+        const double sn = q[RS_ZN + k] / n + dwv, sp = q[RS_ZP + k] / p + dwv;
+        double rc;
+        if (soc) rc = (i == 0) ? cs0[k] : ST[i - 1][ST_CS + k];
+        else rc = ((i == 0) ? c0[k] : ST[i - 1][ST_CN + k]) + n - p;
+        q[RS_D + k] = 1.0 / sn + 1.0 / sp;
+        q[RS_DH + k] = rc - (K_RESTO_RHO - mu_r / n) / sn + (K_RESTO_RHO - mu_r / p) / sp;
+      }
+    }
+    gsync();
+  }
+
+  // P~ = (I + P D)^-1 P, p~ = (I + P D)^-1 p for the cost-to-go entering constraint block blk; stored for the forward
+  // sweep.  Over (x, y, psi, v, epsi) as a 5x5 Cholesky of I + E P E, E = D^1/2; the cte term is a scalar.  Returns
+  // whether every pivot was positive (part of the inertia test).
+  __device__ __forceinline__ bool resto_soften(int blk, double (&Pm)[6][6], double (&pv)[6], double &P44, double &p4) {
+    const double *q = rs(blk);
+    const double Dk[5] = {q[RS_D + 0], q[RS_D + 1], q[RS_D + 2], q[RS_D + 3], q[RS_D + 5]};
+    const double Dc = q[RS_D + 4];
+    double e[5], S[5][5], X[5][5], qv[5];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 5; j++) e[j] = sqrt(Dk[j]);
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) { S[r][c] = e[r] * Pm[r][c] * e[c] + (r == c ? 1.0 : 0.0); X[r][c] = e[r] * Pm[r][c]; }
+      qv[r] = e[r] * pv[r];
+    }
+    // Cholesky S = L L^T in place (lower), then X <- L^-1 X, qv <- L^-1 qv
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      double d = S[j][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) d -= S[j][k] * S[j][k];
+      ok = ok && (d > 0.0);
+      const double l = sqrt(d), il = 1.0 / l;
+      S[j][j] = l;
+#pragma unroll
+      for (int i = j + 1; i < 5; i++) {
+        double v = S[i][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) v -= S[i][k] * S[j][k];
+        S[i][j] = v * il;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const double il = 1.0 / S[i][i];
+#pragma unroll
+      for (int c = 0; c < 5; c++) {
+        double v = X[i][c];
+#pragma unroll
+        for (int k = 0; k < i; k++) v -= S[i][k] * X[k][c];
+        X[i][c] = v * il;
+      }
+      double v = qv[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) v -= S[i][k] * qv[k];
+      qv[i] = v * il;
+    }
+    double Pt[5][5], pt[5];
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+#pragma unroll
+      for (int c = r; c < 5; c++) {
+        double v = Pm[r][c];
+#pragma unroll
+        for (int k = 0; k < 5; k++) v -= X[k][r] * X[k][c];
+        Pt[r][c] = v;
+      }
+      double v = pv[r];
+#pragma unroll
+      for (int k = 0; k < 5; k++) v -= X[k][r] * qv[k];
+      pt[r] = v;
+    }
+    const double den = fma(Dc, P44, 1.0);
+    ok = ok && (den > 0.0);
+    const double P44t = P44 / den, p4t = p4 / den;
+    if (g0 == 0) {
+      double *w = rs(blk) + RS_PT;
+      int t = 0;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+#pragma unroll
+        for (int c = r; c < 5; c++) w[t++] = Pt[r][c];
+      }
+#pragma unroll
+      for (int r = 0; r < 5; r++) w[15 + r] = pt[r];
+      w[20] = P44t; w[21] = p4t;
+    }
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+#pragma unroll
+      for (int c = r; c < 5; c++) { Pm[r][c] = Pt[r][c]; Pm[c][r] = Pt[r][c]; }
+      pv[r] = pt[r];
+      Pm[r][5] = 0.0; Pm[5][r] = 0.0;
+    }
+    Pm[5][5] = 0.0; pv[5] = 0.0;
+    P44 = P44t; p4 = p4t;
+    return ok;
+  }
+
+  // backward Riccati sweep of the restoration problem: riccati()'s stage algebra on the pieces of resto_build_lh, with
+  // the cost-to-go softened at every constraint block (the initial-state block included) and no steering-rate coupling
+  __device__ bool riccati_resto(double dwv) {
+    const double dt = PC[LC_DT];
+    double Pm[6][6], pv[6], P44, p4;
+    {
+      StageHess H;
+      load_hess(N - 1, dwv, H);
+      const double *q = &ST[N - 1][ST_LH];
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) Pm[r][c] = 0.0;
+      }
+      Pm[0][0] = H.qxx; Pm[1][1] = H.qyy; Pm[2][2] = H.qpp; Pm[3][3] = H.qvv; Pm[4][4] = H.qee;
+      P44 = H.qcc;
+      pv[0] = q[28]; pv[1] = q[29]; pv[2] = H.gp; pv[3] = H.gv; pv[4] = H.ge; pv[5] = 0.0;
+      p4 = H.gc;
+    }
+    bool ok = true;
+#pragma unroll 1
+    for (int i = N - 2; i >= 0; i--) {
+      ok = resto_soften(i + 1, Pm, pv, P44, p4) && ok;
+      StageLin L;
+      StageHess H;
+      load_lin(i, L);
+      load_hess(i, dwv, H);
+      const double gx = ST[i][ST_LH + 28], gy = ST[i][ST_LH + 29];
+      const double *dh = rs(i + 1) + RS_DH;
+      double d[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) d[k] = -dh[k];
+      // v = P+ d + p+   (rows X, Y, PSI, V, E, DP; d over x, y, psi, v, epsi; cte apart)
+      double vv[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+        vv[r] = fma(Pm[r][4], d[5], fma(Pm[r][3], d[3], fma(Pm[r][2], d[2], fma(Pm[r][1], d[1], fma(Pm[r][0], d[0], pv[r])))));
+      const double v4 = fma(P44, d[4], p4);
+      double T[6][6];
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double pe = Pm[r][2] + Pm[r][4];
+        T[r][0] = fma(L.a61, Pm[r][4], Pm[r][0]);
+        T[r][1] = Pm[r][1];
+        T[r][2] = fma(L.a23, Pm[r][1], L.a13 * Pm[r][0]) + pe;
+        T[r][3] = fma(L.a34, pe, fma(L.a24, Pm[r][1], L.a14 * Pm[r][0])) + Pm[r][3];
+        T[r][4] = fma(L.b3, pe, Pm[r][5]);
+        T[r][5] = dt * Pm[r][3];
+      }
+      double M[6][6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const double te = T[2][c] + T[4][c];
+        M[0][c] = fma(L.a61, T[4][c], T[0][c]);
+        if (c >= 1) M[1][c] = T[1][c];
+        if (c >= 2) M[2][c] = fma(L.a23, T[1][c], L.a13 * T[0][c]) + te;
+        if (c >= 3) M[3][c] = fma(L.a34, te, fma(L.a24, T[1][c], L.a14 * T[0][c])) + T[3][c];
+        if (c >= 4) M[4][c] = fma(L.b3, te, T[5][c]);
+        if (c >= 5) M[5][c] = dt * T[3][c];
+      }
+      // the softened cost-to-go is dense over (x, y, psi, v, epsi): the epsi column of M = G^T P~ G, which is zero
+      // with a hard constraint, is not (G's epsi column is only the cte row, handled below; P~'s epsi row is T[.][.])
+      // epsi enters s_{i+1} only through cte (a56), so G^T P~ G has no epsi entries beyond the cte rank-1 term.
+      const double g4x = P44 * L.a51, g4v = P44 * L.a54, g4e = P44 * L.a56;
+      const double Mxx = fma(g4x, L.a51, M[0][0]) + H.qxx;
+      const double Mxy = M[0][1] - g4x;
+      const double Mxp = M[0][2];
+      const double Mxv = fma(g4x, L.a54, M[0][3]);
+      const double Mxe = g4x * L.a56;
+      const double Mxd = M[0][4], Mxa = M[0][5];
+      const double Myy = M[1][1] + P44 + H.qyy;
+      const double Myp = M[1][2];
+      const double Myv = M[1][3] - g4v;
+      const double Mye = -g4e;
+      const double Myd = M[1][4], Mya = M[1][5];
+      const double Mpp = M[2][2] + H.qpp;
+      const double Mpv = M[2][3] + H.qpv;
+      const double Mpd = M[2][4], Mpa = M[2][5];
+      const double Mvv = fma(g4v, L.a54, M[3][3]) + H.qvv;
+      const double Mve = fma(g4v, L.a56, H.qve);
+      const double Mvd = M[3][4] + H.svd, Mva = M[3][5];
+      const double Mee = fma(g4e, L.a56, H.qee);
+      const double Mdd = M[4][4] + H.rdd, Mda = M[4][5], Maa = M[5][5] + H.raa;
+      const double ve = vv[2] + vv[4];
+      const double mx = fma(L.a51, v4, fma(L.a61, vv[4], vv[0])) + gx;
+      const double my = vv[1] - v4 + gy;
+      const double mp = fma(L.a23, vv[1], L.a13 * vv[0]) + ve + H.gp;
+      const double mv = fma(L.a54, v4, fma(L.a34, ve, fma(L.a24, vv[1], L.a14 * vv[0])) + vv[3]) + H.gv;
+      const double me = fma(L.a56, v4, H.ge);
+      const double md = fma(L.b3, ve, vv[5]) + H.gd;
+      const double ma = fma(dt, vv[3], H.ga);
+      const double det = fma(Mdd, Maa, -(Mda * Mda));
+      ok = ok && (Mdd > 0.0) && (det > 0.0);
+      const double idet = 1.0 / det;
+      const double i11 = Maa * idet, i12 = -Mda * idet, i22 = Mdd * idet;
+      const double cd[5] = {Mxd, Myd, Mpd, Mvd, 0.0};
+      const double ca[5] = {Mxa, Mya, Mpa, Mva, 0.0};
+      double K0[5], K1[5];
+#pragma unroll
+      for (int c = 0; c < 5; c++) {
+        K0[c] = -fma(i11, cd[c], i12 * ca[c]);
+        K1[c] = -fma(i12, cd[c], i22 * ca[c]);
+        ST[i][ST_KG + c] = K0[c];
+        ST[i][ST_KG + 5 + c] = K1[c];
+      }
+      const double k0 = -fma(i11, md, i12 * ma), k1 = -fma(i12, md, i22 * ma);
+      ST[i][ST_KG + 10] = k0; ST[i][ST_KG + 11] = k1;
+      Pm[0][0] = fma(Mxa, K1[0], fma(Mxd, K0[0], Mxx));
+      Pm[0][1] = fma(Mxa, K1[1], fma(Mxd, K0[1], Mxy));
+      Pm[0][2] = fma(Mxa, K1[2], fma(Mxd, K0[2], Mxp));
+      Pm[0][3] = fma(Mxa, K1[3], fma(Mxd, K0[3], Mxv));
+      Pm[0][4] = Mxe;
+      Pm[0][5] = 0.0;
+      Pm[1][1] = fma(Mya, K1[1], fma(Myd, K0[1], Myy));
+      Pm[1][2] = fma(Mya, K1[2], fma(Myd, K0[2], Myp));
+      Pm[1][3] = fma(Mya, K1[3], fma(Myd, K0[3], Myv));
+      Pm[1][4] = Mye;
+      Pm[1][5] = 0.0;
+      Pm[2][2] = fma(Mpa, K1[2], fma(Mpd, K0[2], Mpp));
+      Pm[2][3] = fma(Mpa, K1[3], fma(Mpd, K0[3], Mpv));
+      Pm[2][4] = 0.0;
+      Pm[2][5] = 0.0;
+      Pm[3][3] = fma(Mva, K1[3], fma(Mvd, K0[3], Mvv));
+      Pm[3][4] = Mve;
+      Pm[3][5] = 0.0;
+      Pm[4][4] = Mee;
+      Pm[4][5] = 0.0;
+      Pm[5][5] = 0.0;
+#pragma unroll
+      for (int r = 1; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < r; c++) Pm[r][c] = Pm[c][r];
+      }
+      pv[0] = fma(Mxa, k1, fma(Mxd, k0, mx));
+      pv[1] = fma(Mya, k1, fma(Myd, k0, my));
+      pv[2] = fma(Mpa, k1, fma(Mpd, k0, mp));
+      pv[3] = fma(Mva, k1, fma(Mvd, k0, mv));
+      pv[4] = me;
+      pv[5] = 0.0;
+      P44 = H.qcc;
+      p4 = H.gc;
+    }
+    ok = resto_soften(0, Pm, pv, P44, p4) && ok;
+    gsync();
+    return ok;
+  }
+
+  // forward sweep of the restoration problem: the soft successor of every constraint block gives the new multipliers
+  // y+ (kept in the scratch rows) and the primal step; then, one stage per lane, the slack steps
+  //   dn = (mu/n - rho - y+) / (Sigma_n + dw),   dp = (mu/p - rho + y+) / (Sigma_p + dw)
+  // the fraction-to-the-boundary ratios over x, n, p and their multipliers, and grad(phi_R)^T d
+  __device__ void forward_resto(double dwv) {
+    const double dt = PC[LC_DT], eta = eta_r;
+    double t[6], w[6];
+    {
+      const double *dh = rs(0) + RS_DH;
+#pragma unroll
+      for (int k = 0; k < 6; k++) w[k] = -dh[k];
+    }
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+      const bool hasu = i < N - 1;
+      // soft step of block i: y+ = -(P~ w + p~) over (x, y, psi, v, epsi | cte), then ds = w + D y+
+      const double *q = rs(i);
+      const double *pt = q + RS_PT;
+      const double w5[5] = {w[0], w[1], w[2], w[3], w[5]};
+      double y5[5];
+      {
+        double Pt[5][5];
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+#pragma unroll
+          for (int cc = r; cc < 5; cc++) { Pt[r][cc] = pt[c]; Pt[cc][r] = pt[c]; c++; }
+        }
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          double v = pt[15 + r];
+#pragma unroll
+          for (int cc = 0; cc < 5; cc++) v = fma(Pt[r][cc], w5[cc], v);
+          y5[r] = -v;
+        }
+      }
+      const double yc = -fma(pt[20], w[4], pt[21]);
+      const double yp[6] = {y5[0], y5[1], y5[2], y5[3], yc, y5[4]};
+#pragma unroll
+      for (int k = 0; k < 6; k++) t[k] = fma(q[RS_D + k], yp[k], w[k]);
+      if (g0 == 0) {
+        double *qq = rs(i);
+#pragma unroll
+        for (int k = 0; k < 6; k++) qq[RS_YP + k] = yp[k];
+      }
+      double du0 = 0.0, du1 = 0.0;
+      if (hasu) {
+        double kg[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) kg[k] = ST[i][ST_KG + k];
+        du0 = fma(kg[3], t[3], fma(kg[2], t[2], fma(kg[1], t[1], fma(kg[0], t[0], kg[10]))));
+        du1 = fma(kg[8], t[3], fma(kg[7], t[2], fma(kg[6], t[1], fma(kg[5], t[0], kg[11]))));
+        StageLin L;
+        load_lin(i, L);
+        const double *dh = rs(i + 1) + RS_DH;
+        w[0] = fma(L.a14, t[3], fma(L.a13, t[2], t[0])) - dh[0];
+        w[1] = fma(L.a24, t[3], fma(L.a23, t[2], t[1])) - dh[1];
+        w[2] = fma(L.b3, du0, fma(L.a34, t[3], t[2])) - dh[2];
+        w[3] = fma(dt, du1, t[3]) - dh[3];
+        w[4] = fma(L.a56, t[5], fma(L.a54, t[3], fma(L.a51, t[0], -t[1]))) - dh[4];
+        w[5] = fma(L.b3, du0, fma(L.a34, t[3], fma(L.a61, t[0], t[2]))) - dh[5];
+      }
+      if (i % gstep == g0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ST[i][ST_DS + k] = t[k];
+        ST[i][ST_DU + 0] = du0; ST[i][ST_DU + 1] = du1;
+      }
+    }
+    gsync();
+    // ---- step-length ratios and the directional derivative, one stage per lane
+    double rmax = 0.0, zn = 1.0, zd = 0.0, gbd = 0.0;
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const bool hasu = i < N - 1;
+      const double *b = bk(i);
+      const double *q = rs(i);
+      double s[6], ds[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { s[k] = ST[i][ST_S + k]; ds[k] = ST[i][ST_DS + k]; }
+      const double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+      const double du0 = hasu ? ST[i][ST_DU + 0] : 0.0, du1 = hasu ? ST[i][ST_DU + 1] : 0.0;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) acc = fma(eta * dr2_of(b[ST_S + k]) * (s[k] - b[ST_S + k]), ds[k], acc);
+      if (hasu) {
+        acc = fma(eta * dr2_of(b[ST_U + 0]) * (u0 - b[ST_U + 0]), du0, acc);
+        acc = fma(eta * dr2_of(b[ST_U + 1]) * (u1 - b[ST_U + 1]), du1, acc);
+      }
+      double il[4], iu[4];
+      slack_rcp(s[2], s[3], u0, u1, hasu, il, iu);
+      const double dx[4] = {ds[2], ds[3], du0, du1};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k < 2 || hasu) {
+          const double zl = ST[i][ST_ZL + k], zu = ST[i][ST_ZU + k];
+          acc = fma(mu_r * (iu[k] - il[k]), dx[k], acc);
+          rmax = dmax(rmax, dmax(-dx[k] * il[k], dx[k] * iu[k]));
+          const double dzl = fma(fma(-zl, dx[k], mu_r), il[k], -zl);
+          const double dzu = fma(fma(zu, dx[k], mu_r), iu[k], -zu);
+          if (dzl < 0.0 && (zd == 0.0 || zl * zd < zn * (-dzl))) { zn = zl; zd = -dzl; }
+          if (dzu < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu))) { zn = zu; zd = -dzu; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double n = q[RS_N + k], p = q[RS_P + k], z_n = q[RS_ZN + k], z_p = q[RS_ZP + k], yp = q[RS_YP + k];
+        const double sn = z_n / n, sp = z_p / p;
+        const double dn = (mu_r / n - K_RESTO_RHO - yp) / (sn + dwv), dp = (mu_r / p - K_RESTO_RHO + yp) / (sp + dwv);
+        acc += (K_RESTO_RHO - mu_r / n) * dn + (K_RESTO_RHO - mu_r / p) * dp;
+        rmax = dmax(rmax, dmax(-dn / n, -dp / p));
+        const double dzn = mu_r / n - z_n - sn * dn, dzp = mu_r / p - z_p - sp * dp;
+        if (dzn < 0.0 && (zd == 0.0 || z_n * zd < zn * (-dzn))) { zn = z_n; zd = -dzn; }
+        if (dzp < 0.0 && (zd == 0.0 || z_p * zd < zn * (-dzp))) { zn = z_p; zd = -dzp; }
+      }
+      gbd += acc;
+    }
+    const int G = PAR ? NS_GROUP : 1;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double on = __shfl_xor_sync(gm, zn, o, G), od = __shfl_xor_sync(gm, zd, o, G);
+      const bool take = od > 0.0 && (zd == 0.0 || on * zd < zn * od || (on * zd == zn * od && on < zn));
+      if (take) { zn = on; zd = od; }
+    }
+    rmax = gmax<NS_GROUP>(rmax, gm);
+    gbd_r = gsum<NS_GROUP>(gbd, gm);
+    alpha_max_r = (rmax > tau_r) ? tau_r / rmax : 1.0;
+    alpha_z_r = (zd > 0.0 && tau_r * zn < zd) ? tau_r * zn / zd : 1.0;
+  }
+
+  // restoration-problem terms of a trial point x + a dx, n + a dn, p + a dp -- after eval_sweep(a) has left the
+  // original problem's values (ft, lt, tht) and the trial residuals (ST_CT, c0t; cur: the iterate's own, a = 0): theta_R = ||c + n - p||_1,
+  // rho sum(n + p) + eta/2 ||D_R (x - x_R)||^2, sum of log n + log p
+  __device__ void resto_eval_extra(double a, double dwv, bool cur) {
+    const double eta = eta_r;
+    double th = 0.0, f = 0.0, l = 0.0;
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const bool hasu = i < N - 1;
+      const double *b = bk(i);
+      const double *q = rs(i);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double n = q[RS_N + k], p = q[RS_P + k], yp = q[RS_YP + k];
+        const double dn = (mu_r / n - K_RESTO_RHO - yp) / (q[RS_ZN + k] / n + dwv), dp = (mu_r / p - K_RESTO_RHO + yp) / (q[RS_ZP + k] / p + dwv);
+        const double nt = fma(a, dn, n), pt = fma(a, dp, p);
+        const double ct = cur ? ((i == 0) ? c0[k] : ST[i - 1][ST_CN + k]) : ((i == 0) ? c0t[k] : ST[i - 1][ST_CT + k]);
+        th += fabs(ct + nt - pt);
+        f = fma(K_RESTO_RHO, nt + pt, f);
+        l += log(nt) + log(pt);
+        const double xt = fma(a, ST[i][ST_DS + k], ST[i][ST_S + k]) - b[ST_S + k];
+        f = fma(0.5 * eta * dr2_of(b[ST_S + k]) * xt, xt, f);
+      }
+      if (hasu) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const double xt = fma(a, ST[i][ST_DU + k], ST[i][ST_U + k]) - b[ST_U + k];
+          f = fma(0.5 * eta * dr2_of(b[ST_U + k]) * xt, xt, f);
+        }
+      }
+    }
+    r_thR = gsum<NS_GROUP>(th, gm); r_fR = gsum<NS_GROUP>(f, gm); r_lR = gsum<NS_GROUP>(l, gm);
+  }
+
+  // second-order-correction residual of the restoration problem:  CS = a (first ? rc : CS) + rc_trial
+  __device__ void resto_soc_rhs(bool first, double a, double dwv) {
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const double *q = rs(i);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double n = q[RS_N + k], p = q[RS_P + k], yp = q[RS_YP + k];
+        const double dn = (mu_r / n - K_RESTO_RHO - yp) / (q[RS_ZN + k] / n + dwv), dp = (mu_r / p - K_RESTO_RHO + yp) / (q[RS_ZP + k] / p + dwv);
+        const double nt = fma(a, dn, n), pt = fma(a, dp, p);
+        if (i == 0) {
+          const double old = first ? (c0[k] + n - p) : cs0[k];
+          cs0[k] = a * old + (c0t[k] + nt - pt);
+        } else {
+          const double old = first ? (ST[i - 1][ST_CN + k] + n - p) : ST[i - 1][ST_CS + k];
+          ST[i - 1][ST_CS + k] = a * old + (ST[i - 1][ST_CT + k] + nt - pt);
+        }
+      }
+    }
+    // cs0 is uniform per-problem state: every lane needs block 0's value
+    if (gstep > 1) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) cs0[k] = __shfl_sync(gm, cs0[k], 0, PAR ? NS_GROUP : 1);
+    }
+    gsync();
+  }
+
+  // accept the trial point of the restoration problem: x, n, p with a; y with a; every bound multiplier with az and
+  // Ipopt's kappa_sigma safeguard; the trial residuals and trig/polynomial values become the iterate's
+  __device__ void resto_accept(double a, double az, double dwv) {
+    const double zcap = K_KAPPA_SIGMA * mu_r, zfloor = mu_r / K_KAPPA_SIGMA;
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const bool hasu = i < N - 1;
+      double *q = rs(i);
+      double s[6], ds[6], zl[4], zu[4], il[4], iu[4], iln[4], iun[4];
+      double u0 = hasu ? ST[i][ST_U + 0] : 0.0, u1 = hasu ? ST[i][ST_U + 1] : 0.0;
+      const double du0 = hasu ? ST[i][ST_DU + 0] : 0.0, du1 = hasu ? ST[i][ST_DU + 1] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { s[k] = ST[i][ST_S + k]; ds[k] = ST[i][ST_DS + k]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { zl[k] = ST[i][ST_ZL + k]; zu[k] = ST[i][ST_ZU + k]; }
+      slack_rcp(s[2], s[3], u0, u1, hasu, il, iu);
+      const double dx[4] = {ds[2], ds[3], du0, du1};
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        s[k] = fma(a, ds[k], s[k]);
+        ST[i][ST_S + k] = s[k];
+        const double n = q[RS_N + k], p = q[RS_P + k], z_n = q[RS_ZN + k], z_p = q[RS_ZP + k], yp = q[RS_YP + k];
+        const double sn = z_n / n, sp = z_p / p;
+        const double dn = (mu_r / n - K_RESTO_RHO - yp) / (sn + dwv), dp = (mu_r / p - K_RESTO_RHO + yp) / (sp + dwv);
+        const double dzn = mu_r / n - z_n - sn * dn, dzp = mu_r / p - z_p - sp * dp;
+        const double nn = fma(a, dn, n), pn = fma(a, dp, p);
+        q[RS_ZN + k] = dmax(dmin(fma(az, dzn, z_n), zcap / nn), zfloor / nn);
+        q[RS_ZP + k] = dmax(dmin(fma(az, dzp, z_p), zcap / pn), zfloor / pn);
+        q[RS_N + k] = nn; q[RS_P + k] = pn;
+        const double y = ST[i][ST_LAM + k];
+        ST[i][ST_LAM + k] = fma(a, yp - y, y);
+      }
+      if (hasu) {
+        u0 = fma(a, du0, u0); u1 = fma(a, du1, u1);
+        ST[i][ST_U + 0] = u0; ST[i][ST_U + 1] = u1;
+      }
+      slack_rcp(s[2], s[3], u0, u1, hasu, iln, iun);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k < 2 || hasu) {
+          const double dzl = fma(fma(-zl[k], dx[k], mu_r), il[k], -zl[k]);
+          const double dzu = fma(fma(zu[k], dx[k], mu_r), iu[k], -zu[k]);
+          ST[i][ST_ZL + k] = dmax(dmin(fma(az, dzl, zl[k]), zcap * iln[k]), zfloor * iln[k]);
+          ST[i][ST_ZU + k] = dmax(dmin(fma(az, dzu, zu[k]), zcap * iun[k]), zfloor * iun[k]);
+        }
+      }
+      if (hasu) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ST[i][ST_CN + k] = ST[i][ST_CT + k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) ST[i][ST_TG + k] = ST[i][ST_TT + k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) c0[k] = c0t[k];
+    gsync();
+  }
+
+  // the restoration phase's own line-search state (same tests as the main algorithm's, separate filter)
+  struct RestoLS {
+    double theta, phi, gbd, pow_gbd, pow_theta;
+    int nf, n_resets, succ_rej;
+    bool last_rej;
+  };
+  __device__ static bool r_is_ftype(const RestoLS &R, double a) { return R.gbd < 0.0 && a * R.pow_gbd > R.pow_theta; }
+  __device__ static bool r_armijo(const RestoLS &R, double a, double phi_t) {
+    return cmp_le(phi_t - R.phi, K_ETA_PHI * a * R.gbd, R.phi);
+  }
+  // CheckAcceptabilityOfTrialPoint for the restoration problem (theta_min = 1e-4, theta_max = 1e8: its theta_0 is 0)
+  __device__ int resto_ls_accept(const RestoLS &R, const double *F, double a, double theta_t, double phi_t) const {
+    if (!(theta_t == theta_t) || !(phi_t == phi_t) || isinf(phi_t)) return -1;
+    if (theta_t > K_RESTO_THETA_MAX_FACT) return -1;
+    bool ok;
+    if (a > 0.0 && r_is_ftype(R, a) && R.theta <= 1e-4) {
+      ok = r_armijo(R, a, phi_t);
+    } else {
+      ok = true;
+      if (phi_t > R.phi) {
+        double basval = 1.0;
+        if (fabs(R.phi) > 10.0) basval = log10(fabs(R.phi));
+        if (log10(phi_t - R.phi) > K_OBJ_MAX_INC + basval) ok = false;
+      }
+      ok = ok && (cmp_le(theta_t, (1.0 - K_GAMMA_THETA) * R.theta, R.theta) || cmp_le(phi_t - R.phi, -K_GAMMA_PHI * R.theta, R.phi));
+    }
+    if (!ok) return 0;
+    for (int k = 0; k < R.nf; k++) {
+      const double f_t = F[2 * k], f_p = F[2 * k + 1];
+      if (!(cmp_le(theta_t, f_t, f_t) || cmp_le(phi_t, f_p, f_p))) return 1;
+    }
+    return 2;
+  }
+
   __device__ void restoration(const KParams &P) {
-    status = 9; mode = LM_FINISH;
+    // ---- entry (BacktrackingLineSearch): the current point joins the filter; stop here if it is already acceptable
+    // or almost feasible (nothing for a feasibility restoration to do)
+    filter_add((1.0 - K_GAMMA_THETA) * ls_theta, ls_phi - K_GAMMA_PHI * ls_theta);
+    if (acceptable_now) { status = 4; mode = LM_FINISH; return; }
+    if (theta <= 1e-2 * P.tol) { status = 9; mode = LM_FINISH; return; }
+    // ---- backup of the outer iterate: x_R, and the multipliers the outer algorithm goes on with
+    {
+      double *r = scratch + SC_BK_ROWS;
+#pragma unroll 1
+      for (int i = g0; i < N; i += gstep)
+        for (int k = 0; k < ST_KEEP; k++) r[i * ST_KEEP + k] = ST[i][k];
+    }
+    double c0_R[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) c0_R[k] = c0[k];
+    gsync();
+    // ---- RestoIterateInitializer
+    mu_r = fmax(mu, cviol);
+    tau_r = fmax(K_TAU_MIN, 1.0 - mu_r);
+    double tol_r = P.tol;
+    const double theta_R = theta, infpr_R = cviol;
+    const double orig_inf_pr_max = fmax(K_RESTO_KAPPA * infpr_R, fmin(P.tol, K_CONSTR_VIOL_TOL));
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const bool hasu = i < N - 1;
+      double *q = rs(i);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double c = (i == 0) ? c0[k] : ST[i - 1][ST_CN + k];
+        const double a = mu_r / (2.0 * K_RESTO_RHO) - 0.5 * c, b = c * mu_r / (2.0 * K_RESTO_RHO);
+        const double n = a + sqrt(a * a + b), p = c + n;
+        q[RS_N + k] = n; q[RS_P + k] = p; q[RS_ZN + k] = mu_r / n; q[RS_ZP + k] = mu_r / p;
+      }
+    }
+    gsync();   // everybody has read the residuals before the multipliers change
+#pragma unroll 1
+    for (int i = g0; i < N; i += gstep) {
+      const bool hasu = i < N - 1;
+#pragma unroll
+      for (int k = 0; k < 6; k++) ST[i][ST_LAM + k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k < 2 || hasu) {
+          ST[i][ST_ZL + k] = fmin(K_RESTO_RHO, ST[i][ST_ZL + k]);
+          ST[i][ST_ZU + k] = fmin(K_RESTO_RHO, ST[i][ST_ZU + k]);
+        }
+      }
+    }
+    gsync();
+    RestoLS R;
+    R.nf = 0; R.n_resets = 0; R.succ_rej = 0; R.last_rej = false;
+    double FR[2 * NFILT];
+    double dw_last_r = 0.0;
+    int accept_cnt_r = 0;
+    bool first = true;
+    int rstatus = -1;
+    const int nz = 4 * N + 4 * (N - 1) + 12 * N, m = 6 * N;
+    for (;;) {
+      eta_r = sqrt(mu_r);
+      resto_errors();
+      const double sd = fmax(K_S_MAX, (r_ysum + r_zsum) / (double)(m + nz)) / K_S_MAX;
+      const double sc = fmax(K_S_MAX, r_zsum / (double)nz) / K_S_MAX;
+      const double cp0 = nanmax(fabs(r_amax), fabs(r_amin));
+      const double E0 = nanmax(r_dinf / sd, nanmax(r_cviol, cp0 / sc));
+      // ---- IpRestoConvCheck / IpRestoFilterConvCheck: is this point good enough for the original problem?
+      if (!first) {
+        const double theta_t = theta, infpr_t = r_infpr;
+        bool conv = false;
+        if (K_RESTO_KAPPA * theta_R < theta_t) conv = false;
+        else if (infpr_t > orig_inf_pr_max) conv = false;
+        else {
+          const double phi_t = fma(-mu, lsum, fx);
+          conv = filter_ok(theta_t, phi_t) && acceptable_to_current(theta_t, phi_t, true);
+        }
+        if (conv) { rstatus = 0; break; }
+        bool solved = E0 <= tol_r && r_dinf <= K_DUAL_INF_TOL && r_cviol <= K_CONSTR_VIOL_TOL && cp0 <= K_COMPL_INF_TOL;
+        if (!solved) {
+          if (E0 <= K_ACCEPT_TOL && r_cviol <= K_ACCEPT_CONSTR_VIOL_TOL && cp0 <= K_ACCEPT_COMPL_INF_TOL) {
+            if (++accept_cnt_r >= K_ACCEPT_ITER) solved = true;
+          } else {
+            accept_cnt_r = 0;
+          }
+        }
+        if (solved) {
+          if (infpr_t <= 1e2 * P.tol) {
+            if (tol_r > 1e-1 * P.tol) { tol_r *= 1e-2; accept_cnt_r = 0; }
+            else { rstatus = 9; break; }
+          } else { rstatus = 5; break; }
+        }
+        if (!(E0 == E0)) { rstatus = 11; break; }
+      }
+      if (iter >= P.max_iter) { rstatus = 2; break; }
+      // ---- monotone barrier update (not in the first restoration iteration)
+      if (!first) {
+        for (;;) {
+          const double cpm = nanmax(fabs(r_amax - mu_r), fabs(r_amin - mu_r));
+          const double Emu = nanmax(r_dinf / sd, nanmax(r_cviol, cpm / sc));
+          if (!(Emu <= K_KAPPA_EPS * mu_r)) break;
+          const double mu_min = fmin(tol_r, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0);
+          const double new_mu = fmax(mu_min, fmin(K_KAPPA_MU * mu_r, mu_r * sqrt(mu_r)));
+          if (new_mu == mu_r) break;
+          mu_r = new_mu;
+          tau_r = fmax(K_TAU_MIN, 1.0 - mu_r);
+          R.nf = 0; R.succ_rej = 0; R.last_rej = false;
+          eta_r = sqrt(mu_r);
+          resto_errors();   // the dual infeasibility depends on eta
+        }
+      }
+      first = false;
+      // ---- search direction with inertia correction (its own delta_w history)
+      resto_build_lh();
+      double dwv = 0.0;
+      bool okf = false, first_try = true;
+      for (;;) {
+        resto_rhs(false, dwv);
+        okf = riccati_resto(dwv);
+        if (okf) break;
+        if (first_try) { dwv = (dw_last_r == 0.0) ? K_DW_FIRST : fmax(K_DW_MIN, dw_last_r * K_DW_DEC); first_try = false; }
+        else dwv = (dw_last_r == 0.0) ? dwv * K_DW_INC_FIRST : dwv * K_DW_INC;
+        if (dwv > K_DW_MAX) break;
+      }
+      if (!okf) { rstatus = 10; break; }
+      if (dwv > 0.0) dw_last_r = dwv;
+      forward_resto(dwv);
+      // ---- filter line search on (theta_R, phi_R)
+      resto_eval_extra(0.0, dwv, true);   // the current point's restoration terms (eval_sweep's part is fx, lsum, theta)
+      R.theta = r_thR;
+      R.phi = r_fR - mu_r * (lsum + r_lR);
+      R.gbd = gbd_r;
+      R.pow_gbd = R.gbd < 0.0 ? pow(-R.gbd, K_S_PHI) : 0.0;
+      R.pow_theta = pow(R.theta, K_S_THETA);
+      double amin_ = K_GAMMA_THETA;
+      if (R.gbd < 0.0) {
+        amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * R.theta / (-R.gbd));
+        if (R.theta <= 1e-4) amin_ = fmin(amin_, R.pow_theta / R.pow_gbd);
+      }
+      const double alpha_min_r = amin_ * K_ALPHA_MIN_FRAC;
+      double a = alpha_max_r, a_test = a, phi_acc = 0.0;
+      bool accepted = false;
+      int nt = 0;
+      while (!accepted) {
+        eval_sweep(a);
+        resto_eval_extra(a, dwv, false);
+        double th_t = r_thR, ph_t = r_fR - mu_r * (lt + r_lR);
+        a_test = a;
+        int acc = resto_ls_accept(R, FR, a_test, th_t, ph_t);
+        if (acc == 2) { accepted = true; phi_acc = ph_t; break; }
+        if (acc >= 0) R.last_rej = acc == 1;
+        if (nt == 0 && th_t >= R.theta) {
+          // second-order correction
+          int cnt = 0;
+          double th_old = 0.0, a_soc = a;
+          bool firsts = true;
+          while (cnt < K_MAX_SOC && !accepted && (cnt == 0 || th_t <= K_KAPPA_SOC * th_old)) {
+            th_old = th_t;
+            resto_soc_rhs(firsts, a_soc, dwv);
+            firsts = false;
+            resto_rhs(true, dwv);
+            riccati_resto(dwv);
+            forward_resto(dwv);
+            a_soc = alpha_max_r;
+            eval_sweep(a_soc);
+            resto_eval_extra(a_soc, dwv, false);
+            th_t = r_thR; ph_t = r_fR - mu_r * (lt + r_lR);
+            acc = resto_ls_accept(R, FR, a_test, th_t, ph_t);
+            if (acc == 2) { accepted = true; a = a_soc; phi_acc = ph_t; }
+            else { if (acc >= 0) R.last_rej = acc == 1; cnt++; }
+          }
+          if (accepted) break;
+          // back to the uncorrected direction
+          resto_rhs(false, dwv);
+          riccati_resto(dwv);
+          forward_resto(dwv);
+        }
+        a *= 0.5;
+        nt++;
+        if (a < alpha_min_r) break;
+      }
+      if (!accepted) { rstatus = 9; break; }   // no restoration phase inside the restoration phase
+      // filter reset heuristic, then the filter update (as in commit_accept)
+      {
+        const bool add = !r_is_ftype(R, a_test) || !r_armijo(R, a_test, phi_acc);
+        if (R.n_resets < K_MAX_FILTER_RESETS) {
+          if (R.last_rej) {
+            if (R.succ_rej + 1 >= P.filter_reset_trigger) { R.n_resets++; R.nf = 0; R.succ_rej = 0; } else R.succ_rej++;
+          } else {
+            R.succ_rej = 0;
+          }
+          R.last_rej = false;
+        }
+        if (add) {
+          const double th = (1.0 - K_GAMMA_THETA) * R.theta, ph = R.phi - K_GAMMA_PHI * R.theta;
+          int k = 0;
+          for (int j = 0; j < R.nf; j++) {
+            const double f_t = FR[2 * j], f_p = FR[2 * j + 1];
+            if (!(f_t >= th && f_p >= ph)) { FR[2 * k] = f_t; FR[2 * k + 1] = f_p; k++; }
+          }
+          if (k < NFILT) { FR[2 * k] = th; FR[2 * k + 1] = ph; k++; }
+          R.nf = k;
+        }
+      }
+      resto_accept(a, alpha_z_r, dwv);
+      fx = ft; lsum = lt; theta = tht;
+      iter++;
+    }
+    if (rstatus == 0) {
+      // ---- back to the original problem (PerformRestoration): the bound multipliers take one primal-dual "step"
+      // from x_R to the new point (reset to 1 if that leaves any above bound_mult_reset_threshold), the constraint
+      // multipliers are reset to zero (constr_mult_reset_threshold = 0)
+      double zn = 1.0, zd = 0.0, zmax = 0.0;
+      double dzl[NPASS][4], dzu[NPASS][4];
+#pragma unroll
+      for (int p = 0; p < NPASS; p++) {
+        const int i = g0 + p * gstep;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { dzl[p][k] = 0.0; dzu[p][k] = 0.0; }
+        if (i < N) {
+          const bool hasu = i < N - 1;
+          const double *b = bk(i);
+          const double xn[4] = {ST[i][ST_S + 2], ST[i][ST_S + 3], hasu ? ST[i][ST_U + 0] : 0.0, hasu ? ST[i][ST_U + 1] : 0.0};
+          const double xr[4] = {b[ST_S + 2], b[ST_S + 3], b[ST_U + 0], b[ST_U + 1]};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < 2 || hasu) {
+              const double zl = b[ST_ZL + k], zu = b[ST_ZU + k];
+              const double sRl = xr[k] - PC[LC_LO + k], sNl = xn[k] - PC[LC_LO + k];
+              const double sRu = PC[LC_HI + k] - xr[k], sNu = PC[LC_HI + k] - xn[k];
+              dzl[p][k] = (zl * (sRl - sNl) + mu) / sRl - zl;
+              dzu[p][k] = (zu * (sRu - sNu) + mu) / sRu - zu;
+              if (dzl[p][k] < 0.0 && (zd == 0.0 || zl * zd < zn * (-dzl[p][k]))) { zn = zl; zd = -dzl[p][k]; }
+              if (dzu[p][k] < 0.0 && (zd == 0.0 || zu * zd < zn * (-dzu[p][k]))) { zn = zu; zd = -dzu[p][k]; }
+            }
+          }
+        }
+      }
+      const int G = PAR ? NS_GROUP : 1;
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        const double on = __shfl_xor_sync(gm, zn, o, G), od = __shfl_xor_sync(gm, zd, o, G);
+        const bool take = od > 0.0 && (zd == 0.0 || on * zd < zn * od || (on * zd == zn * od && on < zn));
+        if (take) { zn = on; zd = od; }
+      }
+      const double az = (zd > 0.0 && tau * zn < zd) ? tau * zn / zd : 1.0;
+#pragma unroll
+      for (int p = 0; p < NPASS; p++) {
+        const int i = g0 + p * gstep;
+        if (i < N) {
+          const bool hasu = i < N - 1;
+          const double *b = bk(i);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < 2 || hasu) {
+              const double zl = fma(az, dzl[p][k], b[ST_ZL + k]), zu = fma(az, dzu[p][k], b[ST_ZU + k]);
+              ST[i][ST_ZL + k] = zl; ST[i][ST_ZU + k] = zu;
+              zmax = dmax(zmax, dmax(fabs(zl), fabs(zu)));
+            }
+          }
+        }
+      }
+      zmax = gmax<NS_GROUP>(zmax, gm);
+      if (zmax > K_BOUND_MULT_RESET) {
+#pragma unroll 1
+        for (int i = g0; i < N; i += gstep) {
+          const bool hasu = i < N - 1;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k < 2 || hasu) { ST[i][ST_ZL + k] = 1.0; ST[i][ST_ZU + k] = 1.0; }
+          }
+        }
+      }
+      gsync();
+      iter++;   // the call itself is an iteration of the outer algorithm
+      wd_short = 0; wd_skip = false; in_watchdog = false;
+      lh_stale = true;
+      // multipliers to zero, optimality errors at the new iterate, then Ipopt's tests and the barrier update
+      advance(false, false, true);
+      check_and_update_mu(P);
+    } else {
+      // the restoration failed: the outer algorithm stops with its own iterate
+      gsync();
+      const double *r = scratch + SC_BK_ROWS;
+#pragma unroll 1
+      for (int i = g0; i < N; i += gstep)
+        for (int k = 0; k < ST_KEEP; k++) ST[i][k] = r[i * ST_KEEP + k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) c0[k] = c0_R[k];
+      gsync();
+      status = rstatus; mode = LM_FINISH;
+    }
   }
 
   // ---- one trip of the state machine, in four slots (shared by the lane kernel and the coop kernel) -------
