@@ -34,7 +34,8 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_launch_count", "mpc_last_error", "mpc_version", "mpc_measure_fp64_peak", "mpc_set_kernel",
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
            "mpc_rollout", "mpc_set_handoff", "mpc_set_tail", "mpc_tail_counts", "mpc_measure_solve_latency", "mpc_set_dual_outputs", "mpc_config_from_cli",
-           "mpc_telemetry_parse", "mpc_telemetry_step"]
+           "mpc_telemetry_parse", "mpc_telemetry_step", "mpc_create_multi", "mpc_destroy_multi", "mpc_multi_device_count",
+           "mpc_multi_handle", "mpc_solve_batch_multi"]
 
 
 class MpcError(RuntimeError):
@@ -128,6 +129,13 @@ def lib():
     L.mpc_solve_batch.argtypes = [vp, C.c_int] + [vp] * 13 + [vp]
     L.mpc_solve_batch_host.argtypes = [vp, C.c_int] + [vp] * 13
     L.mpc_solve_one.argtypes = [vp, dp, dp, C.c_double, C.c_double, dp, dp, dp, ip, ip]
+    L.mpc_create_multi.argtypes = [cfgp, ip, C.c_int, C.POINTER(vp)]
+    L.mpc_destroy_multi.argtypes = [vp]
+    L.mpc_destroy_multi.restype = None
+    L.mpc_multi_device_count.argtypes = [vp]
+    L.mpc_multi_handle.argtypes = [vp, C.c_int]
+    L.mpc_multi_handle.restype = vp
+    L.mpc_solve_batch_multi.argtypes = [vp, C.c_int] + [vp] * 13
     L.mpc_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.mpc_run_prepare.argtypes = [cfgp, dp, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, C.POINTER(MpcRunAux)]
     L.mpc_run_finish.argtypes = [cfgp, C.POINTER(MpcRunAux), C.c_double, dp, dp]
@@ -151,6 +159,52 @@ def _check(rc, what):
                  -6: "MPC_EPARSE"}
         raise MpcError("%s failed: %s (%d) %s" % (what, names.get(rc, "?"), rc,
                                                   lib().mpc_last_error().decode()))
+
+
+class MultiSolver:
+    """``mpc_create_multi`` / ``mpc_solve_batch_multi``: the C-ABI's own multi-GPU path (one host thread, one handle
+    and stream per device, contiguous shards).  bench.py's --gpus N uses one process per GPU instead; this class exists
+    for the tests and for the bench's report of what a C++ caller gets."""
+
+    def __init__(self, cfg, devices):
+        self.cfg = cfg
+        self._m = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices)
+        _check(lib().mpc_create_multi(C.byref(cfg), dev, len(devices), C.byref(self._m)), "mpc_create_multi")
+
+    def close(self):
+        if self._m:
+            lib().mpc_destroy_multi(self._m)
+            self._m = C.c_void_p()
+
+    @property
+    def n_devices(self):
+        return lib().mpc_multi_device_count(self._m)
+
+    def solve_raw(self, B, state, coeffs, yaw_lo, yaw_hi, result, traj_x=None, traj_y=None, full=None, status=None,
+                  iters=None, weights=None, N_per=None, dt_per=None):
+        """Host arrays in the C layout ([k][B], batch index fastest); pinned memory lets the devices' copies overlap."""
+        _check(lib().mpc_solve_batch_multi(self._m, B, _ptr(state), _ptr(coeffs), _ptr(yaw_lo), _ptr(yaw_hi), _ptr(weights),
+                                           _ptr(N_per), _ptr(dt_per), _ptr(result), _ptr(traj_x), _ptr(traj_y), _ptr(full),
+                                           _ptr(status), _ptr(iters)), "mpc_solve_batch_multi")
+
+    def solve_batch_host(self, state, coeffs, yaw_lo, yaw_hi, weights=None, N_per=None, dt_per=None, want_full=False):
+        B, N = state.shape[0], self.cfg.N
+        st = np.ascontiguousarray(np.asarray(state, dtype=np.float64).T)
+        co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64).T)
+        yl = np.ascontiguousarray(yaw_lo, dtype=np.float64)
+        yh = np.ascontiguousarray(yaw_hi, dtype=np.float64)
+        w = None if weights is None else np.ascontiguousarray(np.asarray(weights, dtype=np.float64).T)
+        npp = None if N_per is None else np.ascontiguousarray(N_per, dtype=np.int32)
+        dtp = None if dt_per is None else np.ascontiguousarray(dt_per, dtype=np.float64)
+        res, tx, ty = np.zeros((9, B)), np.zeros((N, B)), np.zeros((N, B))
+        full = np.zeros((8 * N - 2, B)) if want_full else None
+        status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        self.solve_raw(B, st, co, yl, yh, res, tx, ty, full, status, iters, w, npp, dtp)
+        out = {"result": res.T.copy(), "traj_x": tx.T.copy(), "traj_y": ty.T.copy(), "status": status, "iters": iters}
+        if want_full:
+            out["full"] = full.T.copy()
+        return out
 
 
 def config_defaults():

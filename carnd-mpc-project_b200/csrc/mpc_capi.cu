@@ -853,6 +853,100 @@ extern "C" int mpc_solve_batch_host(mpc_handle *h, int B, const double *state, c
   return MPC_OK;
 }
 
+// ---- several devices, one host thread ----------------------------------------------------------------------------
+struct mpc_multi {
+  int n;
+  mpc_handle *h[64];
+};
+
+extern "C" int mpc_create_multi(const mpc_config *cfg, const int *devices, int n_devices, mpc_multi **out) {
+  if (!out) return MPC_EINVAL;
+  *out = nullptr;
+  if (!devices || n_devices < 1 || n_devices > 64) return MPC_EINVAL;
+  mpc_multi *m = new (std::nothrow) mpc_multi();
+  if (!m) return MPC_ENOMEM;
+  m->n = 0;
+  for (int g = 0; g < n_devices; g++) {
+    const int rc = mpc_create(cfg, devices[g], &m->h[g]);
+    if (rc) { mpc_destroy_multi(m); return rc; }
+    m->n = g + 1;
+  }
+  *out = m;
+  return MPC_OK;
+}
+
+extern "C" void mpc_destroy_multi(mpc_multi *m) {
+  if (!m) return;
+  for (int g = 0; g < m->n; g++) mpc_destroy(m->h[g]);
+  delete m;
+}
+
+extern "C" int mpc_multi_device_count(const mpc_multi *m) { return m ? m->n : 0; }
+extern "C" mpc_handle *mpc_multi_handle(mpc_multi *m, int g) { return (m && g >= 0 && g < m->n) ? m->h[g] : nullptr; }
+
+extern "C" int mpc_solve_batch_multi(mpc_multi *m, int B, const double *state, const double *coeffs,
+                                     const double *yaw_lo, const double *yaw_hi, const double *weights,
+                                     const int *N_per, const double *dt_per, double *result, double *traj_x,
+                                     double *traj_y, double *full, int *status, int *iters) {
+  if (!m || m->n < 1 || B < 0 || !state || !coeffs || !yaw_lo || !yaw_hi || !result) return MPC_EINVAL;
+  if (B == 0) return MPC_OK;
+  const int G = m->n;
+  const int N = m->h[0]->cfg.N;
+  const size_t pitchB = (size_t)B * sizeof(double);
+  // queue every shard: copies in, launches, copies out -- nothing here waits for a device
+  for (int g = 0; g < G; g++) {
+    const long long lo = (long long)B * g / G, hi = (long long)B * (g + 1) / G;
+    const int Bs = (int)(hi - lo);
+    if (Bs == 0) continue;
+    mpc_handle *h = m->h[g];
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_staging(h, (size_t)Bs, N, weights != nullptr);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    const size_t cap = h->cap_B, w = (size_t)Bs * sizeof(double);
+    double *d_state = h->d_in, *d_coef = d_state + 6 * cap, *d_ylo = d_coef + 5 * cap, *d_yhi = d_ylo + cap;
+    double *d_w = d_yhi + cap, *d_dt = d_w + 12 * cap;
+    double *d_res = h->d_out, *d_tx = d_res + 9 * cap, *d_ty = d_tx + (size_t)N * cap, *d_full = d_ty + (size_t)N * cap;
+    int *d_status = h->d_iout, *d_iters = d_status + cap, *d_N = d_iters + cap;
+    // a shard of a [rows][B] array is `rows` runs of Bs values: one strided copy per array
+    auto in2d = [&](double *dst, const double *src, int rows) {
+      return cudaMemcpy2DAsync(dst, w, src + lo, pitchB, w, (size_t)rows, cudaMemcpyHostToDevice, st);
+    };
+    auto out2d = [&](double *dst, const double *src, int rows) {
+      return cudaMemcpy2DAsync(dst + lo, pitchB, src, w, w, (size_t)rows, cudaMemcpyDeviceToHost, st);
+    };
+    CK(in2d(d_state, state, 6));
+    CK(in2d(d_coef, coeffs, 5));
+    CK(in2d(d_ylo, yaw_lo, 1));
+    CK(in2d(d_yhi, yaw_hi, 1));
+    if (weights) CK(in2d(d_w, weights, 12));
+    if (dt_per) CK(in2d(d_dt, dt_per, 1));
+    if (N_per) {
+      CK(cudaMemcpyAsync(d_N, N_per + lo, (size_t)Bs * sizeof(int), cudaMemcpyHostToDevice, st));
+      // rows at or beyond a problem's horizon stay as the caller left them (see mpc_solve_batch_host)
+      if (traj_x) CK(in2d(d_tx, traj_x, N));
+      if (traj_y) CK(in2d(d_ty, traj_y, N));
+      if (full) CK(in2d(d_full, full, 8 * N - 2));
+    }
+    h->want_pre = false;
+    rc = mpc_solve_batch(h, Bs, d_state, d_coef, d_ylo, d_yhi, weights ? d_w : nullptr, N_per ? d_N : nullptr,
+                         dt_per ? d_dt : nullptr, d_res, traj_x ? d_tx : nullptr, traj_y ? d_ty : nullptr,
+                         full ? d_full : nullptr, d_status, d_iters, st);
+    if (rc) return rc;
+    CK(out2d(result, d_res, 9));
+    if (traj_x) CK(out2d(traj_x, d_tx, N));
+    if (traj_y) CK(out2d(traj_y, d_ty, N));
+    if (full) CK(out2d(full, d_full, 8 * N - 2));
+    if (status) CK(cudaMemcpyAsync(status + lo, d_status, (size_t)Bs * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters + lo, d_iters, (size_t)Bs * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  for (int g = 0; g < G; g++) {
+    CK(cudaSetDevice(m->h[g]->device));
+    CK(cudaStreamSynchronize(m->h[g]->stream));
+  }
+  return MPC_OK;
+}
+
 // One problem, host pointers.
 extern "C" int mpc_solve_one(mpc_handle *h, const double *state, const double *coeffs, double yaw_lo,
                              double yaw_hi, double *result, double *traj_x, double *traj_y, int *status,

@@ -2588,75 +2588,79 @@ struct Lane {
         }
       }
       first = false;
-      // ---- search direction with inertia correction (its own delta_w history)
+      // ---- search direction (inertia correction with its own delta_w history) and filter line search on
+      // (theta_R, phi_R), written as one loop around a single copy of each sweep: `need` says which system to solve
+      // next -- the Newton system (again with a larger delta_w if the inertia is wrong), the second-order-corrected
+      // one, or the uncorrected one again after the corrections failed
       resto_build_lh();
-      double dwv = 0.0;
-      bool okf = false, first_try = true;
+      enum { SOLVE_NONE = 0, SOLVE_NEWTON, SOLVE_SOC, SOLVE_BACK };
+      int need = SOLVE_NEWTON, nt = 0, cnt = 0;
+      double dwv = 0.0, a = 0.0, a_soc = 0.0, a_test = 0.0, phi_acc = 0.0, th_old = 0.0, alpha_min_r = 0.0;
+      bool first_try = true, accepted = false, on_soc = false;
       for (;;) {
-        resto_rhs(false, dwv);
-        okf = riccati_resto(dwv);
-        if (okf) break;
-        if (first_try) { dwv = (dw_last_r == 0.0) ? K_DW_FIRST : fmax(K_DW_MIN, dw_last_r * K_DW_DEC); first_try = false; }
-        else dwv = (dw_last_r == 0.0) ? dwv * K_DW_INC_FIRST : dwv * K_DW_INC;
-        if (dwv > K_DW_MAX) break;
-      }
-      if (!okf) { rstatus = 10; break; }
-      if (dwv > 0.0) dw_last_r = dwv;
-      forward_resto(dwv);
-      // ---- filter line search on (theta_R, phi_R)
-      resto_eval_extra(0.0, dwv, true);   // the current point's restoration terms (eval_sweep's part is fx, lsum, theta)
-      R.theta = r_thR;
-      R.phi = r_fR - mu_r * (lsum + r_lR);
-      R.gbd = gbd_r;
-      R.pow_gbd = R.gbd < 0.0 ? pow(-R.gbd, K_S_PHI) : 0.0;
-      R.pow_theta = pow(R.theta, K_S_THETA);
-      double amin_ = K_GAMMA_THETA;
-      if (R.gbd < 0.0) {
-        amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * R.theta / (-R.gbd));
-        if (R.theta <= 1e-4) amin_ = fmin(amin_, R.pow_theta / R.pow_gbd);
-      }
-      const double alpha_min_r = amin_ * K_ALPHA_MIN_FRAC;
-      double a = alpha_max_r, a_test = a, phi_acc = 0.0;
-      bool accepted = false;
-      int nt = 0;
-      while (!accepted) {
-        eval_sweep(a);
-        resto_eval_extra(a, dwv, false);
-        double th_t = r_thR, ph_t = r_fR - mu_r * (lt + r_lR);
-        a_test = a;
-        int acc = resto_ls_accept(R, FR, a_test, th_t, ph_t);
-        if (acc == 2) { accepted = true; phi_acc = ph_t; break; }
-        if (acc >= 0) R.last_rej = acc == 1;
-        if (nt == 0 && th_t >= R.theta) {
-          // second-order correction
-          int cnt = 0;
-          double th_old = 0.0, a_soc = a;
-          bool firsts = true;
-          while (cnt < K_MAX_SOC && !accepted && (cnt == 0 || th_t <= K_KAPPA_SOC * th_old)) {
-            th_old = th_t;
-            resto_soc_rhs(firsts, a_soc, dwv);
-            firsts = false;
-            resto_rhs(true, dwv);
-            riccati_resto(dwv);
-            forward_resto(dwv);
-            a_soc = alpha_max_r;
-            eval_sweep(a_soc);
-            resto_eval_extra(a_soc, dwv, false);
-            th_t = r_thR; ph_t = r_fR - mu_r * (lt + r_lR);
-            acc = resto_ls_accept(R, FR, a_test, th_t, ph_t);
-            if (acc == 2) { accepted = true; a = a_soc; phi_acc = ph_t; }
-            else { if (acc >= 0) R.last_rej = acc == 1; cnt++; }
+        if (need != SOLVE_NONE) {
+          resto_rhs(need == SOLVE_SOC, dwv);
+          const bool okf = riccati_resto(dwv);
+          if (need == SOLVE_NEWTON && !okf) {
+            if (first_try) { dwv = (dw_last_r == 0.0) ? K_DW_FIRST : fmax(K_DW_MIN, dw_last_r * K_DW_DEC); first_try = false; }
+            else dwv = (dw_last_r == 0.0) ? dwv * K_DW_INC_FIRST : dwv * K_DW_INC;
+            if (dwv > K_DW_MAX) { rstatus = 10; break; }
+            continue;
           }
-          if (accepted) break;
-          // back to the uncorrected direction
-          resto_rhs(false, dwv);
-          riccati_resto(dwv);
           forward_resto(dwv);
+          if (need == SOLVE_NEWTON) {
+            if (dwv > 0.0) dw_last_r = dwv;
+            resto_eval_extra(0.0, dwv, true);   // the current point's restoration terms (eval_sweep's part is fx, lsum, theta)
+            R.theta = r_thR;
+            R.phi = r_fR - mu_r * (lsum + r_lR);
+            R.gbd = gbd_r;
+            R.pow_gbd = R.gbd < 0.0 ? pow(-R.gbd, K_S_PHI) : 0.0;
+            R.pow_theta = pow(R.theta, K_S_THETA);
+            double amin_ = K_GAMMA_THETA;
+            if (R.gbd < 0.0) {
+              amin_ = fmin(K_GAMMA_THETA, K_GAMMA_PHI * R.theta / (-R.gbd));
+              if (R.theta <= 1e-4) amin_ = fmin(amin_, R.pow_theta / R.pow_gbd);
+            }
+            alpha_min_r = amin_ * K_ALPHA_MIN_FRAC;
+            a = alpha_max_r; nt = 0; on_soc = false;
+          } else if (need == SOLVE_SOC) {
+            a_soc = alpha_max_r; on_soc = true;
+          } else {   // the uncorrected direction is back: go on backtracking
+            on_soc = false;
+            a *= 0.5; nt++;
+            if (a < alpha_min_r) break;
+          }
+          need = SOLVE_NONE;
         }
-        a *= 0.5;
-        nt++;
-        if (a < alpha_min_r) break;
+        const double a_eval = on_soc ? a_soc : a;
+        eval_sweep(a_eval);
+        resto_eval_extra(a_eval, dwv, false);
+        const double th_t = r_thR, ph_t = r_fR - mu_r * (lt + r_lR);
+        if (!on_soc) a_test = a;
+        const int acc = resto_ls_accept(R, FR, a_test, th_t, ph_t);
+        if (acc == 2) { accepted = true; phi_acc = ph_t; if (on_soc) a = a_soc; break; }
+        if (acc >= 0) R.last_rej = acc == 1;
+        if (!on_soc) {
+          if (nt == 0 && th_t >= R.theta) {   // second-order correction
+            cnt = 0; th_old = th_t;
+            resto_soc_rhs(true, a, dwv);
+            need = SOLVE_SOC;
+          } else {
+            a *= 0.5; nt++;
+            if (a < alpha_min_r) break;
+          }
+        } else {
+          cnt++;
+          if (cnt < K_MAX_SOC && th_t <= K_KAPPA_SOC * th_old) {
+            th_old = th_t;
+            resto_soc_rhs(false, a_soc, dwv);
+            need = SOLVE_SOC;
+          } else {
+            need = SOLVE_BACK;
+          }
+        }
       }
+      if (rstatus >= 0) break;
       if (!accepted) { rstatus = 9; break; }   // no restoration phase inside the restoration phase
       // filter reset heuristic, then the filter update (as in commit_accept)
       {
@@ -2814,10 +2818,11 @@ struct Lane {
       zero = true; err = true;
     } else if (FULL && m1 == LM_LSFAIL) {
       restoration(P);
-      return;
     } else if (m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
       const double phi_t = fma(-mu, lt, ft);
-      if (m1 == LM_TRIAL && !(FULL && in_watchdog)) alpha_test = alpha;
+      // the step size the switching condition and the Armijo test are made with: this trial's, or -- while the
+      // watchdog runs -- the one of the step it started with
+      if (m1 == LM_TRIAL) alpha_test = (FULL && in_watchdog) ? wd_alpha_test : alpha;
       bool take = false;
       if (FULL && force_accept) {
         // a tiny step (trip_solve): taken untested, the filter and the watchdog counter stay as they are
@@ -2826,9 +2831,10 @@ struct Lane {
       } else {
         const int acc = ls_accept(alpha_test, tht, phi_t);
         if (acc == 2) {
-          if (!commit_accept(P, phi_t)) { escalate = true; return; }
-          if (FULL) in_watchdog = false;
-          take = true;
+          // (no early return here: it would move the reconvergence point of this whole if-chain behind the sweep
+          // below, and the lanes of a warp would run it in two or three passes)
+          if (commit_accept(P, phi_t)) { if (FULL) in_watchdog = false; take = true; }
+          else escalate = true;
         } else {
           if (acc >= 0) last_rej_filter = acc == 1;
           if (FULL && in_watchdog) {

@@ -146,6 +146,27 @@ int mpc_solve_batch_host(mpc_handle *h, int B,
                          double *result, double *traj_x, double *traj_y, double *full,
                          int *status, int *iters);
 
+/* ---- all the GPUs of one box from one host thread ----------------------------------------------------------------
+ * The reference is a single-threaded C++ program (src/mpc_main.cpp:51); a C++ caller of this header gets several GPUs
+ * without Python or MPI: one solver handle and stream per device, the batch cut into contiguous shards
+ * [g*B/G, (g+1)*B/G) (problems are independent: no exchange step, no collective), every shard's host->device copies,
+ * launches and device->host copies queued asynchronously on its device's stream, one wait per device at the end.
+ * HOST pointers, same layout and meaning as mpc_solve_batch_host; every output array is gathered.  Page-locked
+ * (cudaMallocHost / cudaHostRegister) caller arrays let the copies of different devices overlap.  devices may name
+ * a device more than once (two handles on one GPU).  mpc_multi_handle(m, g) gives shard g's handle for the
+ * mpc_set_* calls. */
+typedef struct mpc_multi mpc_multi;
+int mpc_create_multi(const mpc_config *cfg, const int *devices, int n_devices, mpc_multi **out);
+void mpc_destroy_multi(mpc_multi *m);
+int mpc_multi_device_count(const mpc_multi *m);
+mpc_handle *mpc_multi_handle(mpc_multi *m, int g);
+int mpc_solve_batch_multi(mpc_multi *m, int B,
+                          const double *state, const double *coeffs,
+                          const double *yaw_lo, const double *yaw_hi,
+                          const double *weights, const int *N_per, const double *dt_per,
+                          double *result, double *traj_x, double *traj_y, double *full,
+                          int *status, int *iters);
+
 /* Kernel selection.  MPC_KERNEL_AUTO (default): batches of at least MPC_LANE_MIN_BATCH problems (N <= 32) or more
  * than MPC_COOP_MAX_BATCH_LONG problems (N > 32) run the throughput kernel (one problem per lane, tail handled as
  * mpc_set_tail describes); smaller batches -- where the time is set by the longest-running problem, not by

@@ -20,7 +20,7 @@ if _NAME not in sys.modules:
 
 _pkg = sys.modules[_NAME]
 from carnd_mpc_project_b200 import *  # noqa: F401,F403,E402
-from carnd_mpc_project_b200 import (MpcConfig, MpcError, Solver, build, lib, LIB_PATH, EXPORTS,  # noqa: E402,F401
+from carnd_mpc_project_b200 import (MpcConfig, MpcError, Solver, MultiSolver, build, lib, LIB_PATH, EXPORTS,  # noqa: E402,F401
                                     config_defaults, config_from_json_file, config_from_json_text, config_from_cli,
                                     STATUS_NAMES, STATUS_SUCCESS, KERNEL_AUTO, KERNEL_LANE, KERNEL_COOP,
                                     LANE_MIN_BATCH, MpcRunAux, MpcTelemetry, telemetry_parse, run_prepare, run_finish, compute_throttle,

@@ -6,7 +6,8 @@ oracle/ref_shim).  Build container only:   make -C oracle/ref_shim && python tes
 Cases: (a) src/test.cpp's scenario (run() + 25 x solve(), test.cpp:64-111) for its four fixtures;
 (b) MPC::run from perturbed poses on lake-track windows, all three shipped configs; (c) MPC::solve with
 modified Config::weights -- including the acceleration weights, which the recorded tape ignores;
-(d) MPC::solve over the N x dt grid of examples/."""
+(d) MPC::solve over the N x dt grid of examples/; (f) MPC::solve on long-horizon cells (N = 20, 30, 40 at dt = 0.1)
+for problems whose line search runs below alpha_min, i.e. that ENTER Ipopt's feasibility restoration phase."""
 import json
 import os
 import sys
@@ -85,6 +86,30 @@ for (Ng, dtg) in [(10, 0.1), (20, 0.1), (30, 0.1), (10, 0.05), (20, 0.05), (30, 
                             "yaw_hi": b["yaw_hi"][i], "status": s["status"], "iters": s["iters"], "result": L(s["result"]),
                             "traj_x": L(s["traj_x"]), "traj_y": L(s["traj_y"])})
     print("grid", Ng, dtg, [c["status"] for c in out["grid"][-3:]], [c["iters"] for c in out["grid"][-3:]])
+pr.set_horizon(js["N"], js["dt"])
+
+# (f) problems that enter the restoration phase (long horizons at dt = 0.1: the fit is extrapolated, the line search
+# stalls).  Picked with the plain-C oracle's counters, solved through the reference's own MPC::solve.
+import ctypes  # noqa: E402
+out["resto"] = []
+for (Ng, dtg, want) in [(20, 0.1, 3), (30, 0.1, 5), (40, 0.1, 4)]:
+    jsg = dict(js, N=Ng, dt=dtg)
+    cdg = po.load_config_dict(jsg)
+    bb = mpc.workloads.batch_perturbed_states(160, 1, cdg)
+    probs = po.problems_from_arrays(bb["state"], bb["coeffs"], bb["yaw_lo"], bb["yaw_hi"])
+    res = (po.OrcResult * 160)()
+    ocfg = po.make_config(cdg)
+    po.lib().orc_solve_batch(ctypes.byref(ocfg), probs, 160, res, 8)
+    idx = [i for i in range(160) if res[i].n_resto > 0][:want]
+    pr.set_horizon(Ng, dtg)
+    for i in idx:
+        s = pr.solve(bb["state"][i], bb["coeffs"][i], bb["yaw_lo"][i], bb["yaw_hi"][i], Ng)
+        out["resto"].append({"N": Ng, "dt": dtg, "state": L(bb["state"][i]), "coeffs": L(bb["coeffs"][i]), "yaw_lo": bb["yaw_lo"][i],
+                             "yaw_hi": bb["yaw_hi"][i], "status": s["status"], "iters": s["iters"], "result": L(s["result"]),
+                             "traj_x": L(s["traj_x"]), "traj_y": L(s["traj_y"]),
+                             "oracle_n_resto": int(res[i].n_resto), "oracle_n_resto_iter": int(res[i].n_resto_iter),
+                             "oracle_iters": int(res[i].iters), "oracle_status": int(res[i].status)})
+        print("resto", Ng, dtg, i, "ref status", s["status"], "iters", s["iters"], "| oracle iters", res[i].iters, "resto calls", res[i].n_resto)
 pr.set_horizon(js["N"], js["dt"])
 
 # (e) plant and actuation map: Vehicle::move, Vehicle::computeThrottle (Vehicle.cpp:81-103,145-168)

@@ -588,3 +588,52 @@ def test_repeated_runs_give_the_same_bits(mpc, stable_cfg, stable_cd):
         else:
             assert all(torch.equal(a, b_) for a, b_ in zip(ref, (res, tx, st, it))), rep
     S.close()
+
+
+def test_c_abi_multi_gpu_entry_point(mpc, stable_cfg, stable_cd, refdata, tmp_path):
+    """mpc_create_multi / mpc_solve_batch_multi: contiguous shards over several handles (one per device; here every
+    visible device, and three handles dealt over them so that the sharding is exercised on a one-GPU box too), from
+    Python and from a C++ program that uses nothing but include/mpc_b200.h.  Same bits as one handle."""
+    import subprocess
+    import torch
+    nd = torch.cuda.device_count()
+    b = mpc.workloads.batch_perturbed_states(20011, 5, stable_cd)      # odd size: uneven shards
+    args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S = mpc.Solver(stable_cfg, 0)
+    ref = S.solve_batch_host(*args, want_full=True)
+    S.close()
+    for devices in ([0], list(range(nd)), [k % nd for k in range(3)]):
+        M = mpc.MultiSolver(stable_cfg, devices)
+        assert M.n_devices == len(devices)
+        got = M.solve_batch_host(*args, want_full=True)
+        M.close()
+        for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
+            assert np.array_equal(got[k], ref[k]), (devices, k)
+    # ragged batch through the multi entry point: rows beyond a problem's horizon stay untouched
+    Np = np.random.default_rng(2).choice([4, 7, 10], 3000).astype(np.int32)
+    S = mpc.Solver(stable_cfg, 0)
+    a3 = tuple(a[:3000] for a in args)
+    ref = S.solve_batch_host(*a3, N_per=Np)
+    S.close()
+    M = mpc.MultiSolver(stable_cfg, [k % nd for k in range(2)])
+    got = M.solve_batch_host(*a3, N_per=Np)
+    M.close()
+    for k in ("result", "traj_x", "traj_y", "status", "iters"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert (got["traj_x"][Np == 4][:, 4:] == 0).all()
+    with pytest.raises(mpc.MpcError):
+        mpc.MultiSolver(stable_cfg, [])
+    # the C++ caller
+    exe = tmp_path / "test_multi_gpu"
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "carnd-mpc-project_b200")
+    root = os.path.dirname(pkg)
+    subprocess.run(["g++", "-O2", "-std=c++11", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include", "-o", str(exe),
+                    os.path.join(root, "tests", "cpp", "test_multi_gpu.cpp"), "-L", pkg, "-lmpc_b200", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                    "-Wl,-rpath," + pkg, "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    cfgp = tmp_path / "config-stable.json"
+    cfgp.write_text(json.dumps(refdata["configs"]["stable"]))
+    for nh in (1, max(2, nd)):
+        out = subprocess.run([str(exe), str(cfgp), "30000", str(nh)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        f = out.stdout.split()
+        assert f[f.index("mismatches") + 1] == "0" and float(f[f.index("ok_frac") + 1]) > 0.99, out.stdout

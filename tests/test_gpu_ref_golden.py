@@ -69,8 +69,6 @@ def test_weight_sweep_cases(gold, solver):
 
 def test_horizon_grid_cases(gold, mpc, refdata, kernel_kind):
     for c in gold["grid"]:
-        if kernel_kind == 1 and c["N"] > 32:
-            continue
         cfg = mpc.config_from_json_text(json.dumps(dict(refdata["configs"]["stable"], N=c["N"], dt=c["dt"])))
         S = mpc.Solver(cfg, 0)
         S.set_kernel(kernel_kind)
@@ -78,6 +76,23 @@ def test_horizon_grid_cases(gold, mpc, refdata, kernel_kind):
         S.close()
         assert r["status"][0] == c["status"] == 1
         _cmp(r["result"][0], c["result"])
+        assert np.abs(r["traj_y"][0] - np.array(c["traj_y"])).max() < ABS_TOL
+
+
+def test_restoration_cases_of_the_reference_sources(gold, mpc, refdata, kernel_kind):
+    """Problems whose solve ENTERS Ipopt's restoration phase (N = 30, 40 at dt = 0.1), as solved by the reference's
+    own MPC::solve / FG_eval compiled against the AD + interior-point stand-ins: same status, same optimum."""
+    assert len(gold["resto"]) >= 8
+    for c in gold["resto"]:
+        assert c["oracle_n_resto"] >= 1 and c["status"] == 1
+        cfg = mpc.config_from_json_text(json.dumps(dict(refdata["configs"]["stable"], N=c["N"], dt=c["dt"])))
+        S = mpc.Solver(cfg, 0)
+        S.set_kernel(kernel_kind)
+        r = S.solve_batch_host(np.array([c["state"]]), np.array([c["coeffs"]]), np.array([c["yaw_lo"]]), np.array([c["yaw_hi"]]))
+        S.close()
+        assert r["status"][0] == c["status"]
+        _cmp(r["result"][0], c["result"])
+        assert np.abs(r["traj_x"][0] - np.array(c["traj_x"])).max() < ABS_TOL
         assert np.abs(r["traj_y"][0] - np.array(c["traj_y"])).max() < ABS_TOL
 
 

@@ -1,0 +1,183 @@
+"""The rare branches of Ipopt's algorithm on the GPU: feasibility restoration phase, watchdog, tiny steps, filter
+reset heuristic.  Long horizons at dt = 0.1 extrapolate the fitted polynomial far beyond the waypoints; there the
+line search stalls on ~10 % of the problems and Ipopt (MPC.cpp:290-292, every default on) switches to its
+restoration phase.  Every comparison below is UNMASKED: all problems of a batch, whatever their status."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import nlp_numpy as nn
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ABS_TOL, REL_TOL = 1e-4, 1e-6
+
+
+def _oracle_full(po, cd, b, **knobs):
+    B = b["state"].shape[0]
+    probs = po.problems_from_arrays(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    res = (po.OrcResult * B)()
+    cfg = po.make_config(cd, **knobs)
+    po.lib().orc_solve_batch(C.byref(cfg), probs, B, res, os.cpu_count() or 4)
+    f = lambda name: np.array([getattr(r, name) for r in res])
+    out = {k: f(k) for k in ("status", "iters", "n_resto", "n_resto_iter", "n_watchdog", "n_tiny", "n_filter_reset", "n_filter_max")}
+    out["result"] = np.array([list(r.result) for r in res])
+    return out
+
+
+def _gpu_cfg(mpc, js, **knobs):
+    cfg = mpc.config_from_json_text(json.dumps(js))
+    for k, v in knobs.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _assert_all_equal(g, c):
+    assert np.array_equal(g["status"], c["status"]), (np.nonzero(g["status"] != c["status"])[0][:10], g["status"][g["status"] != c["status"]][:10])
+    d = np.abs(g["result"] - c["result"])
+    assert d[:, :8].max() < ABS_TOL, d[:, :8].max()
+    assert (d[:, 8] / np.maximum(1.0, np.abs(c["result"][:, 8]))).max() < REL_TOL
+    return d
+
+
+@pytest.mark.parametrize("N,dt,B", [(30, 0.1, 240), (40, 0.1, 120), (50, 0.05, 120)])
+def test_restoration_cells_match_oracle_unmasked(mpc, po, refdata, N, dt, B, kernel_kind):
+    js = dict(refdata["configs"]["stable"], N=N, dt=dt)
+    cd = po.load_config_dict(js)
+    b = mpc.workloads.batch_perturbed_states(B, 1, cd)
+    c = _oracle_full(po, cd, b)
+    assert (c["n_resto"] > 0).sum() >= 3                    # the cell does exercise the restoration phase
+    assert (c["status"] == 1).mean() >= 0.995               # ... and with it Ipopt's algorithm converges here
+    if N <= 40:
+        assert (c["n_filter_max"] > 8).sum() >= 3           # more filter entries than a lane of the lane kernel holds
+    S = mpc.Solver(_gpu_cfg(mpc, js), 0)
+    S.set_kernel(kernel_kind)
+    g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.close()
+    d = _assert_all_equal(g, c)
+    r = c["n_resto"] > 0
+    assert d[r][:, :8].max() < 1e-6                         # the problems that went through restoration: same optimum
+    # iteration counts: identical except where rounding (dense LDL^T vs Riccati) moves a step-size decision
+    assert (g["iters"] == c["iters"]).mean() > 0.85
+
+
+def test_lane_chain_and_coop_kernel_same_bits_on_hard_cell(mpc, po, refdata):
+    """The lane kernel hands a problem to the coop kernel when it needs the restoration phase or a 9th filter entry,
+    at a point where nothing of the trip is committed: the result is bit-identical to solving it in the coop kernel
+    from the start -- with records (tail packing on) and through the restart list (no record buffers in use)."""
+    js = dict(refdata["configs"]["stable"], N=30, dt=0.1)
+    cd = po.load_config_dict(js)
+    b = mpc.workloads.batch_perturbed_states(1500, 1, cd)
+    args = (b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S = mpc.Solver(_gpu_cfg(mpc, js), 0)
+    S.set_kernel(mpc.KERNEL_COOP)
+    ref = S.solve_batch_host(*args, want_full=True)
+    assert (ref["status"] == 1).mean() > 0.995 and ref["iters"].max() > 100
+    S.set_kernel(mpc.KERNEL_LANE)
+    for park, resume in ((0, 0), (16, 3), (8, 1)):
+        S.set_tail(park, resume)
+        got = S.solve_batch_host(*args, want_full=True)
+        for k in ("result", "traj_x", "traj_y", "full", "status", "iters"):
+            assert np.array_equal(got[k], ref[k]), (park, resume, k)
+    S.close()
+
+
+@pytest.mark.parametrize("knobs,counter", [({"watchdog_trigger": 1}, "n_watchdog"), ({"watchdog_trigger": 2}, "n_watchdog"),
+                                           ({"tiny_step_tol": 1e-7}, "n_tiny"), ({"filter_reset_trigger": 1}, "n_filter_reset")])
+def test_watchdog_tiny_step_and_filter_reset_branches(mpc, po, refdata, knobs, counter, kernel_kind):
+    """These branches almost never fire with Ipopt's default triggers on this problem family (the watchdog on one
+    problem in a few hundred at N = 30), so they are forced through the options Ipopt has for them
+    (watchdog_shortened_iter_trigger, tiny_step_tol, filter_reset_trigger) and compared with the oracle run with the
+    same options."""
+    js = dict(refdata["configs"]["stable"], N=30, dt=0.1)
+    cd = po.load_config_dict(js)
+    b = mpc.workloads.batch_perturbed_states(200, 1, cd)
+    c = _oracle_full(po, cd, b, **knobs)
+    assert (c[counter] > 0).sum() >= 1, "the branch did not fire in the oracle"
+    # With the watchdog forced on after ONE shortened step a few long runs become chaotic: the oracle itself lands on
+    # a different local optimum when the 14th digit of the start speed changes (seen on one problem of this batch:
+    # cost 30389.5 / 29537.9 / 11454.5 for relative changes of 0 / -1e-14 / 1e-13; with Ipopt's default trigger the same
+    # problem is stable).  No implementation can be compared on those: keep the problems whose oracle answer survives
+    # a 1e-13 relative change of v0, and say how many that is.
+    b2 = dict(b, state=b["state"] * np.array([1, 1, 1, 1 + 1e-13, 1, 1]))
+    c2 = _oracle_full(po, cd, b2, **knobs)
+    stable = (np.abs(c2["result"] - c["result"])[:, :8].max(axis=1) < 1e-6) & (c2["status"] == c["status"])
+    assert stable.mean() > 0.97
+    S = mpc.Solver(_gpu_cfg(mpc, js, **knobs), 0)
+    S.set_kernel(kernel_kind)
+    g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.close()
+    assert (g["status"] == 1).mean() >= 0.995
+    d = _assert_all_equal({k: g[k][stable] for k in ("status", "result")}, {k: c[k][stable] for k in ("status", "result")})
+    f = c[counter][stable] > 0
+    assert f.sum() >= 1
+    assert d[f][:, :8].max() < 1e-6
+    assert (g["iters"][stable][f] == c["iters"][stable][f]).mean() >= 0.5
+
+
+def test_default_watchdog_fires_and_matches(mpc, po, refdata):
+    """Ipopt's default trigger (10 successive shortened steps) on a batch where it does fire."""
+    js = dict(refdata["configs"]["stable"], N=30, dt=0.1)
+    cd = po.load_config_dict(js)
+    b = mpc.workloads.batch_perturbed_states(200, 1, cd)
+    c = _oracle_full(po, cd, b)
+    if (c["n_watchdog"] > 0).sum() == 0:
+        pytest.skip("no watchdog activation in this batch")
+    S = mpc.Solver(_gpu_cfg(mpc, js), 0)
+    g = S.solve_batch_host(b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"])
+    S.close()
+    w = c["n_watchdog"] > 0
+    assert np.array_equal(g["status"][w], c["status"][w])
+    assert np.abs(g["result"][w] - c["result"][w])[:, :8].max() < 1e-6
+
+
+def test_recovered_points_carry_a_kkt_certificate(mpc, po, refdata):
+    """Solver-independent check of the points reached THROUGH the restoration phase: with the multipliers the kernel
+    returns they satisfy the KKT conditions of the reference's NLP as stated independently in tests/nlp_numpy.py."""
+    import torch
+    N, dt, B = 30, 0.1, 240
+    js = dict(refdata["configs"]["stable"], N=N, dt=dt)
+    cd = po.load_config_dict(js)
+    b = mpc.workloads.batch_perturbed_states(B, 1, cd)
+    c = _oracle_full(po, cd, b)
+    r = c["n_resto"] > 0
+    assert r.sum() >= 5
+    S = mpc.Solver(_gpu_cfg(mpc, js), 0)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a.T if a.ndim == 2 else a)).to(dev)
+    lam = torch.zeros(6 * N, B, dtype=torch.float64, device=dev)
+    zl = torch.zeros(8 * N - 2, B, dtype=torch.float64, device=dev)
+    zu = torch.zeros(8 * N - 2, B, dtype=torch.float64, device=dev)
+    full = torch.zeros(8 * N - 2, B, dtype=torch.float64, device=dev)
+    res = torch.zeros(9, B, dtype=torch.float64, device=dev)
+    st = torch.zeros(B, dtype=torch.int32, device=dev)
+    S.set_dual_outputs(lam, zl, zu)
+    S.solve_batch_device(B, up(b["state"]), up(b["coeffs"]), up(b["yaw_lo"]), up(b["yaw_hi"]), res, None, None, full, st, None)
+    torch.cuda.synchronize()
+    S.set_dual_outputs(None, None, None)
+    S.close()
+    assert (st.cpu().numpy()[r] == 1).all()
+    z, lam, zl, zu = full.cpu().numpy().T[r], lam.cpu().numpy().T[r], zl.cpu().numpy().T[r], zu.cpu().numpy().T[r]
+    state, coeffs = b["state"][r], b["coeffs"][r]
+    fz = {k: v[r] if isinstance(v, np.ndarray) and v.shape[0] == B else v for k, v in nn.frozen(cd, b["state"]).items()}
+    # Ipopt converges on bounds relaxed by 1e-8 * max(1, |b|) and then clips the point onto the original bounds
+    # (honor_original_bounds): over this 3 s horizon the speed reaches its bound (53.6 m/s), so a clipped v moves by up
+    # to 5.4e-7 and the dynamics rows that contain it by as much
+    assert np.abs(nn.constraints(cd, state, coeffs, z)).max() < 1e-6
+    xl, xu = nn.var_bounds(cd, b["yaw_lo"][r], b["yaw_hi"][r])
+    assert (z >= xl).all() and (z <= xu).all()
+    assert (zl >= 0).all() and (zu >= 0).all()
+    g = nn.lagrangian_gradient(cd, fz, state, coeffs, z, lam, zl, zu)
+    sd = np.maximum(100.0, (np.abs(lam).sum(axis=1) + zl.sum(axis=1) + zu.sum(axis=1)) / (6 * N + 4 * N + 4 * (N - 1))) / 100.0
+    gn = np.abs(g).max(axis=1) / sd
+    # a point clipped onto its original bound moved by up to 1e-8 * |bound|: 5.4e-7 for the speed bound, which most of
+    # these trajectories reach, i.e. ~1e-6 in the gradient (2 w_v dv); ~3e-5 where a steering bound is active
+    assert gn.max() < 1e-4, gn.max()
+    assert np.median(gn) < 5e-6
+    bl, bu = xl > -1e18, xu < 1e18
+    cl = np.where(bl, zl * (z - xl), 0.0).max(axis=1)
+    cu = np.where(bu, zu * (xu - z), 0.0).max(axis=1)
+    assert max(cl.max(), cu.max()) < 1e-4

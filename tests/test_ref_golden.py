@@ -65,6 +65,19 @@ def test_oracle_matches_reference_horizon_grid(gold, po, stable_cd):
         assert np.abs(r["z"][c["N"]:2 * c["N"]] - np.array(c["traj_y"])).max() < 1e-6
 
 
+def test_oracle_matches_reference_on_restoration_cases(gold, po, stable_cd):
+    """The analytic restatement and the reference's own FG_eval (through the AD tape) walk the same path through the
+    restoration phase: same status, same iteration count, same point."""
+    assert len(gold["resto"]) >= 8
+    for c in gold["resto"]:
+        cd = dict(stable_cd, N=c["N"], dt=c["dt"])
+        r = po.solve(po.make_config(cd), po.make_problem(c["state"], c["coeffs"], c["yaw_lo"], c["yaw_hi"]))
+        assert r["n_resto"] == c["oracle_n_resto"] >= 1
+        assert r["status"] == c["status"] == 1
+        assert r["iters"] == c["iters"]
+        _cmp(r["result"], c["result"], tol=1e-6)
+
+
 def test_host_run_logic_matches_reference(gold, mpc, po, refdata):
     """mpc_run_prepare / mpc_run_finish (product, host C++) == MPC::run of the reference: vehicle-frame
     waypoints, adaptive-order fit, cte/epsi, yaw bounds; then steer adjustment, accel clamp, normalisation
