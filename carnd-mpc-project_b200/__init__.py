@@ -35,7 +35,7 @@ EXPORTS = ["mpc_config_defaults", "mpc_config_load_json", "mpc_config_parse_json
            "mpc_run_prepare", "mpc_run_finish", "mpc_compute_throttle", "mpc_vehicle_move", "mpc_run_batch",
            "mpc_rollout", "mpc_set_handoff", "mpc_set_tail", "mpc_tail_counts", "mpc_measure_solve_latency", "mpc_set_dual_outputs", "mpc_config_from_cli",
            "mpc_telemetry_parse", "mpc_telemetry_step", "mpc_create_multi", "mpc_destroy_multi", "mpc_multi_device_count",
-           "mpc_multi_handle", "mpc_solve_batch_multi"]
+           "mpc_multi_handle", "mpc_solve_batch_multi", "mpc_set_rollout_mode"]
 
 
 class MpcError(RuntimeError):
@@ -120,6 +120,7 @@ def lib():
     L.mpc_set_config.argtypes = [vp, cfgp]
     L.mpc_set_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mpc_set_handoff.argtypes = [vp, C.c_int]
+    L.mpc_set_rollout_mode.argtypes = [vp, C.c_int]
     L.mpc_set_tail.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.mpc_tail_counts.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
     L.mpc_measure_solve_latency.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -324,6 +325,10 @@ class Solver:
     def set_kernel(self, kind=KERNEL_AUTO, lane_threads=0, lane_ctas_per_sm=0):
         """Pick the kernel (auto / one problem per warp / one problem per lane) and the lane grid."""
         _check(lib().mpc_set_kernel(self._h, kind, lane_threads, lane_ctas_per_sm), "mpc_set_kernel")
+
+    def set_rollout_mode(self, mode):
+        """0 = automatic, 1 = three launches per control step, 2 = one persistent launch (mpc_set_rollout_mode)."""
+        _check(lib().mpc_set_rollout_mode(self._h, int(mode)), "mpc_set_rollout_mode")
 
     def set_tail(self, park_lanes, resume_launches, sort_ragged=True, resume_min=0, late_copy=False):
         """Tail packing of the lane kernel (mpc_set_tail): sparse-warp threshold, resume launches (each runs only if it

@@ -67,6 +67,7 @@ struct mpc_handle {
   size_t cap_ckpt;      // records per buffer
   int ckpt_ns;
   bool sort_ragged;     // ragged batches (N_per given): hand the problems out longest horizon first
+  int rollout_mode;     // MPC_ROLLOUT_AUTO / PER_STEP / PERSISTENT
   int *d_restart;       // indices of the problems the lane kernel handed over without a record
   size_t cap_restart;
   double *d_scratch;    // coop kernels: global scratch per lane group (watchdog backup, restoration rows)
@@ -628,15 +629,8 @@ extern "C" int mpc_set_kernel(mpc_handle *h, int kind, int lane_threads, int lan
   return MPC_OK;
 }
 
-extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const double *coeffs,
-                               const double *yaw_lo, const double *yaw_hi, const double *weights,
-                               const int *N_per, const double *dt_per, double *result, double *traj_x,
-                               double *traj_y, double *full, int *status, int *iters, void *cuda_stream) {
-  if (!h || B < 0 || !state || !coeffs || !yaw_lo || !yaw_hi || !result) return MPC_EINVAL;
-  if (B == 0) return MPC_OK;
-  CK(cudaSetDevice(h->device));
-  const mpc_config &c = h->cfg;
-  KParams kp;
+// the configuration part of the launch parameters
+static void fill_kparams(const mpc_config &c, int B, KParams &kp) {
   memset(&kp, 0, sizeof(kp));
   kp.B = B; kp.Nmax = c.N; kp.max_iter = c.max_iter; kp.n_steers = c.n_steers; kp.n_steer_speeds = c.n_steer_speeds;
   kp.dt = c.dt; kp.Lf = c.Lf; kp.cte_panic = c.cte_panic; kp.epsi_panic = c.epsi_panic;
@@ -646,6 +640,18 @@ extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const 
   memcpy(kp.weights, c.weights, sizeof(kp.weights));
   memcpy(kp.steers, c.steers, sizeof(kp.steers));
   memcpy(kp.steer_speeds, c.steer_speeds, sizeof(kp.steer_speeds));
+}
+
+extern "C" int mpc_solve_batch(mpc_handle *h, int B, const double *state, const double *coeffs,
+                               const double *yaw_lo, const double *yaw_hi, const double *weights,
+                               const int *N_per, const double *dt_per, double *result, double *traj_x,
+                               double *traj_y, double *full, int *status, int *iters, void *cuda_stream) {
+  if (!h || B < 0 || !state || !coeffs || !yaw_lo || !yaw_hi || !result) return MPC_EINVAL;
+  if (B == 0) return MPC_OK;
+  CK(cudaSetDevice(h->device));
+  const mpc_config &c = h->cfg;
+  KParams kp;
+  fill_kparams(c, B, kp);
   kp.state = state; kp.coeffs = coeffs; kp.yaw_lo = yaw_lo; kp.yaw_hi = yaw_hi; kp.weights_pp = weights;
   kp.N_pp = N_per; kp.dt_pp = dt_per;
   kp.result = result; kp.traj_x = traj_x; kp.traj_y = traj_y; kp.full = full; kp.status = status; kp.iters = iters;
@@ -1125,6 +1131,40 @@ extern "C" int mpc_run_batch(mpc_handle *h, int B, const double *pose, const dou
   return MPC_OK;
 }
 
+// the closed loop as one launch of mpc_rollout_kernel: a lane group per vehicle, all T steps
+template <int NS>
+static int launch_rollout(mpc_handle *h, const LoopArgs &A, int T, cudaStream_t st) {
+  const int threads = 128, G = NS <= 16 ? 16 : 32, groups = threads / G;
+  const size_t smem = (size_t)groups * NS * ST_ROW_SH * sizeof(double);
+  static thread_local int cached_dev = -1, per_sm = 0;
+  if (cached_dev != h->device) {
+    CK(cudaFuncSetAttribute(mpc_rollout_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_rollout_kernel<NS>, threads, smem));
+    cached_dev = h->device;
+  }
+  if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "rollout kernel does not fit on an SM (smem %zu)", smem); return MPC_ECUDA; }
+  long long want = ((long long)A.V + groups - 1) / groups, grid = (long long)h->sm_count * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  KParams kp;
+  fill_kparams(h->cfg, A.V, kp);
+  kp.state = A.state; kp.coeffs = A.coeffs; kp.yaw_lo = A.yaw_lo; kp.yaw_hi = A.yaw_hi;
+  kp.result = A.result; kp.status = const_cast<int *>(A.status); kp.iters = const_cast<int *>(A.iters);
+  kp.handoff_iter = INT_MAX;
+  int rc = ensure_coop_scratch<NS>(h, kp, grid * groups);
+  if (rc) return rc;
+  mpc_rollout_kernel<NS><<<(unsigned)grid, threads, smem, st>>>(kp, h->cfg, A, T);
+  CK(cudaGetLastError());
+  h->launches++;
+  return MPC_OK;
+}
+
+extern "C" int mpc_set_rollout_mode(mpc_handle *h, int mode) {
+  if (!h || mode < MPC_ROLLOUT_AUTO || mode > MPC_ROLLOUT_PERSISTENT) return MPC_EINVAL;
+  h->rollout_mode = mode;
+  return MPC_OK;
+}
+
 extern "C" int mpc_rollout(mpc_handle *h, int V, int T, const double *track_x, const double *track_y, int n_track,
                            double *veh, int *seg, double *pending, double dt_ctrl, double tau_solve, double *rec,
                            void *cuda_stream) {
@@ -1144,6 +1184,19 @@ extern "C" int mpc_rollout(mpc_handle *h, int V, int T, const double *track_x, c
   A.aux = w + 13 * (size_t)V; A.result = w + 17 * (size_t)V;
   int *d_status = h->d_run_i, *d_iters = h->d_run_i + V;
   A.status = d_status; A.iters = d_iters;
+  const bool persistent = h->rollout_mode == MPC_ROLLOUT_PERSISTENT || (h->rollout_mode == MPC_ROLLOUT_AUTO && V <= MPC_ROLLOUT_PERSISTENT_MAX);
+  if (persistent) {
+    A.step = 0;
+    const int N = h->cfg.N;
+    if (N <= 10) return launch_rollout<10>(h, A, T, st);
+#ifndef MPC_DEV_N10
+    if (N <= 20) return launch_rollout<20>(h, A, T, st);
+    if (N <= 32) return launch_rollout<32>(h, A, T, st);
+    return launch_rollout<MPC_NMAX>(h, A, T, st);
+#else
+    return MPC_EINVAL;
+#endif
+  }
   const int thr = 128, grid = (V + thr - 1) / thr;
   for (int k = 0; k < T; k++) {
     A.step = k;

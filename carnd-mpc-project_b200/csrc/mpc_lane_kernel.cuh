@@ -122,6 +122,7 @@ struct Lane {
   int b, N, mode, status, iter, accept_cnt, nfilt, ntrial, soc_cnt;
   // line-search state beyond one iteration (Ipopt's BacktrackingLineSearch / FilterLSAcceptor members)
   int wd_short;                    // watchdog_shortened_iter_: successive iterations that needed backtracking
+  int trips;                       // trips spent on this problem in this kernel (progress guard)
   int n_filter_resets, succ_filter_rej;
   bool last_rej_filter, acceptable_now, escalate, tiny_screen;
   double tiny_tol;                 // KParams::tiny_step_tol
@@ -227,7 +228,7 @@ struct Lane {
     alpha = 0.0; alpha_z = 0.0;
     reset_line_search();
     n_filter_resets = 0; acceptable_now = false; escalate = false; tiny_screen = false; tiny_flag = false;
-    force_accept = false; wd_skip = false; was_tiny = false; wd_trial = 0;
+    force_accept = false; wd_skip = false; was_tiny = false; wd_trial = 0; trips = 0;
     tiny_tol = P.tiny_step_tol;
     mode = LM_EV0;
     gsync();
@@ -1749,7 +1750,7 @@ struct Lane {
     wd_short = (int)n[9]; n_filter_resets = (int)n[10] >> 3; succ_filter_rej = (int)n[10] & 7;
     last_rej_filter = ((int)n[11] & 1) != 0; acceptable_now = ((int)n[11] & 2) != 0;
     escalate = false; tiny_screen = false; tiny_flag = false; tiny_last = false; in_watchdog = false;
-    force_accept = false; wd_skip = false; was_tiny = false; wd_trial = 0;
+    force_accept = false; wd_skip = false; was_tiny = false; wd_trial = 0; trips = 0;
     lh_stale = true;
     gsync();
   }
@@ -2628,7 +2629,7 @@ struct Lane {
           } else {   // the uncorrected direction is back: go on backtracking
             on_soc = false;
             a *= 0.5; nt++;
-            if (a < alpha_min_r) break;
+            if (!(a > alpha_min_r)) break;   // (not `a < alpha_min`: theta_R = 0 gives alpha_min = 0, and a NaN must end the search too)
           }
           need = SOLVE_NONE;
         }
@@ -2647,7 +2648,7 @@ struct Lane {
             need = SOLVE_SOC;
           } else {
             a *= 0.5; nt++;
-            if (a < alpha_min_r) break;
+            if (!(a > alpha_min_r)) break;   // (not `a < alpha_min`: theta_R = 0 gives alpha_min = 0, and a NaN must end the search too)
           }
         } else {
           cnt++;
@@ -2858,7 +2859,7 @@ struct Lane {
             } else {
               alpha *= 0.5;
               ntrial++;
-              if (alpha < alpha_min) line_search_failed();
+              if (!(alpha > alpha_min)) line_search_failed();
             }
           } else {   // rejected SOC trial
             soc_cnt++;
@@ -2905,6 +2906,20 @@ struct Lane {
   __device__ __forceinline__ void line_search_failed() {
     mode = LM_LSFAIL;
     if (!FULL) escalate = true;
+  }
+  // coop kernels: trips until the problem is finished.  Every iteration costs a handful of trips (one in the common
+  // case, a few with inertia correction, second-order corrections or backtracking); a problem that has taken 64 trips
+  // per allowed iteration is not making progress and ends as an internal error instead of holding the device.
+  __device__ __forceinline__ void run_to_completion(const KParams &P) {
+    long long budget = 64LL * (long long)(P.max_iter + 16);
+    while (mode != LM_FINISH) {
+      trip_eval();
+      trip_accept(P);
+      if (mode == LM_FINISH) break;
+      trip_factor();
+      trip_solve(P);
+      if (--budget < 0) { status = 13; mode = LM_FINISH; }
+    }
   }
   // slot 3: factor
   __device__ __forceinline__ void trip_factor() {
@@ -2977,7 +2992,7 @@ struct Lane {
       alpha *= 0.5;
       ntrial++;
       mode = LM_TRIAL;
-      if (alpha < alpha_min) line_search_failed();
+      if (!(alpha > alpha_min)) line_search_failed();
     }
   }
 };
@@ -3086,6 +3101,8 @@ __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KPa
     Z.trip_accept(P);
     Z.trip_factor();
     Z.trip_solve(P);
+    // progress guard (see run_to_completion): a problem that stops making progress must not hold the whole grid
+    if (Z.mode != LM_IDLE && Z.mode != LM_DONE && Z.mode != LM_FINISH && ++Z.trips > 64 * (P.max_iter + 16)) { Z.status = 13; Z.mode = LM_FINISH; }
   }
 }
 
@@ -3118,13 +3135,7 @@ __global__ void __launch_bounds__(128, 2) mpc_coop_kernel(const KParams P) {
     }
     if (nb >= P.B) break;
     Z.init(P, nb);
-    while (Z.mode != LM_FINISH) {
-      Z.trip_eval();
-      Z.trip_accept(P);
-      if (Z.mode == LM_FINISH) break;
-      Z.trip_factor();
-      Z.trip_solve(P);
-    }
+    Z.run_to_completion(P);
     if (Z.g0 == 0) Z.write_outputs(P);
     Z.gsync();
   }
@@ -3168,13 +3179,7 @@ __global__ void __launch_bounds__(128, NS <= 10 ? MPC_COOP_RESUME_MINB : 2) mpc_
       if (k >= cnt) break;
       if (phase == 0) Z.load(rec_in + (size_t)k * Lane<NS, true>::CK_SIZE);
       else Z.init(P, P.restart_list[k]);
-      while (Z.mode != LM_FINISH) {
-        Z.trip_eval();
-        Z.trip_accept(P);
-        if (Z.mode == LM_FINISH) break;
-        Z.trip_factor();
-        Z.trip_solve(P);
-      }
+      Z.run_to_completion(P);
       if (Z.g0 == 0) Z.write_outputs(P);
       Z.gsync();
     }

@@ -8,6 +8,7 @@
 // One thread per vehicle: a 6-point fit of order <= 4 is a few hundred flops.
 #pragma once
 #include <cuda_runtime.h>
+#include "mpc_lane_kernel.cuh"
 #include "mpc_run_logic.h"
 
 namespace mpcb200 {
@@ -67,10 +68,8 @@ struct LoopArgs {
   double *rec;       // [T][8][V] or NULL: cte, epsi, v, steer in [-1,1], throttle, cost, status, iterations
 };
 
-// telemetry -> NLP inputs (mpc_main.cpp:113-169)
-__global__ void __launch_bounds__(128) mpc_loop_pre_kernel(const mpc_config cfg, const LoopArgs A) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.V) return;
+// telemetry -> NLP inputs (mpc_main.cpp:113-169), vehicle b
+__device__ __forceinline__ void loop_pre(const mpc_config &cfg, const LoopArgs &A, int b) {
   const size_t V = (size_t)A.V;
   double x = A.veh[0 * V + b], y = A.veh[1 * V + b], psi = A.veh[2 * V + b], v = A.veh[3 * V + b];
   const double steer = A.veh[4 * V + b], thr = A.veh[5 * V + b];
@@ -101,11 +100,13 @@ __global__ void __launch_bounds__(128) mpc_loop_pre_kernel(const mpc_config cfg,
   A.aux[0 * V + b] = aux.max_yaw_change; A.aux[1 * V + b] = aux.target_speed; A.aux[2 * V + b] = v;
   A.aux[3 * V + b] = (double)aux.fit_order;
 }
-
-// solve result -> actuators -> plant step (mpc_main.cpp:171-214; Vehicle::move as the simulator)
-__global__ void __launch_bounds__(128) mpc_loop_post_kernel(const mpc_config cfg, const LoopArgs A) {
+__global__ void __launch_bounds__(128) mpc_loop_pre_kernel(const mpc_config cfg, const LoopArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= A.V) return;
+  if (b < A.V) loop_pre(cfg, A, b);
+}
+
+// solve result -> actuators -> plant step (mpc_main.cpp:171-214; Vehicle::move as the simulator), vehicle b, step k
+__device__ __forceinline__ void loop_post(const mpc_config &cfg, const LoopArgs &A, int b, int step) {
   const size_t V = (size_t)A.V;
   mpc_run_aux a = {A.aux[0 * V + b], 0.0, A.aux[1 * V + b], 0.0, 0};
   double r[9], o[8];
@@ -125,9 +126,48 @@ __global__ void __launch_bounds__(128) mpc_loop_post_kernel(const mpc_config cfg
   A.veh[0 * V + b] = x; A.veh[1 * V + b] = y; A.veh[2 * V + b] = psi; A.veh[3 * V + b] = v;
   A.veh[4 * V + b] = d_apply; A.veh[5 * V + b] = throttle;
   if (A.rec) {
-    double *q = A.rec + (size_t)A.step * 8 * V + b;
+    double *q = A.rec + (size_t)step * 8 * V + b;
     q[0 * V] = A.state[4 * V + b]; q[1 * V] = A.state[5 * V + b]; q[2 * V] = A.aux[2 * V + b]; q[3 * V] = o[4];
     q[4 * V] = throttle; q[5 * V] = r[8]; q[6 * V] = (double)A.status[b]; q[7 * V] = (double)A.iters[b];
+  }
+}
+__global__ void __launch_bounds__(128) mpc_loop_post_kernel(const mpc_config cfg, const LoopArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < A.V) loop_post(cfg, A, b, A.step);
+}
+
+// The whole closed loop in ONE launch: a lane group owns a vehicle for all T control steps -- message
+// handling and MPC::run's pre-processing by the group's first lane, the solve by the group exactly as in
+// mpc_coop_kernel (same Lane code, so the same bits as the launch-per-step path), actuation and plant step by the
+// first lane again -- then takes the next vehicle.  Vehicles never wait for one another: a control step costs a
+// vehicle its own ~10 trips, not the slowest vehicle's, and there are no launch seams.  The per-vehicle problem
+// slots (state, coeffs, yaw bounds, result) are the same global arrays the launch-per-step path uses.
+template <int NS>
+__global__ void __launch_bounds__(128, 2) mpc_rollout_kernel(const KParams P, const mpc_config cfg, const LoopArgs A, int T) {
+  extern __shared__ double coop_smem[];
+  const int G = Lane<NS, true>::NS_GROUP;
+  const int lane = threadIdx.x & 31;
+  Lane<NS, true> Z;
+  Z.g0 = lane % G; Z.gstep = G;
+  Z.gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - Z.g0));
+  Z.ST = reinterpret_cast<double (*)[ST_ROW_SH]>(coop_smem + (size_t)(threadIdx.x / G) * NS * ST_ROW_SH);
+  Z.lh_stale = false; Z.no_handoff = true;
+  const int group = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G), n_groups = (int)(gridDim.x * blockDim.x / G);
+  Z.scratch = P.scratch + (size_t)group * P.scratch_stride;
+  for (int b = group; b < A.V; b += n_groups) {
+#pragma unroll 1
+    for (int k = 0; k < T; k++) {
+      if (Z.g0 == 0) loop_pre(cfg, A, b);
+      Z.gsync();
+      Z.init(P, b);
+      Z.run_to_completion(P);
+      if (Z.g0 == 0) {
+        Z.write_outputs(P);
+        __threadfence_block();
+        loop_post(cfg, A, b, k);
+      }
+      Z.gsync();
+    }
   }
 }
 

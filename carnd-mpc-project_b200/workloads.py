@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_DATA = os.path.join(os.path.dirname(_HERE), "tests", "golden", "reference_data.json")
+_DATA = os.path.join(_HERE, "data", "reference_data.json")   # config-*.json knob sets, lake-track waypoints, test.cpp fixtures
 NCOEF = 5
 
 

@@ -297,10 +297,18 @@ int mpc_run_batch(mpc_handle *h, int B, const double *pose, const double *steeri
  *   track_x, track_y [n_track] closed centre line;  veh [6][V] in/out: x, y, psi, v, steering angle [rad],
  *   last throttle;  seg [V] in/out: first waypoint of the window;  pending [2][V] in/out: command in flight
  *   (delta, throttle), required when cfg.latency_ms != 0;  rec [T][8][V] or NULL: per step cte, epsi, v,
- *   steer in [-1,1], throttle, cost, status, iterations.  DEVICE pointers; async on cuda_stream. */
+ *   steer in [-1,1], throttle, cost, status, iterations.   DEVICE pointers; async on cuda_stream.
+ * Up to MPC_ROLLOUT_PERSISTENT_MAX vehicles run as ONE launch (a lane group owns a vehicle for all T steps and
+ * vehicles never wait for one another); larger fleets as three launches per control step around the throughput
+ * kernel.  Same arithmetic, same bits either way (mpc_set_rollout_mode forces one or the other). */
 int mpc_rollout(mpc_handle *h, int V, int T, const double *track_x, const double *track_y, int n_track,
                 double *veh, int *seg, double *pending, double dt_ctrl, double tau_solve, double *rec,
                 void *cuda_stream);
+#define MPC_ROLLOUT_AUTO 0
+#define MPC_ROLLOUT_PER_STEP 1
+#define MPC_ROLLOUT_PERSISTENT 2
+#define MPC_ROLLOUT_PERSISTENT_MAX 16384
+int mpc_set_rollout_mode(mpc_handle *h, int mode);
 
 /* Measure the device's FP64 FMA peak with a dependent-chain-free DFMA micro-kernel (8 independent
  * chains per thread, every SM full): the roofline denominator bench.py reports against, since

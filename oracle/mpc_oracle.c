@@ -1012,7 +1012,7 @@ static int restoration(ipm_t *s, ls_t *LSo, double mu_o, double tau_o, int *iter
       alpha *= ALPHA_RED;
       ntrial++;
       out->n_backtrack++;
-      if (alpha < alpha_min) break;
+      if (!(alpha > alpha_min)) break;   /* theta_R = 0 gives alpha_min = 0: `alpha < alpha_min` would never end */
     }
     if (!accepted) { status = ORC_RESTORATION_FAILURE; break; }   /* no restoration inside the restoration */
     if (!is_ftype(&LS, alpha_test) || !armijo(&LS, alpha_test, phi_acc)) filter_augment(&LS);

@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def refdata():
-    with open(os.path.join(ROOT, "tests", "golden", "reference_data.json")) as f:
+    with open(os.path.join(ROOT, "carnd-mpc-project_b200", "data", "reference_data.json")) as f:
         return json.load(f)
 
 

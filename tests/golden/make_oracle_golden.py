@@ -9,10 +9,11 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import pyoracle as po  # noqa: E402
 
-rd = json.load(open(os.path.join(HERE, "reference_data.json")))
+rd = json.load(open(os.path.join(ROOT, "carnd-mpc-project_b200", "data", "reference_data.json")))
 cd = po.load_config_dict(rd["configs"]["stable"])
 cfg = po.make_config(cd)
 out = {"config": "stable", "scenarios": []}

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 from oracle import pyoracle as po, pyref as pr  # noqa: E402
 import mpc_b200 as mpc  # noqa: E402  (workload generator only)
 
-rd = json.load(open(os.path.join(HERE, "reference_data.json")))
+rd = json.load(open(os.path.join(ROOT, "carnd-mpc-project_b200", "data", "reference_data.json")))
 wx, wy = np.array(rd["waypoints"]["x"]), np.array(rd["waypoints"]["y"])
 out = {"generator": "tests/golden/make_ref_golden.py (oracle/_ref/libmpc_ref.so)", "testcpp": [], "run": [],
        "weights": [], "grid": []}

@@ -1,4 +1,4 @@
-"""Regenerates tests/golden/reference_data.json from the read-only reference checkout.
+"""Regenerates carnd-mpc-project_b200/data/reference_data.json from the read-only reference checkout.
 
 Run in the build container only (/root/reference does not exist on the GPU box):
     python tests/golden/make_reference_data.py
@@ -10,7 +10,7 @@ import json
 import os
 
 REF = "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_data.json")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "carnd-mpc-project_b200", "data", "reference_data.json")
 
 data = {"configs": {}, "waypoints": {"x": [], "y": []}, "test_cpp_fixtures": []}
 for name in ("stable", "fast", "no-latency"):

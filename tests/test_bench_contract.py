@@ -27,7 +27,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and "sample" in d["config"]["workload"]
+    # the reference arm runs without the product: no CUDA library of this repository in the process
+    assert all("mpc_b200" not in x for x in d["loaded_repo_libraries"]), d["loaded_repo_libraries"]
+    assert any(x.startswith("oracle") for x in d["loaded_repo_libraries"])
 
 
 def test_reference_arm_other_ranks_do_no_work():

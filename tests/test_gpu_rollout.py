@@ -104,6 +104,7 @@ def test_big_fleet_rollout_uses_the_lane_chain_and_agrees_with_the_coop_kernel(m
     for kind in (mpc.KERNEL_COOP, mpc.KERNEL_AUTO):
         S = mpc.Solver(cfg, 0)
         S.set_kernel(kind)
+        S.set_rollout_mode(1)     # three launches per control step (fleets this size default to the persistent kernel)
         veh = _dev(np.stack([b["px"], b["py"], b["psi"], np.clip(b["v"], 8, 30), np.zeros(V), np.zeros(V)]))
         seg = _dev(b["segment"].astype(np.int32))
         pending = torch.zeros(2, V, dtype=torch.float64, device="cuda")
@@ -118,6 +119,108 @@ def test_big_fleet_rollout_uses_the_lane_chain_and_agrees_with_the_coop_kernel(m
     for a, c in zip(recs[mpc.KERNEL_COOP], recs[mpc.KERNEL_AUTO]):
         assert torch.equal(a, c)
     assert (recs[mpc.KERNEL_AUTO][0][:, 6] == 1).float().mean().item() > 0.99
+
+
+def _rollout(mpc, cfg, b, V, T, wx, wy, tau, mode):
+    import torch
+    veh = _dev(np.stack([b["px"][:V], b["py"][:V], b["psi"][:V], np.clip(b["v"][:V], 8, 30), np.zeros(V), np.zeros(V)]))
+    seg = _dev(b["segment"][:V].astype(np.int32))
+    pending = torch.zeros(2, V, dtype=torch.float64, device="cuda")
+    rec = torch.zeros(T, 8, V, dtype=torch.float64, device="cuda")
+    S = mpc.Solver(cfg, 0)
+    S.set_rollout_mode(mode)
+    n0 = S.launches
+    S.rollout_device(V, T, _dev(wx), _dev(wy), veh, seg, pending, 0.1, tau, rec)
+    torch.cuda.synchronize()
+    launches = S.launches - n0
+    S.close()
+    return rec, veh, seg, launches
+
+
+@pytest.mark.parametrize("name,tau,V,T", [("fast", 0.02, 300, 40), ("stable", 0.0, 37, 25), ("fast", 0.02, 5000, 6)])
+def test_persistent_rollout_kernel_is_one_launch_and_the_same_bits(mpc, refdata, name, tau, V, T):
+    """The closed loop as ONE launch (a lane group owns a vehicle for all T steps) against three launches per control
+    step: the same Lane code runs the solve, so the records, the final vehicle states and the waypoint windows are
+    bit-identical -- also with more vehicles than resident lane groups (several vehicles per group in turn)."""
+    import torch
+    cfg = mpc.config_from_json_text(json.dumps(refdata["configs"][name]))
+    wx, wy = np.array(refdata["waypoints"]["x"]), np.array(refdata["waypoints"]["y"])
+    b = mpc.workloads.batch_perturbed_states(V, 3, cfg.as_dict())
+    per_step = _rollout(mpc, cfg, b, V, T, wx, wy, tau, 1)
+    one = _rollout(mpc, cfg, b, V, T, wx, wy, tau, 2)
+    auto = _rollout(mpc, cfg, b, V, T, wx, wy, tau, 0)
+    assert per_step[3] == 3 * T and one[3] == 1 and auto[3] == 1
+    for a, c, d in zip(per_step[:3], one[:3], auto[:3]):
+        assert torch.equal(a, c) and torch.equal(a, d)
+    assert (one[0][:, 6] == 1).float().mean().item() > 0.99
+
+
+def test_closed_loop_against_the_reference_sources(mpc, refdata):
+    """tests/golden/ref_closed_loop.json: closed loops in which MPC::run, the plant (Vehicle::move) and the throttle map
+    (Vehicle::computeThrottle) are the reference's own compiled code (tests/golden/make_ref_closed_loop.py); 80-150
+    control steps per vehicle, all three shipped configs.  The persistent kernel reproduces them step by step."""
+    import torch
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_closed_loop.json")))
+    wx, wy = np.array(refdata["waypoints"]["x"]), np.array(refdata["waypoints"]["y"])
+    for name in refdata["configs"]:
+        cases = [c for c in gold["cases"] if c["config"] == name]
+        assert cases
+        cfg = mpc.config_from_json_text(json.dumps(refdata["configs"][name]))
+        V, T, tau = len(cases), cases[0]["T"], cases[0]["tau"]
+        veh = _dev(np.array([c["veh0"] for c in cases]).T)
+        seg = _dev(np.array([c["seg0"] for c in cases], dtype=np.int32))
+        pending = torch.zeros(2, V, dtype=torch.float64, device="cuda")
+        rec = torch.zeros(T, 8, V, dtype=torch.float64, device="cuda")
+        S = mpc.Solver(cfg, 0)
+        S.rollout_device(V, T, _dev(wx), _dev(wy), veh, seg, pending, cases[0]["dt_ctrl"], tau, rec)
+        torch.cuda.synchronize()
+        S.close()
+        rec, veh, seg = rec.cpu().numpy(), veh.cpu().numpy(), seg.cpu().numpy()
+        for i, c in enumerate(cases):
+            ref = np.array(c["rec"])
+            assert np.array_equal(rec[:, 6, i], ref[:, 6]) and (ref[:, 6] == 1).all()        # status, every step
+            assert np.abs(rec[:, :5, i] - ref[:, :5]).max() < ABS_TOL                         # cte, epsi, v, steer, throttle
+            assert np.abs(veh[:, i] - np.array(c["veh"])).max() < ABS_TOL
+            assert seg[i] == c["seg"]
+
+
+def test_thousand_step_rollout_spot_check(mpc, po, refdata):
+    """BASELINE config 5 is 1000 control steps per vehicle: 64 vehicles x 1000 steps of config-fast on the persistent
+    kernel against the CPU restatement of the loop (oracle solve + the reference's plant formulas), step by step."""
+    import concurrent.futures as cf
+    import torch
+    js = refdata["configs"]["fast"]
+    cfg = mpc.config_from_json_text(json.dumps(js))
+    cd = po.load_config_dict(js)
+    wx, wy = np.array(refdata["waypoints"]["x"]), np.array(refdata["waypoints"]["y"])
+    V, T, tau = 64, 1000, 0.02
+    b = mpc.workloads.batch_perturbed_states(V, 3, cd)
+    rec, veh, seg, launches = _rollout(mpc, cfg, b, V, T, wx, wy, tau, 0)
+    assert launches == 1
+    rec, veh, seg = rec.cpu().numpy(), veh.cpu().numpy(), seg.cpu().numpy()
+    veh0 = np.stack([b["px"], b["py"], b["psi"], np.clip(b["v"], 8, 30), np.zeros(V), np.zeros(V)])
+    seg0 = b["segment"].astype(np.int32)
+    assert (rec[:, 6] == 1).mean() > 0.995
+    po.lib()
+
+    def one(i):
+        return clr.rollout(po, cd, wx, wy, list(veh0[:, i]), int(seg0[i]), (0.0, 0.0), T, 0.1, tau)
+
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:      # the oracle's C code releases the GIL
+        refs = list(ex.map(one, range(V)))
+    worst = 0.0
+    n_same = 0
+    for i, (r_ref, v_ref, s_ref, _) in enumerate(refs):
+        # a closed loop integrates: compare up to the first step (if any) where the two solvers' statuses differ
+        same = rec[:, 6, i] == r_ref[:, 6]
+        upto = T if same.all() else int(np.argmin(same))
+        n_same += upto == T
+        if upto:
+            worst = max(worst, np.abs(rec[:upto, :5, i] - r_ref[:upto, :5]).max())
+        if upto == T:
+            assert np.abs(veh[:, i] - np.array(v_ref)).max() < 1e-3 and seg[i] == s_ref
+    assert n_same >= V - 2, n_same
+    assert worst < 1e-3, worst
 
 
 def test_telemetry_replay_matches_restated_handler(mpc, po, refdata):
