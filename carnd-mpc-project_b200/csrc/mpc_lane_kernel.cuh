@@ -2817,8 +2817,11 @@ struct Lane {
       lsq = true; err = true;
     } else if (m1 == LM_LSQ_ZERO) {
       zero = true; err = true;
-    } else if (FULL && m1 == LM_LSFAIL) {
-      restoration(P);
+    } else if (m1 == LM_LSFAIL) {
+      // A one-problem-per-lane kernel meets this mode only in a record it has just loaded (a resume launch reading a
+      // problem that an earlier launch handed over): hand it on.  Without this the lane would idle on it, and a warp
+      // holding more than park_lanes such records would never be sparse enough for rule 2 to park them.
+      if (FULL) restoration(P); else escalate = true;
     } else if (m1 == LM_TRIAL || m1 == LM_SOC_TRIAL) {
       const double phi_t = fma(-mu, lt, ft);
       // the step size the switching condition and the Armijo test are made with: this trial's, or -- while the

@@ -115,7 +115,16 @@ def test_watchdog_tiny_step_and_filter_reset_branches(mpc, po, refdata, knobs, c
     f = c[counter][stable] > 0
     assert f.sum() >= 1
     assert d[f][:, :8].max() < 1e-6
-    assert (g["iters"][stable][f] == c["iters"][stable][f]).mean() >= 0.5
+    # Iteration counts: the same, or one more on the GPU.  At N = 30 about 5 % of the problems of this batch -- with or
+    # without the forced option -- take exactly one more iteration than the oracle and end at the same point to 1e-11:
+    # at the last barrier parameter the Riccati recursion leaves a slightly larger rounding residue in the new
+    # multipliers than the oracle's pivoted dense LDL^T, so Ipopt's 1e-8 test on the scaled dual infeasibility is
+    # sometimes met an iteration later (never earlier).  The branch under test shows in the counts themselves: a
+    # problem that took the watchdog path in the oracle but not on the GPU would differ by tens of iterations.
+    di = g["iters"][stable][f].astype(int) - c["iters"][stable][f].astype(int)
+    assert di.min() >= 0 and di.max() <= 1, di
+    da = g["iters"][stable].astype(int) - c["iters"][stable].astype(int)
+    assert (da == 0).mean() > 0.85, np.unique(da, return_counts=True)
 
 
 def test_default_watchdog_fires_and_matches(mpc, po, refdata):
@@ -181,3 +190,28 @@ def test_recovered_points_carry_a_kkt_certificate(mpc, po, refdata):
     cl = np.where(bl, zl * (z - xl), 0.0).max(axis=1)
     cu = np.where(bu, zu * (xu - z), 0.0).max(axis=1)
     assert max(cl.max(), cu.max()) < 1e-4
+
+
+def test_resume_launches_hand_on_the_problems_they_cannot_finish(mpc, po, refdata):
+    """More than 8192 parked records make the chain's resume launches run (smaller batches leave them to the final
+    launch).  A record of a problem whose line search has failed can only be continued by the coop kernel: a resume
+    launch must hand it on, also when a whole warp holds nothing else (found on the 256K horizon grid: such warps never
+    became sparse enough to be parked and their problems ended as internal errors after idling the grid)."""
+    js = dict(refdata["configs"]["stable"], N=30, dt=0.1)
+    cd = po.load_config_dict(js)
+    b = mpc.workloads.batch_perturbed_states(2500, 1, cd)
+    args = [b["state"], b["coeffs"], b["yaw_lo"], b["yaw_hi"]]
+    S = mpc.Solver(_gpu_cfg(mpc, js), 0)
+    S.set_kernel(mpc.KERNEL_COOP)
+    ref = S.solve_batch_host(*args)
+    hard = np.nonzero(ref["iters"] > 40)[0]          # the ones that go through the restoration phase
+    assert len(hard) >= 100
+    idx = np.tile(hard, 12000 // len(hard) + 1)[:12000]
+    S.set_kernel(mpc.KERNEL_LANE)
+    g = S.solve_batch_host(*[a[idx] for a in args])
+    parked = S.tail_counts(5)
+    S.close()
+    assert parked[0] > 8192, parked                    # the main launch handed over enough to make a resume launch run
+    assert np.array_equal(g["status"], ref["status"][idx])
+    assert np.array_equal(g["iters"], ref["iters"][idx])
+    assert np.array_equal(g["result"], ref["result"][idx])
