@@ -488,6 +488,18 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
     if (threads > 256) threads = 256;
   }
   if (threads > MPC_LANE_MAXT) threads = MPC_LANE_MAXT;
+  // hybrid rows (experiment): some columns of the rows in shared memory, laid out for CTAs of at most MPC_LANE_SM_STRIDE threads
+  const bool hybrid = MPC_LANE_HYBRID(NS);
+  const size_t lane_smem = hybrid ? (size_t)NS * MPC_LANE_SM_NC * MPC_LANE_SM_STRIDE * sizeof(double) : 0;
+  if (hybrid) {
+    if (threads > MPC_LANE_SM_STRIDE) threads = MPC_LANE_SM_STRIDE;
+    static thread_local int cached_dev_h = -1;
+    if (cached_dev_h != h->device) {
+      CK(cudaFuncSetAttribute(mpc_lane_kernel<NS, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+      CK(cudaFuncSetAttribute(mpc_lane_kernel<NS, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+      cached_dev_h = h->device;
+    }
+  }
   long long want = ((long long)kp.B + threads - 1) / threads;
   long long grid = (long long)h->sm_count * (h->lane_ctas_per_sm > 0 ? h->lane_ctas_per_sm : 1);
   if (grid > want) grid = want;
@@ -527,7 +539,7 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   }
   if (!h->d_ckpt) {
     // no record buffers at all: one launch, hand-overs go through the restart list
-    mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
+    mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, lane_smem, st>>>(kp);
     CK(cudaGetLastError());
     h->launches++;
     h->pre_recorded = false;
@@ -540,13 +552,14 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   kp.park_lanes = park; kp.handoff_iter = rule1 ? h->handoff_iter : INT_MAX;
   kp.chain_counts = cnt; kp.chain_buf0 = buf[0]; kp.chain_buf1 = buf[1];
   kp.chain_pos = 0; kp.chain_last = phases + 1; kp.resume_min = h->resume_min;
-  mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, 0, st>>>(kp);
+  mpc_lane_kernel<NS, MINB, false><<<(unsigned)grid, threads, lane_smem, st>>>(kp);
   CK(cudaGetLastError());
   h->launches++;
   // resume launches: enough lanes for a full buffer in one pass, dealt over all SMs.  Each works out on the device
   // which buffer holds the live records (chain_resolve) and returns at once if there are too few to be worth a pass.
   int rthreads = (int)(((cap + h->sm_count - 1) / h->sm_count + 31) / 32) * 32;
   if (rthreads > MPC_LANE_MAXT) rthreads = MPC_LANE_MAXT;
+  if (hybrid && rthreads > MPC_LANE_SM_STRIDE) rthreads = MPC_LANE_SM_STRIDE;
   long long rgrid = ((long long)cap + rthreads - 1) / rthreads;
   if (rgrid > (long long)h->sm_count * MPC_LANE_MINB) rgrid = (long long)h->sm_count * MPC_LANE_MINB;
   kp.handoff_iter = INT_MAX;
@@ -554,7 +567,7 @@ static int launch_lane(mpc_handle *h, KParams &kp, cudaStream_t st) {
   kp.ckpt = nullptr; kp.ckpt_count = nullptr;
   for (int k = 1; k <= phases; k++) {
     kp.chain_pos = k;
-    mpc_lane_kernel<NS, MINB, true><<<(unsigned)rgrid, rthreads, 0, st>>>(kp);
+    mpc_lane_kernel<NS, MINB, true><<<(unsigned)rgrid, rthreads, lane_smem, st>>>(kp);
     CK(cudaGetLastError());
     h->launches++;
   }

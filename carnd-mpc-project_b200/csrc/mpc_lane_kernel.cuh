@@ -85,6 +85,37 @@ enum { ST_S = 0,      // iterate: x, y, psi, v, cte, epsi
        ST_LH = 76,    // coop kernel only: StageLin (10) + StageHess (18) of the stage, built one stage per lane
        ST_ROW_SH = 106 };   // shared-memory rows: 104 used; 106 keeps neighbouring lanes' rows 2-way bank-conflict free
 template <int NS, bool SH, bool PAR> struct LaneRows { typedef double type[NS][ST_ROW]; enum { ROW = ST_ROW }; };
+// Experiment (profiles/r02_lane_rows_in_shared_memory.txt): some columns of the lane kernel's thread-private rows in
+// shared memory instead.  Two column ranges [A0, A1) and [B0, B1) (compile-time, -DMPC_LANE_SM_A0=.. etc.) map to NC slots;
+// slot k of stage i of thread t is at sm[(i * NC + k) * STRIDE + t] -- consecutive lanes, consecutive words, no bank
+// conflicts.  Column indices are compile-time constants after unrolling, so the choice costs no instruction.
+#ifndef MPC_LANE_SM_A0
+#define MPC_LANE_SM_A0 0
+#define MPC_LANE_SM_A1 0
+#define MPC_LANE_SM_B0 0
+#define MPC_LANE_SM_B1 0
+#endif
+#define MPC_LANE_SM_NC ((MPC_LANE_SM_A1 - MPC_LANE_SM_A0) + (MPC_LANE_SM_B1 - MPC_LANE_SM_B0))
+#define MPC_LANE_SM_STRIDE 224   /* threads per CTA of the lane kernel when the rows are hybrid */
+#define MPC_LANE_HYBRID(NS) (MPC_LANE_SM_NC > 0 && (NS) <= 10)
+template <int NS> struct HybridRows {
+  alignas(16) double loc[NS][ST_ROW];
+  double *sm;
+  struct Row {
+    double *l, *s;
+    __device__ __forceinline__ double &operator[](int c) const {
+      if (c >= MPC_LANE_SM_A0 && c < MPC_LANE_SM_A1) return s[(c - MPC_LANE_SM_A0) * MPC_LANE_SM_STRIDE];
+      if (c >= MPC_LANE_SM_B0 && c < MPC_LANE_SM_B1) return s[(c - MPC_LANE_SM_B0 + (MPC_LANE_SM_A1 - MPC_LANE_SM_A0)) * MPC_LANE_SM_STRIDE];
+      return l[c];
+    }
+  };
+  __device__ __forceinline__ Row operator[](int i) const {
+    return Row{const_cast<double *>(loc[i]), sm + (size_t)i * (MPC_LANE_SM_NC * MPC_LANE_SM_STRIDE)};
+  }
+};
+#if MPC_LANE_SM_NC > 0
+template <> struct LaneRows<10, false, false> { typedef HybridRows<10> type; enum { ROW = ST_ROW }; };
+#endif
 template <int NS> struct LaneRows<NS, true, true> { typedef double (*type)[ST_ROW_SH]; enum { ROW = ST_ROW_SH }; };
 template <int NS> struct LaneRows<NS, true, false> { typedef double (*type)[ST_ROW]; enum { ROW = ST_ROW }; };
 
@@ -3036,6 +3067,8 @@ __device__ __forceinline__ ChainIO chain_resolve(const KParams &P) {
 // RESUME = true is the same kernel started from the records of the previous launch instead of fresh problems,
 // 32 consecutive records to a warp, warps dealt round-robin to the CTAs -- so the survivors of many sparse
 // warps run in a few full ones.  The last launch of a chain parks nothing (P.ckpt == NULL).
+template <int NS> __device__ __forceinline__ void lane_rows_attach(HybridRows<NS> &r, double *sm) { r.sm = sm; }
+template <class T> __device__ __forceinline__ void lane_rows_attach(T &, double *) {}
 #ifndef MPC_LANE_MAXT
 #define MPC_LANE_MAXT 256   // largest CTA the lane kernel is compiled for (register cap = 65536 / (MAXT * MINB)): experiments only
 #endif
@@ -3046,6 +3079,10 @@ __global__ void __maxnreg__(MPC_LANE_MAXNREG) mpc_lane_kernel(const KParams P) {
 __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KParams P) {
 #endif
   Lane<NS, false> Z;
+#if MPC_LANE_SM_NC > 0
+  extern __shared__ double lane_smem[];
+  if (MPC_LANE_HYBRID(NS)) lane_rows_attach(Z.ST, lane_smem + threadIdx.x);
+#endif
   Z.mode = LM_IDLE;
   Z.b = 0;
   Z.g0 = 0; Z.gstep = 1; Z.gm = 0xffffffffu;

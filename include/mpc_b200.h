@@ -307,7 +307,7 @@ int mpc_rollout(mpc_handle *h, int V, int T, const double *track_x, const double
 #define MPC_ROLLOUT_AUTO 0
 #define MPC_ROLLOUT_PER_STEP 1
 #define MPC_ROLLOUT_PERSISTENT 2
-#define MPC_ROLLOUT_PERSISTENT_MAX 16384
+#define MPC_ROLLOUT_PERSISTENT_MAX 4096
 int mpc_set_rollout_mode(mpc_handle *h, int mode);
 
 /* Measure the device's FP64 FMA peak with a dependent-chain-free DFMA micro-kernel (8 independent
