@@ -1284,3 +1284,13 @@ extern "C" int mpc_tail_counts(mpc_handle *h, int *parked, int n) {
 extern "C" long long mpc_launch_count(const mpc_handle *h) { return h ? h->launches : 0; }
 extern "C" const char *mpc_last_error(void) { return g_err; }
 extern "C" const char *mpc_version(void) { return "mpc_b200 0.3 (sm_100a, fp64 interior point with restoration phase and watchdog; lane and coop kernels, explicit fma)"; }
+
+#ifdef MPC_DEBUG_TIMES
+// development builds only: per-warp "out of work" and exit times of the last main launch (tools/gpu_cta_times.py)
+extern "C" int mpc_debug_times(unsigned long long *out, int n, int reset) {
+  const int m = 4 + 148 * 9 * 2;
+  if (out && n >= m) CK(cudaMemcpyFromSymbol(out, mpcb200::g_dbg_times, m * sizeof(unsigned long long)));
+  if (reset) { static unsigned long long z[4 + 148 * 9 * 2]; CK(cudaMemcpyToSymbol(mpcb200::g_dbg_times, z, sizeof(z))); }
+  return MPC_OK;
+}
+#endif

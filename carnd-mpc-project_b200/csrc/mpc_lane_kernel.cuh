@@ -3067,6 +3067,11 @@ __device__ __forceinline__ ChainIO chain_resolve(const KParams &P) {
 // RESUME = true is the same kernel started from the records of the previous launch instead of fresh problems,
 // 32 consecutive records to a warp, warps dealt round-robin to the CTAs -- so the survivors of many sparse
 // warps run in a few full ones.  The last launch of a chain parks nothing (P.ckpt == NULL).
+#ifdef MPC_DEBUG_TIMES
+// development aid (tools/gpu_cta_times.py): when does each warp of the main launch run out of work, when does its CTA exit
+__device__ unsigned long long g_dbg_times[4 + 148 * 9 * 2];
+__device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 template <int NS> __device__ __forceinline__ void lane_rows_attach(HybridRows<NS> &r, double *sm) { r.sm = sm; }
 template <class T> __device__ __forceinline__ void lane_rows_attach(T &, double *) {}
 #ifndef MPC_LANE_MAXT
@@ -3082,6 +3087,9 @@ __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KPa
 #if MPC_LANE_SM_NC > 0
   extern __shared__ double lane_smem[];
   if (MPC_LANE_HYBRID(NS)) lane_rows_attach(Z.ST, lane_smem + threadIdx.x);
+#endif
+#ifdef MPC_DEBUG_TIMES
+  if (!RESUME && threadIdx.x == 0) { if (blockIdx.x == 0) g_dbg_times[0] = dbg_now(); }
 #endif
   Z.mode = LM_IDLE;
   Z.b = 0;
@@ -3136,6 +3144,13 @@ __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KPa
         }
       }
     }
+#ifdef MPC_DEBUG_TIMES
+    if (!RESUME) {
+      const bool wdone = __all_sync(0xffffffffu, Z.mode == LM_DONE);
+      const int w = blockIdx.x * 9 + (threadIdx.x >> 5);
+      if (wdone && (threadIdx.x & 31) == 0 && g_dbg_times[4 + 2 * w] == 0) g_dbg_times[4 + 2 * w] = dbg_now();
+    }
+#endif
     if (__syncthreads_and(Z.mode == LM_DONE)) break;
     Z.trip_eval();
     Z.trip_accept(P);
@@ -3144,6 +3159,9 @@ __global__ void __launch_bounds__(MPC_LANE_MAXT, MINB) mpc_lane_kernel(const KPa
     // progress guard (see run_to_completion): a problem that stops making progress must not hold the whole grid
     if (Z.mode != LM_IDLE && Z.mode != LM_DONE && Z.mode != LM_FINISH && ++Z.trips > 64 * (P.max_iter + 16)) { Z.status = 13; Z.mode = LM_FINISH; }
   }
+#ifdef MPC_DEBUG_TIMES
+  if (!RESUME && (threadIdx.x & 31) == 0) g_dbg_times[4 + 2 * (blockIdx.x * 9 + (threadIdx.x >> 5)) + 1] = dbg_now();
+#endif
 }
 
 // The same solver with one problem per GROUP of 16 (N <= 16) or 32 lanes and the per-stage rows in shared
