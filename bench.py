@@ -570,6 +570,9 @@ def run_batch64k(ctx, args):
         flush_ms = e0.elapsed_time(e1) / 8
         region_ms = ev_all[0].elapsed_time(ev_all[1]) - flush_ms * args.steps
         ms_per_step = ctx.max_over_ranks(region_ms) / args.steps
+        per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+        ctx.dist.all_gather_into_tensor(per_rank, torch.tensor([sum(step_ms) / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(x) for x in per_rank.cpu().numpy()]
     else:
         ms_per_step = sum(step_ms) / args.steps
     value = B * world / (ms_per_step * 1e-3)
@@ -692,6 +695,10 @@ def run_batch64k(ctx, args):
         "host": {"cpu": cpu_model(), "logical_cpus": os.cpu_count()},
         "status_ok_frac": float((st == 1).mean()), "status_hist": status_hist(st),
     }
+    if world > 1:
+        # rank r solves the seed-r batch: the ranks' own solve times differ with their longest-running problem; the job
+        # runs at the pace of the slowest
+        line["per_rank_solve_ms"] = per_rank_ms
     if strong:
         line["strong_scaling"] = strong
     if world == 1 and not args.no_latency:
@@ -725,7 +732,9 @@ def run_batch64k(ctx, args):
         line["cpu_baseline"] = {"value": sample / t, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "first %d problems of the same batch, one solve per host thread (%d threads), %.1f s; CPU restatement "
                                           "oracle/mpc_oracle.c (dense LDL^T), not Ipopt+CppAD+MUMPS" % (sample, cores, t),
-                                "max_abs_diff_vs_gpu": dmax, "status_equal": bool(np.array_equal(st[:sample], out["status"]))}
+                                "max_abs_diff_vs_gpu": dmax, "status_equal": bool(np.array_equal(st[:sample], out["status"])),
+                                "iters_equal_frac": float((it[:sample] == out["iters"]).mean()),
+                                "iters_diff_hist_gpu_minus_cpu": {str(int(k)): int(c) for k, c in zip(*np.unique(it[:sample].astype(np.int64) - out["iters"].astype(np.int64), return_counts=True))}}
     S.close()
     return line
 

@@ -17,7 +17,7 @@ if 'crossover' in sys.argv:
         ins = [up(b['state'].T), up(b['coeffs'].T), up(b['yaw_lo']), up(b['yaw_hi'])]
         outs = [torch.zeros(9, B, dtype=torch.float64, device=dev), None, None, None, torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)]
         line = 'B=%6d ' % B
-        for kind, nm in ((mpc.KERNEL_WARP, 'warp'), (mpc.KERNEL_LANE, 'lane'), (mpc.KERNEL_COOP, 'coop')):
+        for kind, nm in ((mpc.KERNEL_LANE, 'lane'), (mpc.KERNEL_COOP, 'coop')):
             S.set_kernel(kind)
             best = 1e9
             for _ in range(4):
