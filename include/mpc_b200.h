@@ -104,7 +104,11 @@ int mpc_config_from_cli(int argc, const char *const *argv, const char *config_di
                         char *config_file_out, int config_file_cap);
 
 /* Create a solver bound to CUDA device `device` (workspace, stream-ordered work queue counter).
- * Replaces `MPC::MPC()` (MPC.cpp:160-179): the Ipopt option string becomes max_iter / tol. */
+ * Replaces `MPC::MPC()` (MPC.cpp:160-179): the Ipopt option string becomes max_iter / tol.
+ * Concurrency: handles are independent (no global mutable state; any number of handles, threads and devices), but ONE
+ * call may be in flight per handle -- the launches of a solve share the handle's work queue, record buffers and scratch.
+ * mpc_solve_batch is asynchronous on the caller's stream: issue the next call on the same handle to the same stream
+ * (ordered after it), or use a second handle. */
 int mpc_create(const mpc_config *cfg, int device, mpc_handle **out);
 void mpc_destroy(mpc_handle *h);
 /* replace the configuration of an existing handle (Config::load on a live controller) */

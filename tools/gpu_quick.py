@@ -1,4 +1,4 @@
-"""Quick iteration check: lane kernel vs warp kernel on 2048 problems (parity proxy), then timings."""
+"""Quick iteration check: lane kernel chain vs coop kernel on 2048 problems (must be bit-identical), then timings and the crossover."""
 import json, sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,10 +9,8 @@ cd = cfg.as_dict()
 S = mpc.Solver(cfg, 0)
 b = mpc.workloads.batch_perturbed_states(2048, 3, cd)
 S.set_kernel(mpc.KERNEL_LANE); g = S.solve_batch_host(b['state'], b['coeffs'], b['yaw_lo'], b['yaw_hi'])
-S.set_kernel(mpc.KERNEL_WARP); w = S.solve_batch_host(b['state'], b['coeffs'], b['yaw_lo'], b['yaw_hi'])
 S.set_kernel(mpc.KERNEL_COOP); c = S.solve_batch_host(b['state'], b['coeffs'], b['yaw_lo'], b['yaw_hi'])
 print('coop vs lane: max diff %.3g  iters equal %.4f  status ok %.4f' % (np.abs(g['result'] - c['result']).max(), (g['iters'] == c['iters']).mean(), (c['status'] == 1).mean()))
-print('lane vs warp: max diff %.3g  iters equal %.4f  status ok %.4f' % (np.abs(g['result'] - w['result']).max(), (g['iters'] == w['iters']).mean(), (g['status'] == 1).mean()))
 dev = torch.device('cuda:0')
 S.set_kernel(mpc.KERNEL_LANE)
 for B in [int(x) for x in (sys.argv[1:] or ['4096', '65536', '1048576'])]:
@@ -33,7 +31,7 @@ for B in (1, 256, 1024, 2048, 4096, 8192, 16384):
     ins = [up(b['state']), up(b['coeffs']), up(b['yaw_lo']), up(b['yaw_hi'])]
     outs = [torch.zeros(9, B, dtype=torch.float64, device=dev), None, None, None, torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)]
     line = 'B=%6d ' % B
-    for kind, nm in ((mpc.KERNEL_WARP, 'warp'), (mpc.KERNEL_LANE, 'lane'), (mpc.KERNEL_COOP, 'coop')):
+    for kind, nm in ((mpc.KERNEL_LANE, 'lane'), (mpc.KERNEL_COOP, 'coop')):
         S.set_kernel(kind)
         best = 1e9
         for _ in range(4):
