@@ -59,8 +59,61 @@ def load_workloads():
     return m
 
 
+class NvmlSampler:
+    """SM clock, power and throttle reasons polled through NVML every 2 ms DURING the timed region (a timed region of a few
+    tens of milliseconds is over before an nvidia-smi process has printed its first line)."""
+
+    def __init__(self, index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.sm, self.pw, self.reasons, self.run = [], [], 0, False
+
+    def start(self):
+        self.run = True
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def stop(self):
+        nv = self.nv
+        self.run = False
+        self.t.join(timeout=1)
+        names = []
+        for bit, nm in ((getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                        (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                        (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                        (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")):
+            if self.reasons & int(bit):
+                names.append(nm)
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": mx, "power_w_max": max(self.pw) if self.pw else None,
+                "samples": len(self.sm), "reasons": sorted(names), "source": "NVML, 2 ms poll"}
+
+
+def make_sampler(index):
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (fallback when NVML's Python binding is missing)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -524,7 +577,8 @@ def run_batch64k(ctx, args):
                 w.wait()
             pending[j] = None
         S.solve_batch_device(B, state, coeffs, ylo, yhi, result[j], tx, ty, None, si[j][0], si[j][1])
-        if world > 1:   # the only exchange the path has: result / status / iters of every shard, after its solve
+        if world > 1 and not os.environ.get("MPC_BENCH_NO_GATHER"):   # the only exchange the path has: result / status / iters of every shard, after its solve
+            # (MPC_BENCH_NO_GATHER: development switch -- how much of a step is the exchange?  The line then says so.)
             pending[j] = [ctx.dist.all_gather_into_tensor(g_res[j].view(-1), result[j].view(-1), async_op=True),
                           ctx.dist.all_gather_into_tensor(g_si[j].view(-1), si[j].view(-1), async_op=True)]
 
@@ -535,7 +589,7 @@ def run_batch64k(ctx, args):
                     w.wait()
                 pending[j] = None
 
-    sampler = ClockSampler(smi_index(ctx.local_rank))
+    sampler = make_sampler(smi_index(ctx.local_rank))
     for k in range(args.warmup):
         ctx.flush.fill_(1)
         step(k)
@@ -586,7 +640,7 @@ def run_batch64k(ctx, args):
     log('timed region done: %.3f ms per step' % ms_per_step)
     # ---- strong scaling (the metric as written: 64K problems in total at 1/2/4/8 GPUs)
     strong = None
-    if world > 1:
+    if world > 1 and not args.only_timed:
         Bs_lo, Bs_hi = mpc.sharding.shard_bounds(B, rank, world)
         Bs = Bs_hi - Bs_lo
         b0 = mpc.workloads.batch_perturbed_states(B, 0, cfg.as_dict())
@@ -624,11 +678,11 @@ def run_batch64k(ctx, args):
         if rc != 0:
             raise SystemExit("mpc_solve_batch_host failed: %d %s" % (rc, L.mpc_last_error().decode()))
 
-    for _ in range(3):
+    for _ in range(0 if args.only_timed else 3):
         e2e_step()
     ctx.sync_all()
     e2e_t = []
-    for k in range(args.steps):
+    for k in range(0 if args.only_timed else args.steps):
         ctx.flush.fill_(k & 0xFF)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -636,8 +690,8 @@ def run_batch64k(ctx, args):
         e2e_t.append(time.perf_counter() - t0)
     ctx.sync_all()
     e2e_tot = ctx.max_over_ranks(sum(e2e_t))
-    e2e_value = B * world / (e2e_tot / args.steps)
-    assert np.allclose(h_res, res_last.cpu().numpy(), rtol=0, atol=0), "host-path result differs from device path"
+    e2e_value = B * world / (e2e_tot / args.steps) if e2e_t else None
+    assert args.only_timed or np.allclose(h_res, res_last.cpu().numpy(), rtol=0, atol=0), "host-path result differs from device path"
     h2d = 13 * 8 * B
     d2h = (9 + 2 * N) * 8 * B + 8 * B
 
@@ -695,6 +749,8 @@ def run_batch64k(ctx, args):
         "host": {"cpu": cpu_model(), "logical_cpus": os.cpu_count()},
         "status_ok_frac": float((st == 1).mean()), "status_hist": status_hist(st),
     }
+    if os.environ.get("MPC_BENCH_NO_GATHER"):
+        line["config"]["sharding"] = "DEVELOPMENT RUN WITHOUT THE GATHER (MPC_BENCH_NO_GATHER): not a bench line"
     if world > 1:
         # rank r solves the seed-r batch: the ranks' own solve times differ with their longest-running problem; the job
         # runs at the pace of the slowest
@@ -864,11 +920,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the one-GPU shares of the other BASELINE configs")
+    ap.add_argument("--only-timed", action="store_true", help="development: the timed region only (no strong-scaling, host-API, latency, extras or CPU legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if args.only_timed:
+        args.no_latency = args.no_extras = args.no_cpu_baseline = True
     if args.warmup < 3:
         args.warmup = 3
     ctx = Ctx()

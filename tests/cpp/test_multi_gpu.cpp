@@ -1,7 +1,8 @@
 // A C++ caller of include/mpc_b200.h on every GPU of the box, without Python: mpc_create_multi /
 // mpc_solve_batch_multi against one handle on device 0 (mpc_solve_batch_host).  Problems: the pose of the
 // reference's offline harness (src/test.cpp:45-50) moved and slowed at random, through mpc_run_prepare.
-// usage: test_multi_gpu config.json B n_handles   (handles are dealt round-robin over the visible devices)
+// usage: test_multi_gpu config.json B n_handles [pinned]   (handles are dealt round-robin over the visible devices; "pinned":
+// the caller's arrays are page-locked with cudaHostRegister, so the copies of the devices overlap)
 // prints "devices <d> handles <n> B <B> mismatches <k> ok_frac <f> ms_multi <t> ms_single <t>"
 #include <chrono>
 #include <cstdio>
@@ -41,6 +42,12 @@ int main(int argc, char **argv) {
   std::vector<double> r1, x1, y1, r2, x2, y2;
   std::vector<int> s1, i1, s2, i2;
   outputs(r1, x1, y1, s1, i1); outputs(r2, x2, y2, s2, i2);
+  if (argc > 4 && !strcmp(argv[4], "pinned")) {
+    auto pin = [](void *p, size_t bytes) { if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) { fprintf(stderr, "cudaHostRegister failed\n"); exit(10); } };
+    pin(state.data(), state.size() * 8); pin(coeffs.data(), coeffs.size() * 8); pin(ylo.data(), ylo.size() * 8); pin(yhi.data(), yhi.size() * 8);
+    pin(r1.data(), r1.size() * 8); pin(x1.data(), x1.size() * 8); pin(y1.data(), y1.size() * 8); pin(s1.data(), s1.size() * 4); pin(i1.data(), i1.size() * 4);
+    pin(r2.data(), r2.size() * 8); pin(x2.data(), x2.size() * 8); pin(y2.data(), y2.size() * 8); pin(s2.data(), s2.size() * 4); pin(i2.data(), i2.size() * 4);
+  }
   mpc_handle *h = nullptr;
   mpc_multi *m = nullptr;
   if (mpc_create(&cfg, 0, &h) != MPC_OK) { fprintf(stderr, "create failed: %s\n", mpc_last_error()); return 6; }

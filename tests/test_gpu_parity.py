@@ -40,7 +40,7 @@ def test_golden_testcpp_scenarios(solver):
             assert r["result"][8] == pytest.approx(step["result"][8], rel=REL_TOL)
             assert np.abs(r["traj_x"] - np.array(step["traj_x"])).max() < ABS_TOL
             assert np.abs(r["traj_y"] - np.array(step["traj_y"])).max() < ABS_TOL
-            assert abs(r["iters"] - step["iters"]) <= 2
+            assert 0 <= r["iters"] - step["iters"] <= 1      # the oracle's count, or one more (never fewer: DESIGN.md section 3)
             state = np.array(step["result"][:6])     # feed the golden state back (no drift accumulation)
 
 
@@ -62,7 +62,10 @@ def test_batch_vs_oracle(solver, mpc, po, stable_cd, seed, B):
     assert (c["status"] == 1).mean() > 0.99
     d = _assert_parity(g, c)
     assert np.median(d[:, :8].max(axis=1)) < 1e-9
-    assert (np.abs(g["iters"] - c["iters"]) <= 1).mean() > 0.97
+    # iteration counts: the oracle's on ~99 % of the problems, one more on the rest (the Riccati recursion's rounding residue in
+    # the multipliers meets Ipopt's 1e-8 test one iteration later), never fewer
+    di = g["iters"].astype(int) - c["iters"].astype(int)
+    assert (di == 0).mean() > 0.97 and di.min() >= 0 and di.max() <= 1, np.unique(di, return_counts=True)
 
 
 @pytest.mark.parametrize("name", ["fast", "no-latency"])

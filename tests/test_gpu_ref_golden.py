@@ -33,7 +33,7 @@ def test_testcpp_scenarios(gold, solver):
             _cmp(r["result"], step["result"])
             assert np.abs(r["traj_x"] - np.array(step["traj_x"])).max() < ABS_TOL
             assert np.abs(r["traj_y"] - np.array(step["traj_y"])).max() < ABS_TOL
-            assert abs(r["iters"] - step["iters"]) <= 2
+            assert 0 <= r["iters"] - step["iters"] <= 1      # the reference build's count, or one more
 
 
 def test_run_cases_all_configs(gold, mpc, refdata, kernel_kind):
