@@ -441,8 +441,8 @@ static int ensure_restart(mpc_handle *h, KParams &kp) {
 // The lane kernel and the launches that finish its tail, all on one stream with no host round trip:
 //   main launch            fresh problems from the work queue; parks by rule 1 (iterations) and rule 2 (sparse warp)
 //   resume launches        the parked problems, 32 to a warp; park by rule 2 into the other buffer
-//   final launch           N <= 32: the coop kernel (one problem per lane group, rows in shared memory);
-//                          longer horizons: the solo kernel (one problem per lane, rows in shared memory)
+//   final launch           the coop kernel (one problem per lane group, rows in shared memory, every branch of the
+//                          algorithm): the records that are left, then the problems handed over without a record
 #ifndef MPC_LANE_MINB
 #define MPC_LANE_MINB 1   // CTAs per SM the lane kernel is compiled for (__launch_bounds__(256, MINB)): experiments only
 #endif

@@ -1,14 +1,19 @@
-// mpc_lane_kernel.cuh -- the throughput kernel: one MPC problem per LANE.
+// mpc_lane_kernel.cuh -- the solver: one source, two mappings onto the machine.
 //
-// Same algorithm as mpc_kernel.cuh (the one-problem-per-warp latency kernel): the NLP of FG_eval
-// (/root/reference/src/control/MPC.cpp:50-154) with hand-derived derivatives, Ipopt's primal-dual
-// filter line-search iteration (Ipopt 3.12 defaults, MPC.cpp:160-179) and a stage-wise Riccati
-// factorisation of the block-banded KKT system instead of MUMPS (MPC.cpp:175).  What changes is
-// the mapping onto the machine.  The warp kernel keeps 17 of 32 lanes busy and spends most of its
-// issue slots on shuffles and shared-memory hand-offs (profiles/r01_v1_*); a batch of 64K problems
-// has far more problem-level parallelism than the chip has lanes, so here every lane owns one
-// problem, runs the whole recursion on its own registers and keeps the per-stage iterate in
-// thread-private (lane-interleaved, hence fully coalesced) memory.
+// The NLP of FG_eval (/root/reference/src/control/MPC.cpp:50-154) with hand-derived derivatives, Ipopt's primal-dual
+// filter line-search iteration (Ipopt 3.12 defaults, MPC.cpp:160-179) and a stage-wise Riccati factorisation of the
+// block-banded KKT system instead of MUMPS (MPC.cpp:175), written once as `struct Lane` and instantiated as
+//   mpc_lane_kernel         one problem per LANE, rows in thread-private memory: the throughput kernel (common path of the
+//                           algorithm; a problem that needs a rare branch is handed to the coop kernel)
+//   mpc_coop_kernel etc.    one problem per GROUP of 16/32 lanes, rows in shared memory: every branch of the algorithm
+//                           (restoration phase, watchdog, ...); single solves, small batches, closed loops, the tail of a batch
+// Same floating-point operations in the same order per problem either way, so a problem can move between them at any trip
+// boundary without changing a bit of its result.
+//
+// A batch of 64K problems has far more problem-level parallelism than the chip has lanes, so in the lane kernel every lane
+// owns one problem, runs the whole recursion on its own registers and keeps the per-stage iterate in thread-private
+// (lane-interleaved, hence fully coalesced) memory.  (The first version -- one problem per warp, one stage per lane -- kept
+// 17 of 32 lanes busy and spent most of its issue slots on shuffles: profiles/r01_v1_*.  Removed in round 2.)
 //
 // Lanes of a warp work on different problems with different iteration counts.  To keep them
 // converged the solver is written as a state machine whose trip has a fixed shape
@@ -19,8 +24,8 @@
 // ~0.002 %) simply take extra trips.
 //
 // Memory.  The per-stage state of a problem does not fit in registers, and the state of all resident
-// lanes must fit in the 126 MB L2 or every sweep streams it through HBM (profiles/r01_v2_*: 16.5 GB
-// of DRAM traffic per 64K batch).  So only what cannot be recomputed cheaply is stored -- iterate
+// lanes should fit in the 126 MB L2 or every sweep streams it through HBM (profiles/r01_v2_*: 16.5 GB
+// of DRAM traffic per 64K batch; today 8.8 GB).  So only what cannot be recomputed cheaply is stored -- iterate
 // (x, lambda, z), step, Riccati gains, and the trig/polynomial values and residuals at the iterate:
 // 56 doubles per stage.  Slack reciprocals, trial-point values and the new multipliers are recomputed
 // (the FP64 pipe has the headroom); the costate recursion that yields the new multipliers runs inside
@@ -79,7 +84,7 @@ enum { ST_S = 0,      // iterate: x, y, psi, v, cte, epsi
        ST_KG = 44,    // Riccati gains: K0[x,y,psi,v,dprev], K1[..], k0, k1
        ST_CS = 56,    // second-order-correction right-hand side (rare path only)
        ST_KEEP = 62,  // what is live at a trip boundary: the rows of the one-problem-per-lane kernels, and of a record
-       ST_ROW = 62,   // thread-private / solo rows (a multiple of 16 bytes that is not one of 64)
+       ST_ROW = 62,   // thread-private rows (a multiple of 16 bytes that is not one of 64)
        ST_TT = 62,    // coop kernel only: TG / CN at the trial point, handed from the evaluation to the acceptance sweep
        ST_CT = 70,    //   (the one-problem-per-lane kernels recompute them there instead: 14 doubles less per stage to stream)
        ST_LH = 76,    // coop kernel only: StageLin (10) + StageHess (18) of the stage, built one stage per lane
@@ -124,12 +129,10 @@ struct StageHess { double qxx, qyy, qpp, qpv, qvv, qve, qcc, qee, svd, rdd, raa,
 
 template <int NS, bool SH, bool PAR = SH>
 struct Lane {
-  // ---- per-stage data (thread-private memory): 70 doubles per stage are touched on the common path
-  // Per-stage data: one row of ST_ROW doubles per horizon stage (offsets ST_*).  SH = false: thread-private
-  // memory (one problem per lane; rows 16-byte aligned, so neighbouring doubles pair into 128-bit local
-  // accesses).  SH = true: a pointer into shared memory.  PAR = true (needs SH): one problem per lane GROUP, the
-  // sweeps that are parallel over the horizon run one stage per lane (mpc_coop_kernel); PAR = false with SH: one
-  // problem per lane as in the lane kernel, only the rows live in shared memory (mpc_solo_kernel).
+  // Per-stage data: one row of ST_ROW doubles per horizon stage (offsets ST_*; 56 of them are touched on the common
+  // path).  SH = false: thread-private memory (one problem per lane; rows 16-byte aligned, so neighbouring doubles pair
+  // into 128-bit local accesses).  SH = true: a pointer into shared memory.  PAR = true (needs SH): one problem per lane
+  // GROUP, the sweeps that are parallel over the horizon run one stage per lane (mpc_coop_kernel).
   enum { NS_GROUP = PAR ? (NS <= 16 ? 16 : 32) : 1, NPASS = (NS + NS_GROUP - 1) / NS_GROUP };   // stages per lane of a group
   // FULL: the kernel carries every branch of the algorithm.  The one-problem-per-lane kernel keeps to the branches
   // that occur on almost every problem (Newton step, inertia correction, second-order correction, backtracking); a
