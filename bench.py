@@ -558,15 +558,17 @@ def run_batch64k(ctx, args):
     N = cfg.N
     upT = lambda a: ctx.up(a.T if a.ndim == 2 else a)
     state, coeffs, ylo, yhi = upT(batch["state"]), upT(batch["coeffs"]), upT(batch["yaw_lo"]), upT(batch["yaw_hi"])
-    # outputs double-buffered: the gather of step k runs on NCCL's stream beside the solve of step k+1
+    # outputs double-buffered (--gather overlap: the gather of step k runs on NCCL's stream beside the solve of step k+1).
+    # result[9][B] and status/iters[2][B] share one buffer of 10 x B x 8 bytes, so the exchange is ONE collective.
     nbuf = 2 if world > 1 else 1
-    result = [torch.zeros(9, B, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+    packed = [torch.zeros(10, B, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+    result = [p[:9] for p in packed]
+    si = [p[9].view(torch.int32).view(2, B) for p in packed]       # status, iters
     tx = torch.zeros(N, B, dtype=torch.float64, device=dev)
     ty = torch.zeros(N, B, dtype=torch.float64, device=dev)
-    si = [torch.zeros(2, B, dtype=torch.int32, device=dev) for _ in range(nbuf)]       # status, iters
-    g_res = [torch.zeros(world, 9, B, dtype=torch.float64, device=dev) for _ in range(nbuf)] if world > 1 else None
-    g_si = [torch.zeros(world, 2, B, dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
+    g_out = [torch.zeros(world, 10, B, dtype=torch.float64, device=dev) for _ in range(nbuf)] if world > 1 else None
     pending = [None] * nbuf
+    serial_gather = args.gather == "serial"
     S = mpc.Solver(cfg, ctx.local_rank)
     log('batch64k: inputs resident, B=%d world=%d' % (B, world))
 
@@ -579,8 +581,12 @@ def run_batch64k(ctx, args):
         S.solve_batch_device(B, state, coeffs, ylo, yhi, result[j], tx, ty, None, si[j][0], si[j][1])
         if world > 1 and not os.environ.get("MPC_BENCH_NO_GATHER"):   # the only exchange the path has: result / status / iters of every shard, after its solve
             # (MPC_BENCH_NO_GATHER: development switch -- how much of a step is the exchange?  The line then says so.)
-            pending[j] = [ctx.dist.all_gather_into_tensor(g_res[j].view(-1), result[j].view(-1), async_op=True),
-                          ctx.dist.all_gather_into_tensor(g_si[j].view(-1), si[j].view(-1), async_op=True)]
+            pending[j] = [ctx.dist.all_gather_into_tensor(g_out[j].view(-1), packed[j].view(-1), async_op=True)]
+            if serial_gather:
+                # the solve's persistent grid wants every SM: the next solve starts after the gather kernels have left
+                for w in pending[j]:
+                    w.wait()
+                pending[j] = None
 
     def drain():
         for j in range(nbuf):
@@ -723,9 +729,10 @@ def run_batch64k(ctx, args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: batch 64K independent N=10 dt=0.1 solves from perturbed (cte, epsi, v), config-stable, seed=rank",
                    "batch_per_gpu": B, "N": N, "dt": cfg.dt, "l2": "flushed between timed steps (256 MiB write)",
-                   "sharding": ("independent batch shard per rank, no collective in the solve; per step one all_gather of result[9][B] and of "
-                                "status/iters[2][B], issued after the solve and overlapped with the next step's solve (double-buffered); "
-                                "ms_per_step = device time of the whole timed region (last gathers included, L2 flushes subtracted) / steps, max over ranks") if world > 1 else "single GPU"},
+                   "sharding": ("independent batch shard per rank, no collective in the solve; per step ONE all_gather of result[9][B] + "
+                                "status/iters[2][B] (one packed buffer) after the solve, " + ("finished before the next step's solve starts (the solve's persistent grid wants every SM; "
+                                "NCCL kernels resident beside it cost more than they hide: DESIGN.md section 7); " if serial_gather else "overlapped with the next step's solve (double-buffered); ") +
+                                "ms_per_step = device time of the whole timed region (gathers included, L2 flushes subtracted) / steps, max over ranks") if world > 1 else "single GPU"},
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak if fp64_peak else None, "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,
                      "peak_nominal": FP64_NOMINAL_TFLOPS, "traffic": traffic, "traffic_source": traffic_src,
@@ -920,6 +927,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the one-GPU shares of the other BASELINE configs")
+    ap.add_argument("--gather", default="serial", choices=["overlap", "serial"],
+                    help="multi-GPU: the gather of step k finishes before the solve of step k+1 starts (default), or runs beside it (see DESIGN.md section 7)")
     ap.add_argument("--only-timed", action="store_true", help="development: the timed region only (no strong-scaling, host-API, latency, extras or CPU legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
