@@ -157,3 +157,22 @@ def test_telemetry_message_framing(mpc):
     assert mpc.telemetry_parse('42["steer",{"a":1}]').kind == 0           # other events are ignored
     with pytest.raises(mpc.MpcError, match="MPC_EPARSE"):
         mpc.telemetry_parse('42["telemetry",{"x":1}]')
+
+
+def test_run_level_tables_are_validated(mpc, stable_cfg, refdata):
+    """counts of the run()-level tables outside the fixed-size arrays are argument errors at mpc_create, and
+    MPC::run's pre-processing refuses an empty speed-limit table (the reference calls .back() on an empty vector there,
+    Vehicle.cpp:66-79) instead of silently using a limit of 0."""
+    for field, val in [("n_yaw_changes", mpc.NTAB + 1), ("n_yaw_changes", -1), ("n_yaw_change_speeds", mpc.NTAB + 1), ("n_steers", mpc.NTAB + 1)]:
+        c = mpc.MpcConfig.from_buffer_copy(stable_cfg)
+        setattr(c, field, val)
+        with pytest.raises(mpc.MpcError, match="MPC_EINVAL"):
+            mpc.Solver(c, 0)
+    fx = refdata["test_cpp_fixtures"][0]
+    pose = (fx["x"], fx["y"], fx["psi"], fx["v"])
+    ok = mpc.run_prepare(stable_cfg, pose, fx["ptsx"], fx["ptsy"])
+    assert ok["aux"].target_speed > 0
+    c = mpc.MpcConfig.from_buffer_copy(stable_cfg)
+    c.n_yaw_change_speeds = 0
+    with pytest.raises(mpc.MpcError, match="MPC_EINVAL"):
+        mpc.run_prepare(c, pose, fx["ptsx"], fx["ptsy"])
