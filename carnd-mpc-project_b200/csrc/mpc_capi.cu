@@ -913,10 +913,10 @@ extern "C" int mpc_solve_batch_multi(mpc_multi *m, int B, const double *state, c
   const int N = m->h[0]->cfg.N;
   const size_t pitchB = (size_t)B * sizeof(double);
   // queue every shard: copies in, launches, copies out -- nothing here waits for a device
-  for (int g = 0; g < G; g++) {
+  auto queue_shard = [&](int g) -> int {
     const long long lo = (long long)B * g / G, hi = (long long)B * (g + 1) / G;
     const int Bs = (int)(hi - lo);
-    if (Bs == 0) continue;
+    if (Bs == 0) return MPC_OK;
     mpc_handle *h = m->h[g];
     CK(cudaSetDevice(h->device));
     int rc = ensure_staging(h, (size_t)Bs, N, weights != nullptr);
@@ -958,12 +958,18 @@ extern "C" int mpc_solve_batch_multi(mpc_multi *m, int B, const double *state, c
     if (full) CK(out2d(full, d_full, 8 * N - 2));
     if (status) CK(cudaMemcpyAsync(status + lo, d_status, (size_t)Bs * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (iters) CK(cudaMemcpyAsync(iters + lo, d_iters, (size_t)Bs * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return MPC_OK;
+  };
+  int first_error = MPC_OK, queued = 0;
+  for (; queued < G && first_error == MPC_OK; queued++) first_error = queue_shard(queued);
+  // wait for every device that has work queued -- also after an error, so that no copy into the caller's arrays is
+  // still in flight when this call returns
+  for (int g = 0; g < queued; g++) {
+    if (cudaSetDevice(m->h[g]->device) != cudaSuccess || cudaStreamSynchronize(m->h[g]->stream) != cudaSuccess) {
+      if (first_error == MPC_OK) { snprintf(g_err, sizeof(g_err), "device %d: %s", m->h[g]->device, cudaGetErrorString(cudaGetLastError())); first_error = MPC_ECUDA; }
+    }
   }
-  for (int g = 0; g < G; g++) {
-    CK(cudaSetDevice(m->h[g]->device));
-    CK(cudaStreamSynchronize(m->h[g]->stream));
-  }
-  return MPC_OK;
+  return first_error;
 }
 
 // One problem, host pointers.

@@ -2538,7 +2538,6 @@ struct Lane {
     const double orig_inf_pr_max = fmax(K_RESTO_KAPPA * infpr_R, fmin(P.tol, K_CONSTR_VIOL_TOL));
 #pragma unroll 1
     for (int i = g0; i < N; i += gstep) {
-      const bool hasu = i < N - 1;
       double *q = rs(i);
 #pragma unroll
       for (int k = 0; k < 6; k++) {
